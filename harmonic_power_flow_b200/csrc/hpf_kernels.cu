@@ -1,0 +1,1049 @@
+// sm_100a kernels of the harmonic power-flow solve path + their C ABI (include/hpf_b200.h).
+//
+//   kernel 1  ybus_kernel            Y(h) assembly                      HG:132-171
+//   kernel 2  mismatch_tile_kernel   fused power/current mismatch       HG:313-390
+//   kernel 3  jacobian_kernel        dense FP64 Jacobian -> HBM (TMA)   HG:401-473
+//   kernel 4  lu_solve_kernel        batched smem LU + solves           HG:476-479
+//   fused     solve_kernel           pf() + hpf() Newton loops          HG:244-275,511-560
+//
+// HG = "Harmonic Power Flow/hcne_generalized.py" of the reference.  No reference code is
+// used; the arithmetic is restated from the formulas (see hpf_device.cuh).
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/hpf_b200.h"
+#include "hpf_device.cuh"
+
+#define HPF_THREADS 256
+#define HPF_TILE 32          // scenarios per CTA in the tile kernels
+
+// =======================================================================================
+// kernel 1: Y(h).  One thread per (harmonic, bus row).  Sequential semantics of HG:147-170
+// are kept per row: later lines overwrite earlier ones, the diagonal is minus the
+// sequential row sum, bus shunt only for h != 1, pi-shunts matched with the off-by-one
+// index (1-based ID compared with the 0-based row).
+__global__ void ybus_kernel(int n, int H, int L, const int* __restrict__ harmonics,
+                            const int* __restrict__ from_id, const int* __restrict__ to_id,
+                            const double* __restrict__ R, const double* __restrict__ X,
+                            const double* __restrict__ G, const double* __restrict__ Bsh,
+                            const double* __restrict__ X_sh, double2* __restrict__ Y) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * H) return;
+    const int hi = idx / n, k = idx - hi * n;
+    const double h = (double)harmonics[hi];
+    double2* row = Y + ((size_t)hi * n + k) * n;
+    for (int j = 0; j < n; ++j) row[j] = make_double2(0.0, 0.0);
+    for (int l = 0; l < L; ++l) {
+        const int f = from_id[l] - 1, t = to_id[l] - 1;
+        if (f != k && t != k) continue;
+        // -1 / (R + j X h): Smith's algorithm like numpy's complex division
+        const double br = R[l], bi = X[l] * h;
+        double2 y;
+        if (fabs(br) >= fabs(bi)) {
+            if (br == 0.0 && bi == 0.0) {
+                y = make_double2(1.0 / fabs(br), 0.0 / fabs(bi));
+            } else {
+                const double rat = bi / br, scl = 1.0 / __dadd_rn(br, __dmul_rn(bi, rat));
+                y = make_double2(scl, -rat * scl);
+            }
+        } else {
+            const double rat = br / bi, scl = 1.0 / __dadd_rn(bi, __dmul_rn(br, rat));
+            y = make_double2(rat * scl, -scl);
+        }
+        y = make_double2(-y.x, -y.y);
+        if (f == k) row[t] = y;
+        if (t == k) row[f] = y;
+    }
+    double2 s = make_double2(0.0, 0.0);
+    for (int j = 0; j < n; ++j) s = cadd(s, row[j]);
+    double2 d = make_double2(-s.x, -s.y);
+    if (X_sh[k] != 0.0 && harmonics[hi] != 1) {
+        // 1 / (j X_sh h) = -j / (X_sh h)
+        d.y += -1.0 / (X_sh[k] * h);
+    }
+    for (int l = 0; l < L; ++l) {
+        if (from_id[l] == k || to_id[l] == k) {
+            d.x += G[l] / 2.0;
+            d.y += (h * Bsh[l]) / 2.0;
+        }
+    }
+    row[k] = d;
+}
+
+// =======================================================================================
+// Shared-memory carve-up of one scenario (fused and per-CTA kernels).
+struct ScnSmem {
+    double* A;                                 // ld * (N + 1), column-major, odd ld
+    double *Vm, *Va, *Vre, *Vim, *Ere, *Eim;   // nH each
+    double2 *I1, *Iinj, *IN;                   // n, q*H, q*H
+    double *P, *Q;                             // n each
+    double* rinv;                              // N
+    double* red;                               // 64
+    int* flag;                                 // 8 ints
+};
+
+__host__ __device__ inline int odd_ld(int N) { return N | 1; }
+
+__host__ __device__ inline size_t scn_smem_bytes(int n, int H, int q, int N, bool with_matrix) {
+    const size_t nH = (size_t)n * H;
+    size_t d = 0;
+    if (with_matrix) d += (size_t)odd_ld(N) * (N + 1);
+    d += 6 * nH + 2 * n + 4 * (size_t)q * H + 2 * n + N + 64 + 4;
+    return d * sizeof(double) + 16;
+}
+
+__device__ __forceinline__ ScnSmem carve(double* base, const DevNet& net, bool with_matrix) {
+    ScnSmem s;
+    double* p = base;
+    const int nH = net.nH, qH = net.q * net.H;
+    s.A = p;
+    if (with_matrix) p += (size_t)odd_ld(net.N) * (net.N + 1);
+    if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) p += 1;   // double2 alignment
+    s.I1 = reinterpret_cast<double2*>(p);   p += 2 * net.n;
+    s.Iinj = reinterpret_cast<double2*>(p); p += 2 * qH;
+    s.IN = reinterpret_cast<double2*>(p);   p += 2 * qH;
+    s.Vm = p;  p += nH;
+    s.Va = p;  p += nH;
+    s.Vre = p; p += nH;
+    s.Vim = p; p += nH;
+    s.Ere = p; p += nH;
+    s.Eim = p; p += nH;
+    s.P = p;   p += net.n;
+    s.Q = p;   p += net.n;
+    s.rinv = p; p += net.N;
+    s.red = p; p += 64;
+    s.flag = reinterpret_cast<int*>(p);
+    return s;
+}
+
+// ---- per-CTA phases (VS = 1) -----------------------------------------------------------
+__device__ __forceinline__ void cta_phasors(const ScnSmem& s, int lo, int hi, bool abs_norm) {
+    for (int t = lo + threadIdx.x; t < hi; t += blockDim.x)
+        phasor_one<1>(t, 0, s.Vm, s.Va, s.Vre, s.Vim, s.Ere, s.Eim, abs_norm);
+    __syncthreads();
+}
+
+// I1 = Y1 V1 and (harmonic stage) the Norton injections.
+__device__ __forceinline__ void cta_currents(const DevNet& net, const ScnSmem& s, bool with_norton) {
+    const int qH = with_norton ? net.q * net.H : 0;
+    for (int t = threadIdx.x; t < net.n + qH; t += blockDim.x) {
+        if (t < net.n) {
+            s.I1[t] = ydotv<1>(net, 0, t, 0, s.Vre, s.Vim);
+        } else {
+            const int u = t - net.n, k = u / net.H, h = u - k * net.H;
+            s.Iinj[u] = norton_injection<1>(net, k, h, 0, s.Vre, s.Vim, s.IN[u]);
+        }
+    }
+    __syncthreads();
+}
+
+// Harmonic mismatch into rhs[] (N doubles); returns ||f||_inf (NaN-propagating) to all threads.
+__device__ __forceinline__ double cta_harmonic_mismatch(const DevNet& net, const ScnSmem& s, double* rhs) {
+    cta_phasors(s, 0, net.nH, false);
+    cta_currents(net, s, true);
+    double mx = 0.0;
+    for (int e = threadIdx.x; e < net.nH - 1; e += blockDim.x) {
+        const double2 f = harmonic_mismatch_entry<1>(net, e, 0, s.Vre, s.Vim, s.I1, s.Iinj, s.P, s.Q);
+        rhs[h_row_re(net, e)] = f.x;
+        double a = fabs(f.x);
+        if (e >= net.c - 1) {
+            rhs[h_row_im(net, e)] = f.y;
+            const double b = fabs(f.y);
+            a = (b != b || b > a) ? b : a;
+        }
+        mx = (a != a || a > mx) ? a : mx;
+    }
+    return block_max_nan(mx, s.red);
+}
+
+// Fundamental mismatch (HG:195-202) into rhs[] (Nf doubles).
+__device__ __forceinline__ double cta_fund_mismatch(const DevNet& net, const ScnSmem& s, double* rhs) {
+    cta_phasors(s, 0, net.n, true);
+    cta_currents(net, s, false);
+    const int n = net.n, c = net.c;
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 v = make_double2(s.Vre[i], s.Vim[i]);
+        const double2 sl = cmul(v, cconj(s.I1[i]));
+        const double fr = sl.x + s.P[i], fi = sl.y + s.Q[i];
+        double a = 0.0;
+        if (i >= 1) { rhs[i - 1] = fr; a = fabs(fr); }
+        if (i >= c) {
+            rhs[(n - 1) + i - c] = fi;
+            const double b = fabs(fi);
+            a = (b != b || b > a) ? b : a;
+        }
+        mx = (a != a || a > mx) ? a : mx;
+    }
+    return block_max_nan(mx, s.red);
+}
+
+// Zero `cnt` doubles at A (cnt even or odd; A 8-byte aligned).
+__device__ __forceinline__ void cta_zero(double* A, size_t cnt) {
+    for (size_t t = threadIdx.x; t < cnt; t += blockDim.x) A[t] = 0.0;
+}
+
+// Harmonic Jacobian into a dense matrix addressed A[row*rs + col*cs] (pre-zeroed).
+__device__ __forceinline__ void cta_harmonic_jacobian(const DevNet& net, const ScnSmem& s, double* A,
+                                                      size_t rs, size_t cs) {
+    const int slots = net.n + (net.coupled ? net.H : 0);
+    const int items = (net.nH - 1) * slots;
+    auto put = [=](int row, int col, double v) { A[row * rs + col * cs] = v; };
+    for (int t = threadIdx.x; t < items; t += blockDim.x) {
+        const int e = t / slots, slot = t - e * slots;
+        harmonic_jacobian_item(net, e, slot, s.Vre, s.Vim, s.Ere, s.Eim, s.I1, put);
+    }
+}
+
+__device__ __forceinline__ void cta_fund_jacobian(const DevNet& net, const ScnSmem& s, double* A,
+                                                  size_t rs, size_t cs) {
+    const int n = net.n;
+    auto put = [=](int row, int col, double v) { A[row * rs + col * cs] = v; };
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+        const int i = t / n, j = t - i * n;
+        fund_jacobian_item(net, i, j, s.Vre, s.Vim, s.Ere, s.Eim, s.I1, put);
+    }
+}
+
+// =======================================================================================
+// Fused solve kernel: persistent CTAs pull scenarios from a global work counter
+// (iteration counts differ between scenarios, 8..34+, so static striding would idle SMs).
+// mode 0: fundamental + harmonic (hpf);  mode 1: fundamental only (pf).
+struct SolveArgs {
+    int B, mode, flags;
+    const double *P, *Q;
+    const double2* I_N;
+    double thresh_f, thresh_h;
+    int max_f, max_h;
+    double *V_m, *V_a;
+    double2* I_inj;
+    int *n_iter_f, *n_iter_h, *status;
+    double *err_h, *err_f, *hist_f, *hist_h;
+    int* work_counter;
+    double* workspace;     // GMEM variant: gridDim.x * ld * (N + 1) doubles
+};
+
+#define HPF_THREADS_GMEM 1024
+template <bool GMEM>
+__global__ void __launch_bounds__(GMEM ? HPF_THREADS_GMEM : HPF_THREADS)
+solve_kernel(const DevNet net, const SolveArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    ScnSmem s = carve(smem, net, !GMEM);
+    if (GMEM) s.A = a.workspace + (size_t)blockIdx.x * odd_ld(net.N) * (net.N + 1);
+    const int tid = threadIdx.x;
+    const int n = net.n, c = net.c, nH = net.nH, N = net.N, Nf = net.Nf, H = net.H, q = net.q;
+    const int ld = odd_ld(N);
+    const size_t B = (size_t)a.B;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s.flag[1] = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int b = s.flag[1];
+        if (b >= a.B) break;
+
+        // ---- load scenario, flat start (HG:174-184) ----
+        for (int t = tid; t < n; t += blockDim.x) {
+            s.P[t] = a.P[t * B + b];
+            s.Q[t] = a.Q[t * B + b];
+        }
+        if (a.mode == 0)
+            for (int t = tid; t < q * H; t += blockDim.x) s.IN[t] = a.I_N[t * B + b];
+        for (int t = tid; t < nH; t += blockDim.x) {
+            s.Vm[t] = (t < n) ? 1.0 : 0.1;
+            s.Va[t] = 0.0;
+        }
+        __syncthreads();
+
+        int status = HPF_ST_CONVERGED;
+        // ---- fundamental Newton-Raphson (HG:244-275) ----
+        double* rhs_f = s.A + (size_t)Nf * ld;
+        double err = cta_fund_mismatch(net, s, rhs_f);
+        int it_f = 0;
+        if (a.hist_f && tid == 0) a.hist_f[b] = err;
+        while (err > a.thresh_f && it_f < a.max_f) {
+            cta_zero(s.A, (size_t)ld * Nf);
+            __syncthreads();
+            cta_fund_jacobian(net, s, s.A, 1, ld);
+            const int info = GMEM ? lu_solve_any(s.A, Nf, ld, s.rinv, s.flag, s.red)
+                                  : lu_solve_smem(s.A, Nf, ld, s.rinv, s.flag);
+            if (info) status = HPF_ST_SINGULAR;
+            for (int t = tid; t < Nf; t += blockDim.x) {       // HG:226-235
+                const double dx = rhs_f[t];
+                if (t < n - 1) s.Va[t + 1] -= dx;
+                else s.Vm[c + (t - (n - 1))] -= dx;
+            }
+            __syncthreads();
+            err = cta_fund_mismatch(net, s, rhs_f);
+            ++it_f;
+            if (a.hist_f && tid == 0) a.hist_f[(size_t)it_f * B + b] = err;
+        }
+        if (a.hist_f)
+            for (int t = it_f + 1 + tid; t <= a.max_f; t += blockDim.x) a.hist_f[(size_t)t * B + b] = CUDART_NAN;
+        if (it_f >= a.max_f) status = HPF_ST_MAXITER;
+        if (err != err) status = HPF_ST_NONFINITE;
+        if (tid == 0) {
+            a.n_iter_f[b] = it_f;
+            if (a.err_f) a.err_f[b] = err;
+        }
+
+        if (a.mode == 1) {
+            for (int t = tid; t < nH; t += blockDim.x) {
+                a.V_m[t * B + b] = s.Vm[t];
+                a.V_a[t * B + b] = s.Va[t];
+            }
+            continue;
+        }
+
+        // ---- harmonic Newton-Raphson (HG:531-542) ----
+        double* rhs = s.A + (size_t)N * ld;
+        double err_h = cta_harmonic_mismatch(net, s, rhs);
+        int it_h = 0;
+        if (a.hist_h && tid == 0) a.hist_h[b] = err_h;
+        while (err_h > a.thresh_h && it_h < a.max_h) {
+            cta_zero(s.A, (size_t)ld * N);
+            __syncthreads();
+            cta_harmonic_jacobian(net, s, s.A, 1, ld);
+            const int info = GMEM ? lu_solve_any(s.A, N, ld, s.rinv, s.flag, s.red)
+                                  : lu_solve_smem(s.A, N, ld, s.rinv, s.flag);
+            if (info && status == HPF_ST_CONVERGED) status = HPF_ST_SINGULAR;
+            for (int t = tid; t < N; t += blockDim.x) {        // HG:476-485
+                const double dx = rhs[t];
+                if (t < nH - 1) s.Va[t + 1] -= dx;
+                else s.Vm[c + (t - (nH - 1))] -= dx;
+            }
+            __syncthreads();
+            err_h = cta_harmonic_mismatch(net, s, rhs);
+            ++it_h;
+            if (a.hist_h && tid == 0) a.hist_h[(size_t)it_h * B + b] = err_h;
+        }
+        if (a.hist_h)
+            for (int t = it_h + 1 + tid; t <= a.max_h; t += blockDim.x) a.hist_h[(size_t)t * B + b] = CUDART_NAN;
+        if (it_h >= a.max_h && status == HPF_ST_CONVERGED) status = HPF_ST_MAXITER;
+        if (err_h != err_h) status = HPF_ST_NONFINITE;
+
+        // ---- post-processing (HG:547-549) and result write-out ----
+        for (int t = tid; t < nH; t += blockDim.x) {
+            double vm = s.Vm[t], va = s.Va[t], r = va;
+            if (!(a.flags & HPF_SOLVE_RAW)) {
+                if (vm < 0.0) va += CUDART_PI;
+                const double twopi = 2.0 * CUDART_PI;
+                r = fmod(va, twopi);                 // numpy's % : result takes the divisor's sign
+                if (r != 0.0) { if (r < 0.0) r += twopi; } else r = 0.0;
+                if (vm < 0.0) vm = -vm;
+            }
+            if (!(vm == vm) || !(r == r) || fabs(vm) == CUDART_INF) status = HPF_ST_NONFINITE;
+            a.V_m[t * B + b] = vm;
+            a.V_a[t * B + b] = r;
+        }
+        if (a.I_inj)
+            for (int t = tid; t < q * H; t += blockDim.x) a.I_inj[t * B + b] = s.Iinj[t];
+        // status may differ between threads only through the non-finite check above
+        const int st_any = __syncthreads_or(status == HPF_ST_NONFINITE);
+        if (tid == 0) {
+            a.n_iter_h[b] = it_h;
+            a.err_h[b] = err_h;
+            a.status[b] = st_any ? HPF_ST_NONFINITE : status;
+        }
+    }
+}
+
+// =======================================================================================
+// kernel 2 (standalone): 32 scenarios per CTA, lane = scenario, warps stride over rows.
+// HBM traffic is batch-innermost and fully coalesced: every global access of a warp is one
+// contiguous 256-byte (double) or 512-byte (double2) segment.
+struct MismatchArgs {
+    int B;
+    const double *V_m, *V_a, *P, *Q;
+    const double2* I_N;
+    double *f, *err;
+    double2* I_inj;
+};
+
+__host__ __device__ inline size_t tile_smem_bytes(int n, int H, int q) {
+    const size_t nH = (size_t)n * H;
+    // Vre, Vim [nH][32]; I1 [n][32] c128; Iinj [qH][32] c128; red [8][32]
+    return (2 * nH + 2 * n + 2 * (size_t)q * H + 8) * HPF_TILE * sizeof(double) + 16;
+}
+
+__global__ void __launch_bounds__(HPF_THREADS)
+mismatch_tile_kernel(const DevNet net, const MismatchArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int n = net.n, H = net.H, nH = net.nH, q = net.q, c = net.c, m = net.m;
+    const size_t B = (size_t)a.B;
+    double2* I1 = reinterpret_cast<double2*>(smem);
+    double2* Iinj = I1 + (size_t)n * HPF_TILE;
+    double* Vre = reinterpret_cast<double*>(Iinj + (size_t)q * H * HPF_TILE);
+    double* Vim = Vre + (size_t)nH * HPF_TILE;
+    double* red = Vim + (size_t)nH * HPF_TILE;
+
+    for (size_t tile = blockIdx.x; tile * HPF_TILE < B; tile += gridDim.x) {
+        const size_t b = tile * HPF_TILE + lane;
+        const bool ok = b < B;
+        const size_t bb = ok ? b : B - 1;            // clamp: compute, do not store
+        __syncthreads();
+        // phase A: phasors
+        for (int t = warp; t < nH; t += nw) {
+            const double vm = a.V_m[t * B + bb];
+            double sn, cs;
+            sincos(a.V_a[t * B + bb], &sn, &cs);
+            Vre[t * HPF_TILE + lane] = vm * cs;
+            Vim[t * HPF_TILE + lane] = vm * sn;
+        }
+        __syncthreads();
+        // phase B: I1 = Y1 V1 and Norton injections
+        for (int t = warp; t < n + q * H; t += nw) {
+            if (t < n) {
+                I1[t * HPF_TILE + lane] = ydotv<HPF_TILE>(net, 0, t, lane, Vre, Vim);
+            } else {
+                const int u = t - n, k = u / H, h = u - k * H;
+                const double2 in = a.I_N[u * B + bb];
+                const double2 inj = norton_injection<HPF_TILE>(net, k, h, lane, Vre, Vim, in);
+                Iinj[u * HPF_TILE + lane] = inj;
+                if (a.I_inj && ok) a.I_inj[u * B + b] = inj;
+            }
+        }
+        __syncthreads();
+        // phase C: mismatch rows
+        double mx = 0.0;
+        for (int e = warp; e < nH - 1; e += nw) {
+            double2 f;
+            const int s = e + 1;
+            if (s < m) {
+                const double2 v = make_double2(Vre[s * HPF_TILE + lane], Vim[s * HPF_TILE + lane]);
+                const double2 sl = cmul(v, cconj(I1[s * HPF_TILE + lane]));
+                f = make_double2(a.P[s * B + bb] + sl.x, a.Q[s * B + bb] + sl.y);
+            } else {
+                f = harmonic_mismatch_entry<HPF_TILE>(net, e, lane, Vre, Vim, I1, Iinj, nullptr, nullptr);
+            }
+            double v1 = fabs(f.x);
+            if (ok) a.f[(size_t)h_row_re(net, e) * B + b] = f.x;
+            if (e >= c - 1) {
+                if (ok) a.f[(size_t)h_row_im(net, e) * B + b] = f.y;
+                const double v2 = fabs(f.y);
+                v1 = (v2 != v2 || v2 > v1) ? v2 : v1;
+            }
+            mx = (v1 != v1 || v1 > mx) ? v1 : mx;
+        }
+        red[warp * HPF_TILE + lane] = mx;
+        __syncthreads();
+        if (warp == 0) {
+            double r = 0.0;
+            bool bad = false;
+            for (int w = 0; w < nw; ++w) {
+                const double v = red[w * HPF_TILE + lane];
+                bad |= (v != v);
+                r = fmax(r, v);
+            }
+            if (ok) a.err[b] = bad ? CUDART_NAN : r;
+        }
+    }
+}
+
+// Fallback for networks whose 32-scenario tile does not fit in shared memory (e.g. net1 with
+// 26 harmonics): one scenario per CTA, same arithmetic (VS = 1), strided HBM access.
+__global__ void __launch_bounds__(HPF_THREADS)
+mismatch_cta_kernel(const DevNet net, const MismatchArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const ScnSmem s = carve(smem, net, false);
+    double* rhs = s.rinv;                        // N doubles, unused otherwise in this kernel
+    const int nH = net.nH, qH = net.q * net.H;
+    const size_t B = (size_t)a.B;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < nH; t += blockDim.x) {
+            s.Vm[t] = a.V_m[t * B + b];
+            s.Va[t] = a.V_a[t * B + b];
+        }
+        for (int t = threadIdx.x; t < net.n; t += blockDim.x) {
+            s.P[t] = a.P[t * B + b];
+            s.Q[t] = a.Q[t * B + b];
+        }
+        for (int t = threadIdx.x; t < qH; t += blockDim.x) s.IN[t] = a.I_N[t * B + b];
+        __syncthreads();
+        const double err = cta_harmonic_mismatch(net, s, rhs);
+        for (int t = threadIdx.x; t < net.N; t += blockDim.x) a.f[t * B + b] = rhs[t];
+        if (a.I_inj)
+            for (int t = threadIdx.x; t < qH; t += blockDim.x) a.I_inj[t * B + b] = s.Iinj[t];
+        if (threadIdx.x == 0) a.err[b] = err;
+    }
+}
+
+// =======================================================================================
+// kernel 3 (standalone): one scenario per CTA iteration; the N x N matrix is assembled
+// row-major in shared memory and leaves the SM as ONE bulk asynchronous copy
+// (cp.async.bulk shared -> global, the TMA engine), so the store stream is full 128-byte
+// lines without occupying LSU issue slots.
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                 :: "l"(gdst), "r"(sa), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
+struct JacobianArgs {
+    int B;
+    const double *V_m, *V_a;
+    double* J;
+    long long stride;     // doubles between scenarios (even, >= N*N)
+};
+
+__host__ __device__ inline size_t jac_smem_bytes(int n, int H, int q, int N, long long stride) {
+    return (size_t)stride * sizeof(double) + scn_smem_bytes(n, H, q, N, false) + 16;
+}
+
+__global__ void __launch_bounds__(HPF_THREADS)
+jacobian_kernel(const DevNet net, const JacobianArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    double* Jt = smem;                                   // stride doubles, 16-byte aligned
+    const ScnSmem s = carve(smem + a.stride, net, false);
+    const int nH = net.nH, N = net.N;
+    const size_t B = (size_t)a.B;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        for (int t = threadIdx.x; t < nH; t += blockDim.x) {
+            s.Vm[t] = a.V_m[t * B + b];
+            s.Va[t] = a.V_a[t * B + b];
+        }
+        if (threadIdx.x == 0) bulk_store_wait_read();   // previous matrix has left smem
+        __syncthreads();
+        cta_zero(Jt, (size_t)a.stride);
+        cta_phasors(s, 0, nH, false);                    // (contains a barrier)
+        cta_currents(net, s, false);
+        cta_harmonic_jacobian(net, s, Jt, (size_t)N, 1);
+        fence_proxy_async_smem();                        // generic-proxy writes -> async proxy
+        __syncthreads();
+        if (threadIdx.x == 0)
+            bulk_store_s2g(a.J + (size_t)b * a.stride, Jt, (uint32_t)(a.stride * sizeof(double)));
+    }
+    if (threadIdx.x == 0) bulk_store_wait_read();
+}
+
+// Fallback when the N x N matrix does not fit in shared memory: zero-fill and scatter
+// straight into global memory (the CTA's own L2-resident lines).
+__global__ void __launch_bounds__(HPF_THREADS)
+jacobian_gmem_kernel(const DevNet net, const JacobianArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const ScnSmem s = carve(smem, net, false);
+    const int nH = net.nH, N = net.N;
+    const size_t B = (size_t)a.B;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < nH; t += blockDim.x) {
+            s.Vm[t] = a.V_m[t * B + b];
+            s.Va[t] = a.V_a[t * B + b];
+        }
+        double* Jb = a.J + (size_t)b * a.stride;
+        cta_zero(Jb, (size_t)a.stride);
+        __syncthreads();
+        cta_phasors(s, 0, nH, false);
+        cta_currents(net, s, false);
+        cta_harmonic_jacobian(net, s, Jb, (size_t)N, 1);
+    }
+}
+
+// =======================================================================================
+// kernel 4 (standalone): J [B, stride] row-major from HBM -> padded column-major smem,
+// LU + solves, dx [N, B].
+struct LuArgs {
+    int B;
+    const double *J, *f;
+    double* dx;
+    int* info;
+    long long stride;
+    double* workspace;
+};
+
+template <bool GMEM>
+__global__ void __launch_bounds__(GMEM ? HPF_THREADS_GMEM : HPF_THREADS)
+lu_solve_kernel(const DevNet net, const LuArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    ScnSmem s = carve(smem, net, !GMEM);
+    if (GMEM) s.A = a.workspace + (size_t)blockIdx.x * odd_ld(net.N) * (net.N + 1);
+    const int N = net.N, ld = odd_ld(N);
+    const size_t B = (size_t)a.B;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        __syncthreads();
+        const double* Jb = a.J + (size_t)b * a.stride;
+        for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
+            const int r = t / N, cidx = t - r * N;
+            s.A[r + (size_t)cidx * ld] = Jb[t];
+        }
+        double* rhs = s.A + (size_t)N * ld;
+        for (int t = threadIdx.x; t < N; t += blockDim.x) rhs[t] = a.f[t * B + b];
+        const int info = GMEM ? lu_solve_any(s.A, N, ld, s.rinv, s.flag, s.red)
+                              : lu_solve_smem(s.A, N, ld, s.rinv, s.flag);
+        for (int t = threadIdx.x; t < N; t += blockDim.x) a.dx[t * B + b] = rhs[t];
+        if (threadIdx.x == 0) a.info[b] = info;
+    }
+}
+
+// =======================================================================================
+// THD (HG:563-572): one thread per (bus, scenario); sums run sequentially over the
+// harmonics like Python's sum(); coalesced across the batch.
+__global__ void thd_kernel(int n, int H, const int* __restrict__ harmonics, int B,
+                           const double* __restrict__ V_m, double* __restrict__ thd) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nB = (size_t)n * B;
+    if (idx >= nB) return;
+    double sh = 0.0, sa = 0.0;
+    for (int h = 0; h < H; ++h) {
+        const double v = V_m[(size_t)h * nB + idx];
+        const double v2 = v * v;
+        if (harmonics[h] >= 3) sh = sh + v2;
+        sa = sa + v2;
+    }
+    const double r = sqrt(sh);
+    thd[idx] = r / V_m[idx];
+    thd[nB + idx] = r / sqrt(sa);
+}
+
+// =======================================================================================
+// Host side: handle + C ABI
+struct hpf_handle {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    int n = 0, m = 0, c = 0, H = 0, q = 0, L = 0, n_dev = 0, coupled = 0;
+    bool have_net = false, have_dev = false, have_Y = false;
+    int *d_harm = nullptr, *d_from = nullptr, *d_to = nullptr, *d_devof = nullptr;
+    double *d_R = nullptr, *d_X = nullptr, *d_G = nullptr, *d_B = nullptr, *d_Xsh = nullptr;
+    double2 *d_Y = nullptr, *d_YN = nullptr;
+    int* d_counter = nullptr;
+    double* d_work = nullptr;
+    size_t work_doubles = 0;
+    long long launches = 0;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(hpf_t* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(h, HPF_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+static DevNet devnet(const hpf_t* h) {
+    DevNet d;
+    d.n = h->n; d.m = h->m; d.c = h->c; d.H = h->H; d.q = h->q;
+    d.nH = h->n * h->H;
+    d.N = 2 * d.nH - 1 - h->c;
+    d.Nf = 2 * h->n - 1 - h->c;
+    d.coupled = h->coupled;
+    d.Y = h->d_Y; d.YN = h->d_YN; d.dev_of_nl = h->d_devof;
+    return d;
+}
+
+template <class T>
+static cudaError_t upload(T** dst, const T* src, size_t count) {
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    cudaError_t e = cudaMalloc((void**)dst, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (src && count) e = cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+static int ready(hpf_t* h, const char* who, bool need_dev) {
+    if (!h) return HPF_E_INVALID;
+    if (!h->have_net || !h->have_Y)
+        return fail(h, HPF_E_INVALID, std::string(who) + ": call hpf_set_network and hpf_build_Y first");
+    if (need_dev && h->q > 0 && !h->have_dev)
+        return fail(h, HPF_E_INVALID, std::string(who) + ": call hpf_set_devices first");
+    return HPF_OK;
+}
+
+// Does the dense system fit the shared-memory LU (matrix + state in smem, N <= 32*MAXCHUNK)?
+static bool fits_smem_lu(const hpf_t* h, const DevNet& net) {
+    return net.N <= 32 * HPF_LU_MAXCHUNK &&
+           scn_smem_bytes(net.n, net.H, net.q, net.N, true) <= (size_t)h->smem_optin;
+}
+
+static int ensure_workspace(hpf_t* h, size_t doubles) {
+    if (doubles <= h->work_doubles) return HPF_OK;
+    if (h->d_work) { CK(cudaDeviceSynchronize()); cudaFree(h->d_work); h->d_work = nullptr; h->work_doubles = 0; }
+    CK(cudaMalloc((void**)&h->d_work, doubles * sizeof(double)));
+    h->work_doubles = doubles;
+    return HPF_OK;
+}
+
+template <class K>
+static int prep_kernel(hpf_t* h, K kernel, size_t smem, const char* who, int* ctas_per_sm,
+                       int threads = HPF_THREADS) {
+    if (smem > (size_t)h->smem_optin)
+        return fail(h, HPF_E_UNSUPPORTED,
+                    std::string(who) + ": system too large for the shared-memory path (needs " +
+                        std::to_string(smem) + " B of shared memory per CTA, device offers " +
+                        std::to_string(h->smem_optin) + ")");
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    if (occ < 1) return fail(h, HPF_E_UNSUPPORTED, std::string(who) + ": kernel does not fit on an SM");
+    *ctas_per_sm = occ;
+    return HPF_OK;
+}
+
+static int solve_common(hpf_t* h, int mode, int B, const double* P, const double* Q, const double* I_N,
+                        double thresh_f, int max_f, double thresh_h, int max_h, int flags, double* V_m,
+                        double* V_a, double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h,
+                        double* err_f, int* status, double* hist_f, double* hist_h, void* stream) {
+    const char* who = mode ? "hpf_fund_solve" : "hpf_solve";
+    int rc = ready(h, who, mode == 0);
+    if (rc) return rc;
+    if (B < 0) return fail(h, HPF_E_INVALID, std::string(who) + ": B < 0");
+    if (B == 0) return HPF_OK;
+    if (!P || !Q || !V_m || !V_a || !n_iter_f ||
+        (mode == 0 && (!n_iter_h || !err_h || !status || (h->q > 0 && !I_N))))
+        return fail(h, HPF_E_INVALID, std::string(who) + ": NULL buffer");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DevNet net = devnet(h);
+    if (mode == 1) net.N = net.Nf;      // fundamental only: size the matrix for Nf
+    const bool gm = !fits_smem_lu(h, net);
+    const size_t smem = scn_smem_bytes(net.n, net.H, net.q, net.N, !gm);
+    int occ = 0;
+    rc = gm ? prep_kernel(h, solve_kernel<true>, smem, who, &occ, HPF_THREADS_GMEM)
+            : prep_kernel(h, solve_kernel<false>, smem, who, &occ);
+    if (rc) return rc;
+    SolveArgs a;
+    a.B = B; a.mode = mode; a.flags = flags; a.P = P; a.Q = Q; a.I_N = (const double2*)I_N;
+    a.hist_f = hist_f; a.hist_h = hist_h;
+    a.thresh_f = thresh_f; a.thresh_h = thresh_h; a.max_f = max_f; a.max_h = max_h;
+    a.V_m = V_m; a.V_a = V_a; a.I_inj = (double2*)I_inj;
+    a.n_iter_f = n_iter_f; a.n_iter_h = n_iter_h; a.status = status; a.err_h = err_h; a.err_f = err_f;
+    a.work_counter = h->d_counter;
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
+    long long grid = (long long)occ * h->sm_count;
+    if (grid > B) grid = B;
+    a.workspace = nullptr;
+    if (gm) {
+        rc = ensure_workspace(h, (size_t)grid * odd_ld(net.N) * (net.N + 1));
+        if (rc) return rc;
+        a.workspace = h->d_work;
+        solve_kernel<true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, a);
+    } else {
+        solve_kernel<false><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, a);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+extern "C" {
+
+int hpf_abi_version(void) { return HPF_ABI_VERSION; }
+
+const char* hpf_last_error(const hpf_t* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int hpf_create(hpf_t** out, int device) {
+    hpf_t* h = nullptr;
+    if (!out) return fail(nullptr, HPF_E_INVALID, "hpf_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, HPF_E_CUDA, std::string("hpf_create: no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, HPF_E_INVALID, "hpf_create: bad device ordinal");
+    h = new (std::nothrow) hpf_handle();
+    if (!h) return fail(nullptr, HPF_E_NOMEM, "hpf_create: out of host memory");
+    h->device = device;
+    cudaDeviceProp prop;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(nullptr, HPF_E_CUDA, std::string("hpf_create: ") + cudaGetErrorString(e));
+    }
+    if (prop.major < 10) {
+        delete h;
+        return fail(nullptr, HPF_E_UNSUPPORTED, "hpf_create: this library is built for sm_100a (B200) only");
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    e = cudaMalloc((void**)&h->d_counter, sizeof(int));
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(nullptr, HPF_E_CUDA, std::string("hpf_create: ") + cudaGetErrorString(e));
+    }
+    *out = h;
+    return HPF_OK;
+}
+
+int hpf_destroy(hpf_t* h) {
+    if (!h) return HPF_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->d_harm); cudaFree(h->d_from); cudaFree(h->d_to); cudaFree(h->d_devof);
+    cudaFree(h->d_R); cudaFree(h->d_X); cudaFree(h->d_G); cudaFree(h->d_B); cudaFree(h->d_Xsh);
+    cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work);
+    delete h;
+    return HPF_OK;
+}
+
+int hpf_set_network(hpf_t* h, int n, int m, int c, int H, const int* harmonics, int L,
+                    const int* from_id, const int* to_id, const double* R, const double* X,
+                    const double* G, const double* B, const double* X_sh) {
+    if (!h) return HPF_E_INVALID;
+    if (n < 1 || H < 1 || m < 1 || m > n || c < 1 || c > m || L < 0 || !harmonics || !X_sh ||
+        (L > 0 && (!from_id || !to_id || !R || !X || !G || !B)))
+        return fail(h, HPF_E_INVALID, "hpf_set_network: invalid dimensions or NULL pointer "
+                                      "(need 1 <= c <= m <= n, H >= 1)");
+    if (harmonics[0] != 1) return fail(h, HPF_E_INVALID, "hpf_set_network: harmonics[0] must be 1");
+    for (int l = 0; l < L; ++l)
+        if (from_id[l] < 1 || from_id[l] > n || to_id[l] < 1 || to_id[l] > n)
+            return fail(h, HPF_E_INVALID, "hpf_set_network: line endpoint outside 1..n");
+    CK(cudaSetDevice(h->device));
+    h->n = n; h->m = m; h->c = c; h->H = H; h->q = n - m; h->L = L;
+    CK(upload(&h->d_harm, harmonics, (size_t)H));
+    CK(upload(&h->d_from, from_id, (size_t)L));
+    CK(upload(&h->d_to, to_id, (size_t)L));
+    CK(upload(&h->d_R, R, (size_t)L));
+    CK(upload(&h->d_X, X, (size_t)L));
+    CK(upload(&h->d_G, G, (size_t)L));
+    CK(upload(&h->d_B, B, (size_t)L));
+    CK(upload(&h->d_Xsh, X_sh, (size_t)n));
+    CK(upload(&h->d_Y, (const double2*)nullptr, (size_t)H * n * n));
+    h->have_net = true;
+    h->have_Y = false;
+    h->have_dev = false;
+    return HPF_OK;
+}
+
+int hpf_set_devices(hpf_t* h, int n_dev, int coupled, const double* Y_N, const int* dev_of_nl_bus) {
+    if (!h) return HPF_E_INVALID;
+    if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_set_devices: call hpf_set_network first");
+    if (h->q > 0 && (n_dev < 1 || !Y_N || !dev_of_nl_bus))
+        return fail(h, HPF_E_INVALID, "hpf_set_devices: nonlinear buses present but no device tables");
+    for (int k = 0; k < h->q; ++k)
+        if (dev_of_nl_bus[k] < 0 || dev_of_nl_bus[k] >= n_dev)
+            return fail(h, HPF_E_INVALID, "hpf_set_devices: dev_of_nl_bus entry outside 0..n_dev-1");
+    CK(cudaSetDevice(h->device));
+    h->n_dev = n_dev;
+    h->coupled = coupled ? 1 : 0;
+    const size_t per = coupled ? (size_t)h->H * h->H : (size_t)h->H;
+    CK(upload(&h->d_YN, (const double2*)Y_N, per * (size_t)(n_dev > 0 ? n_dev : 0)));
+    CK(upload(&h->d_devof, dev_of_nl_bus, (size_t)h->q));
+    h->have_dev = true;
+    return HPF_OK;
+}
+
+int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
+    if (!h) return HPF_E_INVALID;
+    if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_build_Y: call hpf_set_network first");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int total = h->n * h->H;
+    ybus_kernel<<<(total + 127) / 128, 128, 0, st>>>(h->n, h->H, h->L, h->d_harm, h->d_from, h->d_to,
+                                                      h->d_R, h->d_X, h->d_G, h->d_B, h->d_Xsh, h->d_Y);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (Y_out)
+        CK(cudaMemcpyAsync(Y_out, h->d_Y, (size_t)h->H * h->n * h->n * sizeof(double2),
+                           cudaMemcpyDeviceToDevice, st));
+    h->have_Y = true;
+    return HPF_OK;
+}
+
+int hpf_set_Y(hpf_t* h, const double* Y) {
+    if (!h) return HPF_E_INVALID;
+    if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_set_Y: call hpf_set_network first");
+    if (!Y) return fail(h, HPF_E_INVALID, "hpf_set_Y: Y is NULL");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(h->d_Y, Y, (size_t)h->H * h->n * h->n * sizeof(double2), cudaMemcpyHostToDevice));
+    h->have_Y = true;
+    return HPF_OK;
+}
+
+int hpf_thd(hpf_t* h, int B, const double* V_m, double* thd, void* stream) {
+    if (!h) return HPF_E_INVALID;
+    if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_thd: call hpf_set_network first");
+    if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_thd: B < 0");
+    if (!V_m || !thd) return fail(h, HPF_E_INVALID, "hpf_thd: NULL buffer");
+    CK(cudaSetDevice(h->device));
+    const size_t total = (size_t)h->n * B;
+    thd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->n, h->H, h->d_harm, B,
+                                                                                    V_m, thd);
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+int hpf_dim_N(const hpf_t* h) { return (h && h->have_net) ? 2 * h->n * h->H - 1 - h->c : 0; }
+int hpf_dim_Nf(const hpf_t* h) { return (h && h->have_net) ? 2 * h->n - 1 - h->c : 0; }
+long long hpf_launch_count(const hpf_t* h) { return h ? h->launches : 0; }
+
+long long hpf_jacobian_stride(const hpf_t* h) {
+    if (!h || !h->have_net) return 0;
+    const long long N = hpf_dim_N(h);
+    return (N * N + 1) & ~1LL;
+}
+
+int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I_N, double thresh_f,
+              int max_iter_f, double thresh_h, int max_iter_h, int flags, double* V_m, double* V_a,
+              double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status,
+              double* err_hist_f, double* err_hist_h, void* stream) {
+    return solve_common(h, 0, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a,
+                        I_inj, n_iter_f, n_iter_h, err_h, nullptr, status, err_hist_f, err_hist_h, stream);
+}
+
+int hpf_fund_solve(hpf_t* h, int B, const double* P, const double* Q, double thresh_f, int max_iter_f,
+                   double* V_m, double* V_a, int* n_iter_f, double* err_f, double* err_hist_f,
+                   void* stream) {
+    return solve_common(h, 1, B, P, Q, nullptr, thresh_f, max_iter_f, 0.0, 0, 0, V_m, V_a, nullptr,
+                        n_iter_f, nullptr, nullptr, err_f, nullptr, err_hist_f, nullptr, stream);
+}
+
+int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const double* I_N, double thresh_f,
+                   int max_iter_f, double thresh_h, int max_iter_h, double* V_m, double* V_a,
+                   double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status) {
+    int rc = ready(h, "hpf_solve_host", true);
+    if (rc) return rc;
+    if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_solve_host: B < 0");
+    CK(cudaSetDevice(h->device));
+    const size_t n = h->n, H = h->H, q = h->q, Bs = (size_t)B;
+    const size_t nP = n * Bs, nI = 2 * q * H * Bs, nV = n * H * Bs;
+    // one device allocation: P, Q, I_N | V_m, V_a, I_inj, err_h | n_iter_f, n_iter_h, status
+    const size_t nd = 2 * nP + nI + 2 * nV + nI + Bs;
+    double* d = nullptr;
+    int* di = nullptr;
+    CK(cudaMalloc((void**)&d, nd * sizeof(double)));
+    cudaError_t e = cudaMalloc((void**)&di, 3 * Bs * sizeof(int));
+    if (e != cudaSuccess) { cudaFree(d); return fail(h, HPF_E_CUDA, cudaGetErrorString(e)); }
+    double *dP = d, *dQ = dP + nP, *dI = dQ + nP, *dVm = dI + nI, *dVa = dVm + nV, *dInj = dVa + nV,
+           *dErr = dInj + nI;
+    cudaStream_t st = nullptr;
+    rc = HPF_OK;
+    auto bail = [&](cudaError_t ee) { rc = fail(h, HPF_E_CUDA, cudaGetErrorString(ee)); };
+    if ((e = cudaMemcpyAsync(dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) bail(e);
+    if (!rc && (e = cudaMemcpyAsync(dQ, Q, nP * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) bail(e);
+    if (!rc && nI && (e = cudaMemcpyAsync(dI, I_N, nI * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) bail(e);
+    if (!rc)
+        rc = hpf_solve(h, B, dP, dQ, dI, thresh_f, max_iter_f, thresh_h, max_iter_h, 0, dVm, dVa,
+                       I_inj ? dInj : nullptr, di, di + Bs, dErr, di + 2 * Bs, nullptr, nullptr, st);
+    if (!rc && (e = cudaMemcpyAsync(V_m, dVm, nV * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
+    if (!rc && (e = cudaMemcpyAsync(V_a, dVa, nV * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
+    if (!rc && I_inj && nI && (e = cudaMemcpyAsync(I_inj, dInj, nI * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
+    if (!rc && (e = cudaMemcpyAsync(err_h, dErr, Bs * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
+    if (!rc && (e = cudaMemcpyAsync(n_iter_f, di, Bs * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
+    if (!rc && (e = cudaMemcpyAsync(n_iter_h, di + Bs, Bs * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
+    if (!rc && (e = cudaMemcpyAsync(status, di + 2 * Bs, Bs * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
+    e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) bail(e);
+    cudaFree(d);
+    cudaFree(di);
+    return rc;
+}
+
+int hpf_mismatch(hpf_t* h, int B, const double* V_m, const double* V_a, const double* P, const double* Q,
+                 const double* I_N, double* f, double* err, double* I_inj, void* stream) {
+    int rc = ready(h, "hpf_mismatch", true);
+    if (rc) return rc;
+    if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_mismatch: B < 0");
+    if (!V_m || !V_a || !P || !Q || !f || !err || (h->q > 0 && !I_N))
+        return fail(h, HPF_E_INVALID, "hpf_mismatch: NULL buffer");
+    CK(cudaSetDevice(h->device));
+    const DevNet net = devnet(h);
+    MismatchArgs a;
+    a.B = B; a.V_m = V_m; a.V_a = V_a; a.P = P; a.Q = Q; a.I_N = (const double2*)I_N;
+    a.f = f; a.err = err; a.I_inj = (double2*)I_inj;
+    size_t smem = tile_smem_bytes(net.n, net.H, net.q);
+    int occ = 0;
+    if (smem <= (size_t)h->smem_optin) {
+        rc = prep_kernel(h, mismatch_tile_kernel, smem, "hpf_mismatch", &occ);
+        if (rc) return rc;
+        long long tiles = ((long long)B + HPF_TILE - 1) / HPF_TILE;
+        long long grid = (long long)occ * h->sm_count;
+        if (grid > tiles) grid = tiles;
+        mismatch_tile_kernel<<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a);
+    } else {
+        smem = scn_smem_bytes(net.n, net.H, net.q, net.N, false);
+        rc = prep_kernel(h, mismatch_cta_kernel, smem, "hpf_mismatch", &occ);
+        if (rc) return rc;
+        long long grid = (long long)occ * h->sm_count;
+        if (grid > B) grid = B;
+        mismatch_cta_kernel<<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+int hpf_jacobian(hpf_t* h, int B, const double* V_m, const double* V_a, double* J, void* stream) {
+    int rc = ready(h, "hpf_jacobian", true);
+    if (rc) return rc;
+    if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_jacobian: B < 0");
+    if (!V_m || !V_a || !J) return fail(h, HPF_E_INVALID, "hpf_jacobian: NULL buffer");
+    if ((reinterpret_cast<uintptr_t>(J) & 15) != 0)
+        return fail(h, HPF_E_INVALID, "hpf_jacobian: J must be 16-byte aligned");
+    CK(cudaSetDevice(h->device));
+    const DevNet net = devnet(h);
+    JacobianArgs a;
+    a.B = B; a.V_m = V_m; a.V_a = V_a; a.J = J; a.stride = hpf_jacobian_stride(h);
+    size_t smem = jac_smem_bytes(net.n, net.H, net.q, net.N, a.stride);
+    int occ = 0;
+    if (smem <= (size_t)h->smem_optin) {
+        rc = prep_kernel(h, jacobian_kernel, smem, "hpf_jacobian", &occ);
+        if (rc) return rc;
+        long long grid = (long long)occ * h->sm_count;
+        if (grid > B) grid = B;
+        jacobian_kernel<<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a);
+    } else {
+        smem = scn_smem_bytes(net.n, net.H, net.q, net.N, false);
+        rc = prep_kernel(h, jacobian_gmem_kernel, smem, "hpf_jacobian", &occ);
+        if (rc) return rc;
+        long long grid = (long long)occ * h->sm_count;
+        if (grid > B) grid = B;
+        jacobian_gmem_kernel<<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, int* info, void* stream) {
+    int rc = ready(h, "hpf_lu_solve", false);
+    if (rc) return rc;
+    if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_lu_solve: B < 0");
+    if (!J || !f || !dx || !info) return fail(h, HPF_E_INVALID, "hpf_lu_solve: NULL buffer");
+    CK(cudaSetDevice(h->device));
+    const DevNet net = devnet(h);
+    LuArgs a;
+    a.B = B; a.J = J; a.f = f; a.dx = dx; a.info = info; a.stride = hpf_jacobian_stride(h);
+    const bool gm = !fits_smem_lu(h, net);
+    const size_t smem = scn_smem_bytes(net.n, net.H, net.q, net.N, !gm);
+    int occ = 0;
+    rc = gm ? prep_kernel(h, lu_solve_kernel<true>, smem, "hpf_lu_solve", &occ, HPF_THREADS_GMEM)
+            : prep_kernel(h, lu_solve_kernel<false>, smem, "hpf_lu_solve", &occ);
+    if (rc) return rc;
+    long long grid = (long long)occ * h->sm_count;
+    if (grid > B) grid = B;
+    a.workspace = nullptr;
+    if (gm) {
+        rc = ensure_workspace(h, (size_t)grid * odd_ld(net.N) * (net.N + 1));
+        if (rc) return rc;
+        a.workspace = h->d_work;
+        lu_solve_kernel<true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, (cudaStream_t)stream>>>(net, a);
+    } else {
+        lu_solve_kernel<false><<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+}  // extern "C"

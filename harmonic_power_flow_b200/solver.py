@@ -1,0 +1,248 @@
+"""Batched solver: Python host over the C ABI.  PyTorch tensors are only the buffer
+container (device memory + the current CUDA stream); every computation is a kernel of
+libhpf_b200.so.  There is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .netio import PackedNet
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _np_i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _np_d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@dataclass
+class BatchResult:
+    """Results of a batch, batch-innermost device tensors exactly as the kernels wrote them."""
+    V_m: torch.Tensor          # [H, n, B] f64
+    V_a: torch.Tensor          # [H, n, B] f64
+    I_inj: torch.Tensor        # [q, H, B] c128 (or None)
+    n_iter_f: torch.Tensor     # [B] i32
+    n_iter_h: torch.Tensor     # [B] i32
+    err_h: torch.Tensor        # [B] f64
+    status: torch.Tensor       # [B] i32  (0 converged, 1 max-iter, 2 singular, 3 non-finite)
+    err_hist_f: torch.Tensor = None
+    err_hist_h: torch.Tensor = None
+
+    @property
+    def B(self):
+        return self.status.shape[0]
+
+    def converged(self):
+        return self.status == _lib.ST_CONVERGED
+
+    def to_host(self):
+        out = {}
+        for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status",
+                  "err_hist_f", "err_hist_h"):
+            v = getattr(self, k)
+            out[k] = None if v is None else v.cpu().numpy()
+        return out
+
+
+class BatchSolver:
+    """One handle = one GPU.  ``net`` is a PackedNet (netio.pack_network)."""
+
+    def __init__(self, net: PackedNet, device: int | None = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("harmonic_power_flow_b200 needs a CUDA device (B200); no CPU fallback")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.net = net
+        self._h = C.c_void_p()
+        _lib.check(None, self.lib.hpf_create(C.byref(self._h), self.device_index))
+        n = net
+        _lib.check(self._h, self.lib.hpf_set_network(
+            self._h, n.n, n.m, n.c, n.H, _np_i(n.harmonics), len(n.R), _np_i(n.from_id), _np_i(n.to_id),
+            _np_d(n.R), _np_d(n.X), _np_d(n.G), _np_d(n.B), _np_d(n.X_sh)))
+        if n.q > 0:
+            if n.Y_N is None:
+                raise ValueError("network has nonlinear buses but no Norton equivalents attached")
+            yn = np.ascontiguousarray(n.Y_N).view(np.float64)
+            _lib.check(self._h, self.lib.hpf_set_devices(self._h, len(n.devices), int(n.coupled),
+                                                         _np_d(yn), _np_i(n.dev_of_nl_bus)))
+        else:
+            _lib.check(self._h, self.lib.hpf_set_devices(self._h, 0, int(n.coupled), None, None))
+        self.Y = self.build_Y()
+
+    # -- plumbing ----------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.hpf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _f64(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=self.device)
+
+    def _i32(self, *shape):
+        return torch.empty(shape, dtype=torch.int32, device=self.device)
+
+    def _c128(self, *shape):
+        return torch.empty(shape, dtype=torch.complex128, device=self.device)
+
+    def _dev(self, a, dtype):
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=dtype)
+        else:
+            t = torch.as_tensor(np.array(a, copy=True, order="C"), dtype=dtype).to(self.device)
+        return t.contiguous()
+
+    @property
+    def N(self):
+        return self.lib.hpf_dim_N(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.hpf_launch_count(self._h))
+
+    # -- kernel 1 ----------------------------------------------------------------------
+    def build_Y(self):
+        """Y(h) [H, n, n] complex128 on the device (HG:132-171)."""
+        n = self.net
+        Y = self._c128(n.H, n.n, n.n)
+        _lib.check(self._h, self.lib.hpf_build_Y(self._h, _ptr(Y), self._stream()))
+        return Y
+
+    def set_Y(self, Y):
+        """Replace Y(h) by a caller-supplied [H, n, n] complex table (pf(Y, buses), HG:244)."""
+        Y = np.ascontiguousarray(Y, dtype=np.complex128)
+        n = self.net
+        if Y.shape != (n.H, n.n, n.n):
+            raise ValueError("Y must be [H, n, n]")
+        _lib.check(self._h, self.lib.hpf_set_Y(self._h, _np_d(Y.view(np.float64))))
+        self.Y = torch.as_tensor(Y).to(self.device)
+
+    def thd(self, V_m):
+        """THD_F, THD_R [2, n, B] from magnitudes [H, n, B] (HG:563-572)."""
+        V_m = self._dev(V_m, torch.float64)
+        B = V_m.shape[2]
+        out = self._f64(2, self.net.n, B)
+        _lib.check(self._h, self.lib.hpf_thd(self._h, B, _ptr(V_m), _ptr(out), self._stream()))
+        return out
+
+    # -- inputs ------------------------------------------------------------------------
+    def prepare(self, P, Q, I_N=None):
+        """Move scenario inputs to the device in batch-innermost layout.
+        P, Q: [n, B]; I_N: [q, H, B] complex."""
+        P = self._dev(P, torch.float64)
+        Q = self._dev(Q, torch.float64)
+        n = self.net
+        if P.shape[0] != n.n or P.shape != Q.shape:
+            raise ValueError("P, Q must be [n, B]")
+        B = P.shape[1]
+        if n.q > 0:
+            I_N = self._dev(I_N, torch.complex128)
+            if tuple(I_N.shape) != (n.q, n.H, B):
+                raise ValueError("I_N must be [q, H, B]")
+        else:
+            I_N = None
+        return P, Q, I_N
+
+    # -- fused solve -------------------------------------------------------------------
+    def solve(self, P, Q, I_N=None, thresh_f=1e-6, max_iter_f=30, thresh_h=1e-4, max_iter_h=50,
+              raw=False, want_I_inj=True, history=False, out: BatchResult | None = None) -> BatchResult:
+        P, Q, I_N = self.prepare(P, Q, I_N)
+        n = self.net
+        B = P.shape[1]
+        if out is None:
+            out = BatchResult(
+                V_m=self._f64(n.H, n.n, B), V_a=self._f64(n.H, n.n, B),
+                I_inj=self._c128(n.q, n.H, B) if (want_I_inj and n.q > 0) else None,
+                n_iter_f=self._i32(B), n_iter_h=self._i32(B), err_h=self._f64(B), status=self._i32(B),
+                err_hist_f=self._f64(max_iter_f + 1, B) if history else None,
+                err_hist_h=self._f64(max_iter_h + 1, B) if history else None)
+        _lib.check(self._h, self.lib.hpf_solve(
+            self._h, B, _ptr(P), _ptr(Q), _ptr(I_N), thresh_f, max_iter_f, thresh_h, max_iter_h,
+            _lib.SOLVE_RAW if raw else 0, _ptr(out.V_m), _ptr(out.V_a), _ptr(out.I_inj),
+            _ptr(out.n_iter_f), _ptr(out.n_iter_h), _ptr(out.err_h), _ptr(out.status),
+            _ptr(out.err_hist_f), _ptr(out.err_hist_h), self._stream()))
+        return out
+
+    def solve_host(self, P, Q, I_N, thresh_f=1e-6, max_iter_f=30, thresh_h=1e-4, max_iter_h=50):
+        """hpf_solve_host: numpy in, numpy out, all copies inside the C call."""
+        n = self.net
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        B = P.shape[1]
+        I_N = np.ascontiguousarray(I_N, dtype=np.complex128) if n.q > 0 else np.zeros(0, np.complex128)
+        V_m = np.empty((n.H, n.n, B)); V_a = np.empty((n.H, n.n, B))
+        I_inj = np.empty((n.q, n.H, B), dtype=np.complex128)
+        nf = np.empty(B, np.int32); nh = np.empty(B, np.int32); st = np.empty(B, np.int32)
+        err = np.empty(B)
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        _lib.check(self._h, self.lib.hpf_solve_host(
+            self._h, B, vp(P), vp(Q), vp(I_N), thresh_f, max_iter_f, thresh_h, max_iter_h,
+            vp(V_m), vp(V_a), vp(I_inj), vp(nf), vp(nh), vp(err), vp(st)))
+        return dict(V_m=V_m, V_a=V_a, I_inj=I_inj, n_iter_f=nf, n_iter_h=nh, err_h=err, status=st)
+
+    def fund_solve(self, P, Q, thresh_f=1e-6, max_iter_f=30, history=False):
+        P, Q, _ = self.prepare(P, Q, None) if self.net.q == 0 else (self._dev(P, torch.float64),
+                                                                    self._dev(Q, torch.float64), None)
+        n = self.net
+        B = P.shape[1]
+        V_m, V_a = self._f64(n.H, n.n, B), self._f64(n.H, n.n, B)
+        nf, err = self._i32(B), self._f64(B)
+        hist = self._f64(max_iter_f + 1, B) if history else None
+        _lib.check(self._h, self.lib.hpf_fund_solve(self._h, B, _ptr(P), _ptr(Q), thresh_f, max_iter_f,
+                                                    _ptr(V_m), _ptr(V_a), _ptr(nf), _ptr(err), _ptr(hist),
+                                                    self._stream()))
+        return V_m, V_a, nf, err, hist
+
+    # -- standalone kernels --------------------------------------------------------------
+    def mismatch(self, V_m, V_a, P, Q, I_N=None, want_I_inj=False):
+        n = self.net
+        V_m, V_a = self._dev(V_m, torch.float64), self._dev(V_a, torch.float64)
+        P, Q, I_N = self.prepare(P, Q, I_N)
+        B = P.shape[1]
+        f, err = self._f64(self.N, B), self._f64(B)
+        I_inj = self._c128(n.q, n.H, B) if want_I_inj else None
+        _lib.check(self._h, self.lib.hpf_mismatch(self._h, B, _ptr(V_m), _ptr(V_a), _ptr(P), _ptr(Q),
+                                                  _ptr(I_N), _ptr(f), _ptr(err), _ptr(I_inj), self._stream()))
+        return (f, err, I_inj) if want_I_inj else (f, err)
+
+    def jacobian_stride(self):
+        return int(self.lib.hpf_jacobian_stride(self._h))
+
+    def jacobian(self, V_m, V_a, out=None):
+        """-> J [B, stride]; use ``jacobian_view`` for the [B, N, N] row-major matrices."""
+        V_m, V_a = self._dev(V_m, torch.float64), self._dev(V_a, torch.float64)
+        B = V_m.shape[2]
+        J = self._f64(B, self.jacobian_stride()) if out is None else out
+        _lib.check(self._h, self.lib.hpf_jacobian(self._h, B, _ptr(V_m), _ptr(V_a), _ptr(J), self._stream()))
+        return J
+
+    def jacobian_view(self, J):
+        N = self.N
+        return J[:, :N * N].view(J.shape[0], N, N)
+
+    def lu_solve(self, J, f):
+        f = self._dev(f, torch.float64)
+        B = f.shape[1]
+        dx, info = self._f64(self.N, B), self._i32(B)
+        _lib.check(self._h, self.lib.hpf_lu_solve(self._h, B, _ptr(J), _ptr(f), _ptr(dx), _ptr(info),
+                                                  self._stream()))
+        return dx, info

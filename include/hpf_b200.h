@@ -1,0 +1,197 @@
+/*
+ * hpf_b200.h - C ABI of the B200-native batched harmonic power-flow solve path.
+ *
+ * Drop-in boundary for the solve path of the reference's
+ *   "Harmonic Power Flow/hcne_generalized.py"  (HG below, cited as HG:line).
+ * The reference has no FFI/plugin interface (it is a flat Python script), so the
+ * boundary is the function-level API of HG; each entry point below names the HG
+ * function(s) it replaces.  The Python host layer (harmonic_power_flow_b200/)
+ * binds these symbols with ctypes and mirrors the HG function names.
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only, no C++/torch types.  Return 0 on success,
+ *    a negative HPF_E_* code on failure; hpf_last_error() gives the text.
+ *    Nothing throws across the ABI.  Per-scenario NUMERICAL outcomes are
+ *    reported in status[B] (HPF_ST_*), never in the return code.
+ *  - "host" pointers are read during the call and copied.  "device" pointers are
+ *    caller-owned CUDA device memory on the handle's device; the handle owns only
+ *    the network, Norton-equivalent tables, Y(h) and small scratch.
+ *  - Every kernel entry point is asynchronous on `stream` (a cudaStream_t passed
+ *    as void*, NULL = legacy default stream); no hidden synchronisation except
+ *    in hpf_destroy() and the *_host convenience call.
+ *  - All arithmetic is IEEE FP64.  Complex values are interleaved (re, im)
+ *    doubles (numpy/torch complex128).
+ *  - Batch arrays are BATCH-INNERMOST: element (i, b) of an [n, B] array is at
+ *    i*B + b, so a warp touching consecutive scenarios issues one coalesced
+ *    128-bit-vectorisable request.
+ *  - Symbols (HG:11-17,122-127): n buses; m = 0-based index of the first
+ *    nonlinear bus; q = n - m; c = 1 + number of PV buses; H harmonic orders
+ *    including the fundamental; stacked index s = h*n + i (harmonic-major);
+ *    N = 2nH - 1 - c unknowns of the harmonic Newton system,
+ *    Nf = 2n - 1 - c of the fundamental one.  Bus order: slack, PV.., PQ..,
+ *    nonlinear.. (HG:83).
+ *  - Not thread-safe per handle; use one handle per GPU / per host thread.
+ */
+#ifndef HPF_B200_H
+#define HPF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hpf_handle hpf_t;
+
+/* return codes */
+#define HPF_OK              0
+#define HPF_E_INVALID      -1   /* bad argument / call order                      */
+#define HPF_E_CUDA         -2   /* CUDA runtime error (text in hpf_last_error)    */
+#define HPF_E_UNSUPPORTED  -3   /* dimensions exceed what the kernels support     */
+#define HPF_E_NOMEM        -4
+
+/* per-scenario status word (status[B]) */
+#define HPF_ST_CONVERGED    0
+#define HPF_ST_MAXITER      1   /* n_iter == max_iter in either stage (HG:273,558) */
+#define HPF_ST_SINGULAR     2   /* zero pivot met in a Newton step                 */
+#define HPF_ST_NONFINITE    3   /* NaN/Inf in the mismatch or the state            */
+
+/* ABI version of this header: bumped on any signature change. */
+#define HPF_ABI_VERSION 2
+int hpf_abi_version(void);
+
+/* Lifetime.  `device` is the CUDA ordinal the handle is bound to. */
+int hpf_create(hpf_t** out, int device);
+int hpf_destroy(hpf_t* h);
+/* Text of the last error on this handle (h == NULL: last create failure). */
+const char* hpf_last_error(const hpf_t* h);
+
+/*
+ * Network in per-unit, exactly what init_network() yields (HG:45-128):
+ * harmonics[H] orders with harmonics[0] == 1 (HG:584); lines with the CSV's
+ * 1-BASED fromID/toID and R, X, G, B (HG:57-60); X_sh[n] (HG:92).  Host pointers.
+ */
+int hpf_set_network(hpf_t* h, int n, int m, int c, int H, const int* harmonics,
+                    int L, const int* from_id, const int* to_id,
+                    const double* R, const double* X, const double* G, const double* B,
+                    const double* X_sh);
+
+/*
+ * Norton-equivalent admittances, what import_Norton_Equivalents() yields
+ * (HG:278-310) minus I_N (which is per scenario): n_dev device types,
+ * Y_N complex [n_dev, H, H] row-major (row = harmonic of the current, column =
+ * harmonic of the voltage, HG:304) when coupled, else [n_dev, H] (HG:308);
+ * dev_of_nl_bus[q] maps nonlinear bus m+k to its device type.  Host pointers.
+ */
+int hpf_set_devices(hpf_t* h, int n_dev, int coupled, const double* Y_N,
+                    const int* dev_of_nl_bus);
+
+/*
+ * Kernel 1 - per-harmonic bus admittance assembly.  Replaces
+ * build_admittance_matrices() (HG:132-171), including its quirks (assignment of
+ * parallel lines, shunt only for h != 1, pi-shunt index off-by-one).
+ * Result is kept in the handle; if Y_out != NULL it is also written there
+ * (device, complex [H, n, n]).
+ */
+int hpf_build_Y(hpf_t* h, double* Y_out, void* stream);
+
+/*
+ * Use a caller-supplied admittance table instead of building it: Y complex [H, n, n]
+ * (host).  This is what pf(Y, buses) of the reference takes (HG:244,255).
+ */
+int hpf_set_Y(hpf_t* h, const double* Y);
+
+/* hpf_solve flags */
+#define HPF_SOLVE_RAW 1   /* skip the post-processing of HG:547-549: return the raw iterate */
+
+/*
+ * Whole solve for B scenarios: pf() (HG:244-275) followed by the harmonic
+ * Newton-Raphson and post-processing of hpf() (HG:511-560), one fused
+ * persistent kernel (mismatch, Jacobian, shared-memory LU, state update).
+ *   in : P, Q [n, B] p.u.;  I_N complex [q, H, B] p.u.
+ *   out: V_m, V_a [H, n, B] post-processed like HG:547-549 (|V|, angle in [0, 2pi))
+ *        unless HPF_SOLVE_RAW;
+ *        I_inj complex [q, H, B] = I_N - Y_N V at the solution (HG:313-323), may be NULL;
+ *        n_iter_f, n_iter_h, status int32 [B]; err_h [B] final inf-norm mismatch;
+ *        err_hist_f [max_iter_f + 1, B], err_hist_h [max_iter_h + 1, B] (may be NULL):
+ *        the mismatch norm before each Newton step and after the last one (the
+ *        reference's err_t / err_h_t dicts, HG:258,264,533,541); unused tail = NaN.
+ * Loops are exactly `while err > thresh and n_iter < max_iter` (HG:259,536).
+ */
+int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I_N,
+              double thresh_f, int max_iter_f, double thresh_h, int max_iter_h, int flags,
+              double* V_m, double* V_a, double* I_inj,
+              int* n_iter_f, int* n_iter_h, double* err_h, int* status,
+              double* err_hist_f, double* err_hist_h, void* stream);
+
+/*
+ * Same with HOST buffers (pageable or pinned): copies in, solves, copies out,
+ * synchronises.  This is the call a reference-side binding would make.
+ */
+int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const double* I_N,
+                   double thresh_f, int max_iter_f, double thresh_h, int max_iter_h,
+                   double* V_m, double* V_a, double* I_inj,
+                   int* n_iter_f, int* n_iter_h, double* err_h, int* status);
+
+/*
+ * Fundamental stage only: pf() (HG:244-275).  V_m, V_a [H, n, B] receive the flat
+ * start (HG:174-184) with the h = 1 block replaced by the fundamental solution
+ * (no post-processing, like HG:233-241).
+ */
+int hpf_fund_solve(hpf_t* h, int B, const double* P, const double* Q,
+                   double thresh_f, int max_iter_f,
+                   double* V_m, double* V_a, int* n_iter_f, double* err_f,
+                   double* err_hist_f, void* stream);
+
+/*
+ * Kernel 2 - fused power/current mismatch, harmonic_mismatch() (HG:360-390) with
+ * current_balance() (HG:326-357) and the Norton contraction I = I_N - Y_N V of
+ * current_injections() (HG:313-323).
+ *   in : V_m, V_a [H, n, B] (un-normalised iterate); P, Q [n, B]; I_N [q, H, B]
+ *   out: f [N, B] (row order of HG:388), err [B] = ||f||_inf; I_inj [q,H,B] or NULL
+ */
+int hpf_mismatch(hpf_t* h, int B, const double* V_m, const double* V_a,
+                 const double* P, const double* Q, const double* I_N,
+                 double* f, double* err, double* I_inj, void* stream);
+
+/*
+ * Kernel 3 - harmonic Jacobian, build_harmonic_jacobian() (HG:401-473), dense FP64.
+ *   out: J [B, hpf_jacobian_stride()] ; scenario b holds the N x N matrix
+ *        row-major (same element order as the reference's J.toarray()) followed
+ *        by padding up to the stride (a multiple of 2 doubles so that every
+ *        matrix is 16-byte aligned for the bulk-copy engine).
+ */
+int hpf_jacobian(hpf_t* h, int B, const double* V_m, const double* V_a,
+                 double* J, void* stream);
+/* doubles between consecutive scenarios' matrices in hpf_jacobian/hpf_lu_solve */
+long long hpf_jacobian_stride(const hpf_t* h);
+
+/*
+ * Kernel 4 - batched dense LU (partial pivoting, warp-shuffle pivot search) and
+ * triangular solves in shared memory: dx = J^{-1} f, the linear algebra of
+ * update_harmonic_state_vec() (HG:476-479).
+ *   in : J [B, stride] as written by hpf_jacobian (not modified); f [N, B]
+ *   out: dx [N, B]; info int32 [B] (0 ok, k+1 = zero pivot at step k)
+ */
+int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f,
+                 double* dx, int* info, void* stream);
+
+/*
+ * Post-processing after the path - get_THD() (HG:563-572): for every bus and scenario
+ * THD_F = sqrt(sum_{order>=3} V_m^2) / V_m(order 1), THD_R = same / sqrt(sum_all V_m^2).
+ *   in : V_m [H, n, B];  out: thd [2, n, B]  (plane 0 = THD_F, plane 1 = THD_R)
+ */
+int hpf_thd(hpf_t* h, int B, const double* V_m, double* thd, void* stream);
+
+/* Dimensions derived by hpf_set_network (0 before it). */
+int hpf_dim_N(const hpf_t* h);
+int hpf_dim_Nf(const hpf_t* h);
+
+/*
+ * Number of kernel launches this handle has issued since creation (each CUDA
+ * kernel launch of this library counts 1).  Used by bench.py for gpu_launches.
+ */
+long long hpf_launch_count(const hpf_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPF_B200_H */

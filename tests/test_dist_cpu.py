@@ -1,0 +1,56 @@
+"""world_size-2 gloo test of the multi-GPU host logic (sharding + the final gather)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from harmonic_power_flow_b200 import dist as hdist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, B, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, n = 3, 4
+        g = torch.Generator().manual_seed(1234)
+        full_V = torch.rand((H, n, B), dtype=torch.float64, generator=g)
+        full_I = torch.complex(torch.rand((2, H, B), dtype=torch.float64, generator=g),
+                               torch.rand((2, H, B), dtype=torch.float64, generator=g))
+        full_st = torch.randint(0, 4, (B,), dtype=torch.int32, generator=g)
+        V, I, st = hdist.shard_inputs(rank, world, full_V, full_I, full_st)
+        lo, hi = hdist.shard_bounds(B, world, rank)
+        assert V.shape[-1] == hi - lo
+        gV = hdist.gather_last_axis(V.contiguous(), B)
+        gI = hdist.gather_last_axis(I.contiguous(), B)
+        gs = hdist.gather_last_axis(st.contiguous(), B)
+        ok = torch.equal(gV, full_V) and torch.equal(gI, full_I) and torch.equal(gs, full_st)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [64, 37, 1])
+def test_gather_is_identity_permutation_world2(B):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=10) for _ in range(2))
+    assert got == [(0, True), (1, True)]

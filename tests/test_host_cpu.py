@@ -1,0 +1,130 @@
+"""CPU-only tests: C-ABI surface, data-contract layer, scenario generator, sharding math."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+from conftest import GOLDEN, ROOT
+from harmonic_power_flow_b200 import _lib, netio, scenarios
+from harmonic_power_flow_b200 import dist as hdist
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hpf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hpf_[a-z_A-Z0-9]+)\s*\(", hdr))
+    assert declared, "header parse failed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()                        # binds every symbol or raises
+    for name in declared:
+        assert hasattr(lib, name)
+    m = re.search(r"#define HPF_ABI_VERSION (\d+)", hdr)
+    assert lib.hpf_abi_version() == int(m.group(1)) == _lib.ABI_VERSION
+
+
+def test_create_fails_loudly_without_gpu():
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.hpf_create(C.byref(h), 0)
+    assert rc == _lib.HPF_E_CUDA and not h.value
+    assert b"CUDA" in lib.hpf_last_error(None)
+    from harmonic_power_flow_b200 import BatchSolver
+    net, _, _ = None, None, None
+    with pytest.raises(RuntimeError):
+        BatchSolver(helpers.packed_from_files("net3", 5, True, _tmp())[0])
+
+
+def _tmp():
+    import tempfile
+    return tempfile.mkdtemp(prefix="hpf_test_")
+
+
+def test_null_handle_is_rejected():
+    lib = _lib.load()
+    assert lib.hpf_dim_N(None) == 0
+    assert lib.hpf_jacobian_stride(None) == 0
+    assert lib.hpf_destroy(None) == 0
+    assert lib.hpf_build_Y(None, None, None) == _lib.HPF_E_INVALID
+
+
+@pytest.mark.parametrize("case", ["net3_c_h25", "net2_c_h19", "net2ev_c_h19", "net2_uc_h51",
+                                  "net1_c_h25", "net2ev_uc_h19"])
+def test_loader_matches_reference_per_unit_data(case, tmp_path):
+    d = helpers.load_case(case)
+    net, st, _ = helpers.packed_from_files(str(d["net"]), int(d["h_max"]), bool(d["coupled"]), tmp_path,
+                                           julia_schema=str(d["net"]) == "net1")
+    assert (net.n, net.m, net.c) == (int(d["n"]), int(d["m"]), int(d["c"]))
+    assert np.array_equal(net.harmonics, d["harmonics"])
+    assert np.array_equal(net.P, d["P"]) and np.array_equal(net.Q, d["Q"])
+    # the NE CSV text round-trips bit-exactly and the p.u. conversion equals HG:301-308
+    assert np.array_equal(net.I_N, d["I_N"])
+    YN = net.Y_N[net.dev_of_nl_bus]
+    assert np.array_equal(YN, d["Y_N"])
+    assert net.N == 2 * net.n * net.H - 1 - net.c
+
+
+def test_ne_lookup_is_case_insensitive_and_checks_harmonics(tmp_path):
+    helpers.write_ne_csvs(str(tmp_path))
+    assert netio.find_ne_file("SMPS", str(tmp_path)).endswith("smps_NE.csv")
+    with pytest.raises(FileNotFoundError):
+        netio.find_ne_file("toaster", str(tmp_path))
+    pb, pl = helpers.write_net_csvs("net3", str(tmp_path))
+    st = netio.Settings(H_MAX=101, ne_dir=str(tmp_path))          # file only has orders <= 99
+    buses, lines, m, n, c = netio.init_network(pb, pl, st)
+    with pytest.raises(KeyError):
+        netio.import_Norton_Equivalents(buses, True, st)
+
+
+def test_bus_order_is_checked(tmp_path):
+    pb, pl = helpers.write_net_csvs("net3", str(tmp_path))
+    txt = open(pb).read().splitlines()
+    txt[2], txt[3] = txt[3], txt[2]          # PQ before PV
+    open(pb, "w").write("\n".join(txt))
+    with pytest.raises(ValueError):
+        netio.init_network(pb, pl, netio.Settings())
+
+
+def test_trailing_blank_line_and_vnom_column(tmp_path):
+    pb, pl = helpers.write_net_csvs("net3", str(tmp_path))
+    open(pl, "a").write("\n")                 # HPF/net2_lines.csv ends with a blank line
+    rows = open(pb).read().splitlines()
+    rows = [r + (";V_nom" if i == 0 else ";230") for i, r in enumerate(rows)]
+    open(pb, "w").write("\n".join(rows))
+    buses, lines, m, n, c = netio.init_network(pb, pl, netio.Settings())
+    assert (m, n, c) == (3, 4, 2) and len(lines) == 4
+
+
+@pytest.mark.parametrize("name", ["net3_c_h25_tight", "net3_c_h25_wide", "net2ev_c_h19_tight"])
+def test_scenario_generator_reproduces_golden_inputs(name, tmp_path):
+    d = helpers.load_set(name)
+    net, _, _ = helpers.packed_from_files(str(d["net"]), int(d["h_max"]), bool(d["coupled"]), tmp_path)
+    S = len(d["seed"])
+    spread = "tight" if name.endswith("tight") else "wide"
+    P, Q, I_N = scenarios.make_batch(net, S, spread)
+    assert np.array_equal(P.T, d["P"]) and np.array_equal(Q.T, d["Q"])
+    assert np.abs(np.moveaxis(I_N, 2, 0) - d["I_N"]).max() < 1e-15
+    # pure function of (B, spread, seed0), also past the per-seed prefix
+    a = scenarios.make_batch(net, 40, spread, exact_prefix=8)
+    b = scenarios.make_batch(net, 40, spread, exact_prefix=8)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert np.array_equal(a[0][:, :8], P[:, :8])
+
+
+def test_shard_bounds_cover_batch_exactly():
+    for B in (0, 1, 7, 64, 65536, 65537):
+        for w in (1, 2, 3, 4, 8):
+            spans = [hdist.shard_bounds(B, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1
+            per = hdist.shard_size(B, w)
+            assert all(hi - lo <= per for lo, hi in spans)
+            for s in range(0, B, max(1, B // 13)):
+                r = s // per
+                assert spans[r][0] <= s < spans[r][1]
