@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""Benchmark of the harmonic power-flow solve path (driver contract, see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm (oracle port)
+    torchrun ... bench.py --gpus N ...                             # N > 1, one rank per GPU
+
+Workload (BASELINE.json configs[2], the configuration the metric and target are quoted on):
+net3, coupled SMPS Norton equivalent, fundamental + odd harmonics to the 25th (N = 101),
+65,536 seeded randomised load / spectrum scenarios PER GPU (weak scaling: scenarios are
+independent, each rank solves its own block, no data-path collective).  One "step" = one
+complete solve of the batch: fundamental NR + harmonic NR + post-processing.
+
+Keys: `value` = converged solves/s, inputs resident in HBM, CUDA-event timed on the launch
+stream, max over ranks.  `e2e` = the same through the host-buffer C-ABI entry point
+(hpf_solve_host): pinned host inputs -> H2D -> solve -> D2H of every result, plus (N > 1) the
+final NCCL gather of flags and results.  `roofline` = the dominant kernel (fused Newton
+kernel) against the FP64 pipe; `roofline_kernels` = the standalone mismatch / Jacobian kernels
+against measured HBM bandwidth.  `cpu_baseline` = the oracle port on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NET, H_MAX, COUPLED, SPREAD = "net3", 25, True, "tight"
+B_PER_GPU = 65536
+METRIC = "converged harmonic-PF solves/sec (FP64)"
+UNIT = "solves/s"
+
+
+def load_net():
+    """net3 + smps Norton equivalent from the committed fixtures (tests/golden/, SI units),
+    through the product's own per-unit conversion (netio)."""
+    import numpy as np
+    from harmonic_power_flow_b200 import netio
+    import pandas as pd
+    g = os.path.join(ROOT, "tests", "golden")
+    tab = json.load(open(os.path.join(g, "networks.json")))[NET]
+    st = netio.Settings(H_MAX=H_MAX)
+    buses, lines = pd.DataFrame(tab["buses"]), pd.DataFrame(tab["lines"])
+    for col in ("S", "P", "Q"):
+        buses[col] = buses[col].astype(float) / st.BASE_POWER
+    buses["X_sh"] = buses["X_sh"].astype(float) / st.base_impedance
+    for col in ("R", "X"):
+        lines[col] = lines[col].astype(float) / st.base_impedance
+    for col in ("G", "B"):
+        lines[col] = lines[col].astype(float) / st.base_admittance
+    nl = buses.index[buses["type"] == "nonlinear"]
+    m, n = int(min(nl)), len(buses)
+    c = int((buses.type == "PV").sum()) + 1
+    dev = np.load(os.path.join(g, "ne_devices.npz"))
+    freqs = np.array(st.HARMONICS_FREQ)
+    col = np.searchsorted(dev["smps__freqs"], freqs)
+    row = np.searchsorted(dev["smps__Y_N_c_rowfreq"], freqs)
+    net = netio.pack_network(buses, lines, m, n, c, st.HARMONICS)
+    net.devices = ["smps"]
+    net.dev_of_nl_bus = np.zeros(n - m, np.int32)
+    net.coupled = True
+    net.Y_N = np.ascontiguousarray((dev["smps__Y_N_c"][np.ix_(row, col)] / st.base_admittance)[None])
+    net.I_N = np.ascontiguousarray(np.repeat((dev["smps__I_N_c"][col] / st.base_current)[None], n - m, 0))
+    return net
+
+
+def config_dict(n_gpus):
+    return {"workload": "BASELINE configs[2]: net3 coupled (smps_NE), fundamental + odd harmonics <= 25 "
+                        "(N=101), randomised load/spectrum scenarios (P,Q x U(0.9,1.1), I_N x U(0.95,1.05) "
+                        "e^{jU(-0.02,0.02)}), thresh 1e-6/1e-4, caps 30/50",
+            "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n_gpus,
+            "parallelism": "scenario-sharded x%d, no data-path collective" % n_gpus,
+            "cache": "L2 flushed (256 MiB write) between timed steps"}
+
+
+# ------------------------------------------------------------------------------- CPU arm
+_W = {}
+
+
+def _cpu_init():
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hpf_oracle as O
+    from harmonic_power_flow_b200 import scenarios
+    on = O.net_from_golden(os.path.join(ROOT, "tests", "golden"), NET, H_MAX, COUPLED)
+    _W.update(O=O, on=on, Y=O.build_admittance_matrices(on), draw=scenarios.draw_scenario)
+
+
+def _cpu_worker(args):
+    lo, hi, seed0 = args
+    O, on, Y = _W["O"], _W["on"], _W["Y"]
+    conv = iters = 0
+    for s in range(lo, hi):
+        P, Q, I_N = _W["draw"](seed0 + s, on.P, on.Q, on.I_N, SPREAD)
+        o = O.hpf(on, P=P, Q=Q, I_N=I_N, Y=Y)
+        conv += int(o["status"] == 0)
+        iters += o["n_iter_h"]
+    return conv, iters
+
+
+class CpuPool:
+    """Oracle port (numpy + SuperLU step, like the reference) fanned out over the host cores:
+    one worker process per core, network/Y(h) set up once per worker (outside the timing),
+    scenarios split evenly."""
+
+    def __init__(self, procs):
+        from multiprocessing import get_context
+        self.procs = procs
+        self.pool = get_context("fork").Pool(procs, initializer=_cpu_init)
+        self.pool.map(_cpu_worker, [(0, 1, 0)] * procs)          # imports + first-call warm-up
+
+    def solve(self, n_scen, seed0=0):
+        chunk = max(1, n_scen // (self.procs * 4))
+        jobs = [(lo, min(n_scen, lo + chunk), seed0) for lo in range(0, n_scen, chunk)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+        return sum(r[0] for r in res), sum(r[1] for r in res), dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = 256 * cores           # ~12 ms per solve per core -> ~3 s per step
+    pool = CpuPool(cores)
+    for _ in range(a.warmup):
+        pool.solve(min(per_step, 16 * cores))
+    conv = iters = 0
+    dt = 0.0
+    for k in range(a.steps):
+        c_, i_, d_ = pool.solve(per_step, seed0=k * per_step)
+        conv += c_; iters += i_; dt += d_
+    pool.close()
+    v = conv / dt
+    sample = "%d scenarios per step x %d steps of the same seeded workload, %d worker processes" % (
+        per_step, a.steps, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(a.gpus),
+            "us_per_nr_iteration": dt * 1e6 * cores / max(iters, 1),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "oracle/hpf_oracle.py: numpy restatement of the reference solve path "
+                                     "(SuperLU step like the reference); the reference's own pandas code "
+                                     "measured 0.78 solves/s/core in the build container (BASELINE.md)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names)
+                   if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def measure_fp64_peak(torch, dev):
+    """FP64 denominator: cuBLAS DGEMM 8192^3 (uses the DMMA path) - MEASURED_PEAKS.json has no
+    FP64 figure.  Burst (best of 5) in TFLOP/s."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2 * n ** 3 / best / 1e9
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from harmonic_power_flow_b200 import BatchSolver, scenarios
+    from harmonic_power_flow_b200 import dist as hdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_pool = None
+    if world == 1 and not a.no_cpu:        # fork the CPU workers BEFORE the CUDA context exists
+        cpu_pool = CpuPool(os.cpu_count() or 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if a.gpus != world:
+        a.gpus = world
+
+    net = load_net()
+    sol = BatchSolver(net, local)
+    B = a.batch
+    P, Q, I_N = scenarios.make_batch(net, B, SPREAD, seed0=rank * B, exact_prefix=256)
+    hP = torch.as_tensor(P).pin_memory(); hQ = torch.as_tensor(Q).pin_memory()
+    hI = torch.as_tensor(I_N).pin_memory()
+    dP, dQ, dI = sol.prepare(hP, hQ, hI)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    N = sol.N
+    n, H, q, m, c = net.n, net.H, net.q, net.m, net.c
+    Nf = 2 * n - 1 - c
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) ----
+    out = None
+    for _ in range(a.warmup):
+        out = sol.solve(dP, dQ, dI, out=out)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    l0 = sol.launch_count
+    ev = []
+    t_wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = sol.solve(dP, dQ, dI, out=out); e1.record()
+        ev.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = sol.launch_count - l0
+    ms = sum(x.elapsed_time(y) for x, y in ev)
+    clk = clocks.stop()
+    conv = int((out.status == 0).sum().item())
+    it_h = out.n_iter_h.double().sum().item()
+    it_f = out.n_iter_f.double().sum().item()
+
+    # ---- end to end through the host-buffer C-ABI entry point (e2e) ----
+    npP, npQ, npI = hP.numpy(), hQ.numpy(), hI.numpy()
+    for _ in range(max(1, a.warmup - 1)):
+        r = sol.solve_host(npP, npQ, npI)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        if world == 1:
+            r = sol.solve_host(npP, npQ, npI)
+        else:
+            # shard in (pinned H2D), solve, the single collective of the path (final NCCL gather
+            # of flags + results), then this rank's results back to the host
+            res = sol.solve(hP.to(dev, non_blocking=True), hQ.to(dev, non_blocking=True),
+                            hI.to(dev, non_blocking=True))
+            gathered = hdist.gather_result(res, B * world)
+            r = res.to_host()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    conv_e2e = int((r["status"] == 0).sum())
+    h2d = npP.nbytes + npQ.nbytes + npI.nbytes
+    d2h = sum(r[k].nbytes for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status"))
+
+    # ---- standalone kernels against the HBM roofline (rank 0) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks \
+        else (6650.0, "fallback (B200_PROFILING.md)")
+    kernels = []
+    fp64_peak = None
+    if rank == 0:
+        def timed(fn, reps=5):
+            fn(); torch.cuda.synchronize()
+            tot = 0.0
+            for _ in range(reps):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            return tot / reps
+        raw = sol.solve(dP, dQ, dI, raw=True, max_iter_h=3, want_I_inj=False)   # a mid-iteration state
+        Vm, Va = raw.V_m, raw.V_a
+        t_mis = timed(lambda: sol.mismatch(Vm, Va, dP, dQ, dI))
+        by_mis = 16 * n * H + 8 * N + 16 * q * H + 16 * (m - 1) + 8
+        kernels.append({"kernel": "mismatch_tile_kernel", "bound": "hbm", "ms": t_mis,
+                        "achieved": by_mis * B / t_mis / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": by_mis * B / t_mis / 1e6 / hbm_peak, "bytes_per_scenario": by_mis})
+        Bj = min(B, 16384)
+        J = sol.jacobian(Vm[:, :, :Bj].contiguous(), Va[:, :, :Bj].contiguous())
+        Vmj, Vaj = Vm[:, :, :Bj].contiguous(), Va[:, :, :Bj].contiguous()
+        t_jac = timed(lambda: sol.jacobian(Vmj, Vaj, out=J))
+        by_jac = 8 * N * N + 16 * n * H
+        kernels.append({"kernel": "jacobian_kernel", "bound": "hbm", "ms": t_jac, "batch": Bj,
+                        "achieved": by_jac * Bj / t_jac / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": by_jac * Bj / t_jac / 1e6 / hbm_peak, "bytes_per_scenario": by_jac})
+        f, _ = sol.mismatch(Vmj, Vaj, dP[:, :Bj].contiguous(), dQ[:, :Bj].contiguous(), dI[:, :, :Bj].contiguous())
+        t_lu = timed(lambda: sol.lu_solve(J, f), reps=3)
+        fl_lu = 2.0 / 3.0 * N ** 3 + 2.0 * N * N
+        del J
+        fp64_peak = measure_fp64_peak(torch, dev)
+        kernels.append({"kernel": "lu_solve_kernel", "bound": "fp64", "ms": t_lu, "batch": Bj,
+                        "achieved": fl_lu * Bj / t_lu / 1e9, "peak": fp64_peak, "unit": "TFLOP/s",
+                        "frac": fl_lu * Bj / t_lu / 1e9 / fp64_peak, "flops_per_scenario": fl_lu})
+
+    # ---- reduce over ranks ----
+    vals = torch.tensor([ms, t_e2e, float(conv), float(conv_e2e), it_h, it_f, t_wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    else:
+        mx, sm = vals, vals
+    ms_max, e2e_max = mx[0].item(), mx[1].item()
+    conv_tot, conv_e2e_tot, it_h_tot, it_f_tot = sm[2].item(), sm[3].item(), sm[4].item(), sm[5].item()
+
+    if rank == 0:
+        value = conv_tot * a.steps / (ms_max / 1e3)
+        e2e_v = conv_e2e_tot * a.steps / e2e_max
+        # algorithmic FP64 work of one launch of the fused kernel (DESIGN.md "Roofline accounting")
+        fl_iter = 8 * (H * n * n + q * H * H + (m - 1) * n) + 16 * (H * n * n + q * H * H) + \
+            2.0 / 3.0 * N ** 3 + 2.0 * N * N
+        fl_f = 24 * n * n + 2.0 / 3.0 * Nf ** 3 + 2.0 * Nf * Nf
+        flops = (it_h / 1.0) * fl_iter + it_f * fl_f              # this rank's launch
+        t_kernel = ms / a.steps / 1e3
+        ach = flops / t_kernel / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(world),
+                "converged_fraction": conv_tot / (B * world),
+                "mean_nr_iterations": {"fundamental": it_f_tot / (B * world), "harmonic": it_h_tot / (B * world)},
+                "us_per_nr_iteration": (ms_max / a.steps) * 1e3 / max(it_h / 1.0, 1.0),
+                "gpu_launches": int(launches),
+                "wall_s_timed_region": t_wall,
+                "clocks": clk,
+                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_max / a.steps * 1e3,
+                        "path": "BatchSolver.solve_host -> hpf_solve_host (C ABI, host buffers)"
+                                + (" + NCCL all_gather of flags and results" if world > 1 else "")},
+                "roofline": {"kernel": "solve_kernel<false> (fused fundamental + harmonic Newton)",
+                             "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": (ach / fp64_peak) if fp64_peak else None, "traffic": None,
+                             "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (no FP64 figure "
+                                            "in MEASURED_PEAKS.json)",
+                             "flops_per_nr_iteration": fl_iter},
+                "roofline_kernels": kernels, "hbm_peak_source": hbm_src}
+        if cpu_pool is not None:
+            cores = cpu_pool.procs
+            nscen = 1024 * cores
+            c_, i_, d_ = cpu_pool.solve(nscen)
+            cpu_pool.close()
+            line["cpu_baseline"] = {
+                "value": c_ / d_, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "first %d scenarios of the same seeded workload, %d worker processes, %.1f s" % (
+                    nscen, cores, d_),
+                "us_per_nr_iteration_per_core": d_ * 1e6 * cores / max(i_, 1)}
+        print(json.dumps(line))
+    sol.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="scenarios per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

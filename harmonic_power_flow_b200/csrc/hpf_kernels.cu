@@ -622,6 +622,8 @@ struct hpf_handle {
     int* d_counter = nullptr;
     double* d_work = nullptr;
     size_t work_doubles = 0;
+    double* d_io = nullptr;       // staging buffers of hpf_solve_host (grow-only)
+    size_t io_doubles = 0;
     long long launches = 0;
     std::string err;
 };
@@ -790,7 +792,7 @@ int hpf_destroy(hpf_t* h) {
     cudaDeviceSynchronize();
     cudaFree(h->d_harm); cudaFree(h->d_from); cudaFree(h->d_to); cudaFree(h->d_devof);
     cudaFree(h->d_R); cudaFree(h->d_X); cudaFree(h->d_G); cudaFree(h->d_B); cudaFree(h->d_Xsh);
-    cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work);
+    cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work); cudaFree(h->d_io);
     delete h;
     return HPF_OK;
 }
@@ -917,13 +919,16 @@ int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const doub
     CK(cudaSetDevice(h->device));
     const size_t n = h->n, H = h->H, q = h->q, Bs = (size_t)B;
     const size_t nP = n * Bs, nI = 2 * q * H * Bs, nV = n * H * Bs;
-    // one device allocation: P, Q, I_N | V_m, V_a, I_inj, err_h | n_iter_f, n_iter_h, status
-    const size_t nd = 2 * nP + nI + 2 * nV + nI + Bs;
-    double* d = nullptr;
-    int* di = nullptr;
-    CK(cudaMalloc((void**)&d, nd * sizeof(double)));
-    cudaError_t e = cudaMalloc((void**)&di, 3 * Bs * sizeof(int));
-    if (e != cudaSuccess) { cudaFree(d); return fail(h, HPF_E_CUDA, cudaGetErrorString(e)); }
+    // one grow-only device staging area: P, Q, I_N | V_m, V_a, I_inj, err_h | 3 int arrays
+    const size_t nd = 2 * nP + nI + 2 * nV + nI + Bs + (3 * Bs + 1) / 2 + 2;
+    if (nd > h->io_doubles) {
+        if (h->d_io) { cudaFree(h->d_io); h->d_io = nullptr; h->io_doubles = 0; }
+        CK(cudaMalloc((void**)&h->d_io, nd * sizeof(double)));
+        h->io_doubles = nd;
+    }
+    double* d = h->d_io;
+    int* di = reinterpret_cast<int*>(d + 2 * nP + nI + 2 * nV + nI + Bs);
+    cudaError_t e;
     double *dP = d, *dQ = dP + nP, *dI = dQ + nP, *dVm = dI + nI, *dVa = dVm + nV, *dInj = dVa + nV,
            *dErr = dInj + nI;
     cudaStream_t st = nullptr;
@@ -944,8 +949,6 @@ int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const doub
     if (!rc && (e = cudaMemcpyAsync(status, di + 2 * Bs, Bs * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
     e = cudaStreamSynchronize(st);
     if (!rc && e != cudaSuccess) bail(e);
-    cudaFree(d);
-    cudaFree(di);
     return rc;
 }
 
