@@ -17,6 +17,7 @@
 
 #include "../../include/hpf_b200.h"
 #include "hpf_device.cuh"
+#include "hpf_structured.cuh"
 
 #define HPF_THREADS 256
 #define HPF_TILE 32          // scenarios per CTA in the tile kernels
@@ -296,6 +297,7 @@ solve_kernel(const DevNet net, const SolveArgs a) {
                 a.V_m[t * B + b] = s.Vm[t];
                 a.V_a[t * B + b] = s.Va[t];
             }
+            if (tid == 0 && a.status) a.status[b] = status;
             continue;
         }
 
@@ -624,6 +626,10 @@ struct hpf_handle {
     size_t work_doubles = 0;
     double* d_io = nullptr;       // staging buffers of hpf_solve_host (grow-only)
     size_t io_doubles = 0;
+    // structured strategy: 0 = not set up yet, 1 = ready, -1 = not available for this network
+    int struct_state = 0;
+    double2 *d_Ainv = nullptr, *d_Gz = nullptr;
+    double pivot_min = 0.0, pivot_max = 0.0;
     long long launches = 0;
     std::string err;
 };
@@ -746,6 +752,98 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     return HPF_OK;
 }
 
+// ---- structured strategy: setup (once per network) and launches -----------------------
+static StructNet structnet(const hpf_t* h) {
+    StructNet s;
+    s.nZ = h->n * h->H - h->m;
+    s.nx = (h->m - 1) + (h->m - h->c);
+    s.Ainv = h->d_Ainv;
+    s.G = h->d_Gz;
+    return s;
+}
+
+static int ensure_struct(hpf_t* h, cudaStream_t st) {
+    if (h->struct_state != 0) return HPF_OK;
+    h->struct_state = -1;
+    const DevNet net = devnet(h);
+    const int nZ = net.nH - net.m;
+    if (nZ < 1 || nZ > (HPF_ST_THREADS / 32) * HPF_ST_R * HPF_ST_MAXPASS) return HPF_OK;
+    if (harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q) > (size_t)h->smem_optin) return HPF_OK;
+    if (fund_tile_doubles_per_warp(net.n, net.Nf) * sizeof(double) > (size_t)h->smem_optin) return HPF_OK;
+    double2* AZF = nullptr;
+    int* ipiv = nullptr;
+    double* pr = nullptr;
+    cudaFree(h->d_Ainv); cudaFree(h->d_Gz); h->d_Ainv = nullptr; h->d_Gz = nullptr;
+    CK(cudaMalloc((void**)&h->d_Ainv, (size_t)nZ * nZ * sizeof(double2)));
+    CK(cudaMalloc((void**)&h->d_Gz, (size_t)nZ * net.m * sizeof(double2)));
+    CK(cudaMalloc((void**)&AZF, (size_t)nZ * net.m * sizeof(double2)));
+    CK(cudaMalloc((void**)&ipiv, (size_t)(nZ + 2) * sizeof(int)));
+    CK(cudaMalloc((void**)&pr, 2 * sizeof(double)));
+    struct_assemble_kernel<<<64, 256, 0, st>>>(net, h->d_Ainv, AZF);
+    cinv_gj_kernel<<<1, 1024, 0, st>>>(nZ, h->d_Ainv, ipiv, ipiv + nZ, pr);
+    struct_G_kernel<<<(nZ * net.m + 127) / 128, 128, 0, st>>>(nZ, net.m, h->d_Ainv, AZF, h->d_Gz);
+    h->launches += 3;
+    int info = -1;
+    double prh[2] = {0.0, 0.0};
+    cudaError_t e = cudaMemcpyAsync(&info, ipiv + nZ, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(prh, pr, sizeof(prh), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(AZF); cudaFree(ipiv); cudaFree(pr);
+    if (e != cudaSuccess) return fail(h, HPF_E_CUDA, std::string("structured setup: ") + cudaGetErrorString(e));
+    h->pivot_min = prh[0]; h->pivot_max = prh[1];
+    // usable when the inversion met no zero pivot and the pivots span < 1e12 (well conditioned)
+    if (info == 0 && prh[0] > 0.0 && prh[1] / prh[0] < 1e12) h->struct_state = 1;
+    return HPF_OK;
+}
+
+static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, const double* I_N,
+                            double thresh_f, int max_f, double thresh_h, int max_h, int flags,
+                            double* V_m, double* V_a, double* I_inj, int* n_iter_f, int* n_iter_h,
+                            double* err_h, int* status, cudaStream_t st) {
+    const DevNet net = devnet(h);
+    const StructNet sn = structnet(h);
+    // fundamental stage: one lane per scenario
+    {
+        const size_t per_warp = fund_tile_doubles_per_warp(net.n, net.Nf) * sizeof(double);
+        int warps = 4;
+        while (warps > 1 && per_warp * warps > (size_t)h->smem_optin / 2) warps >>= 1;
+        const size_t smem = per_warp * warps;
+        CK(cudaFuncSetAttribute(fund_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fund_tile_kernel, warps * 32, smem));
+        if (occ < 1) return fail(h, HPF_E_UNSUPPORTED, "hpf_solve: fundamental tile kernel does not fit");
+        FundTileArgs fa;
+        fa.B = B; fa.P = P; fa.Q = Q; fa.thresh_f = thresh_f; fa.max_f = max_f;
+        fa.V_m = V_m; fa.V_a = V_a; fa.n_iter_f = n_iter_f; fa.status = status;
+        const long long tiles = ((long long)B + HPF_T - 1) / HPF_T;
+        long long grid = (tiles + warps - 1) / warps;
+        if (grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
+        fund_tile_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(net, fa);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    // harmonic stage
+    {
+        const size_t smem = harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q);
+        int occ = 0;
+        int rc = prep_kernel(h, harm_tile_kernel, smem, "hpf_solve", &occ, HPF_ST_THREADS);
+        if (rc) return rc;
+        HarmTileArgs ha;
+        ha.B = B; ha.flags = flags; ha.step_only = 0; ha.P = P; ha.Q = Q; ha.I_N = (const double2*)I_N;
+        ha.thresh_h = thresh_h; ha.max_h = max_h; ha.V_m = V_m; ha.V_a = V_a; ha.I_inj = (double2*)I_inj;
+        ha.n_iter_h = n_iter_h; ha.status = status; ha.err_h = err_h; ha.work_counter = h->d_counter;
+        ha.dx_out = nullptr;
+        CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
+        const long long tiles = ((long long)B + HPF_T - 1) / HPF_T;
+        long long grid = (long long)occ * h->sm_count;
+        if (grid > tiles) grid = tiles;
+        harm_tile_kernel<<<(unsigned)grid, HPF_ST_THREADS, smem, st>>>(net, sn, ha);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    return HPF_OK;
+}
+
 extern "C" {
 
 int hpf_abi_version(void) { return HPF_ABI_VERSION; }
@@ -792,7 +890,7 @@ int hpf_destroy(hpf_t* h) {
     cudaDeviceSynchronize();
     cudaFree(h->d_harm); cudaFree(h->d_from); cudaFree(h->d_to); cudaFree(h->d_devof);
     cudaFree(h->d_R); cudaFree(h->d_X); cudaFree(h->d_G); cudaFree(h->d_B); cudaFree(h->d_Xsh);
-    cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work); cudaFree(h->d_io);
+    cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work); cudaFree(h->d_io); cudaFree(h->d_Ainv); cudaFree(h->d_Gz);
     delete h;
     return HPF_OK;
 }
@@ -823,6 +921,7 @@ int hpf_set_network(hpf_t* h, int n, int m, int c, int H, const int* harmonics, 
     h->have_net = true;
     h->have_Y = false;
     h->have_dev = false;
+    h->struct_state = 0;
     return HPF_OK;
 }
 
@@ -841,6 +940,7 @@ int hpf_set_devices(hpf_t* h, int n_dev, int coupled, const double* Y_N, const i
     CK(upload(&h->d_YN, (const double2*)Y_N, per * (size_t)(n_dev > 0 ? n_dev : 0)));
     CK(upload(&h->d_devof, dev_of_nl_bus, (size_t)h->q));
     h->have_dev = true;
+    h->struct_state = 0;
     return HPF_OK;
 }
 
@@ -858,6 +958,7 @@ int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
         CK(cudaMemcpyAsync(Y_out, h->d_Y, (size_t)h->H * h->n * h->n * sizeof(double2),
                            cudaMemcpyDeviceToDevice, st));
     h->have_Y = true;
+    h->struct_state = 0;
     return HPF_OK;
 }
 
@@ -868,6 +969,7 @@ int hpf_set_Y(hpf_t* h, const double* Y) {
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpy(h->d_Y, Y, (size_t)h->H * h->n * h->n * sizeof(double2), cudaMemcpyHostToDevice));
     h->have_Y = true;
+    h->struct_state = 0;
     return HPF_OK;
 }
 
@@ -899,8 +1001,65 @@ int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I
               int max_iter_f, double thresh_h, int max_iter_h, int flags, double* V_m, double* V_a,
               double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status,
               double* err_hist_f, double* err_hist_h, void* stream) {
+    // default strategy: structured Newton step; dense LU when forced, when the per-iteration
+    // error history is wanted, or when the network does not admit the structured set-up
+    if (h && !(flags & HPF_SOLVE_DENSE) && !err_hist_f && !err_hist_h && B > 0) {
+        int rc = ready(h, "hpf_solve", true);
+        if (rc) return rc;
+        if (!P || !Q || !V_m || !V_a || !n_iter_f || !n_iter_h || !err_h || !status || (h->q > 0 && !I_N))
+            return fail(h, HPF_E_INVALID, "hpf_solve: NULL buffer");
+        CK(cudaSetDevice(h->device));
+        rc = ensure_struct(h, (cudaStream_t)stream);
+        if (rc) return rc;
+        if (h->struct_state == 1)
+            return solve_structured(h, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags,
+                                    V_m, V_a, I_inj, n_iter_f, n_iter_h, err_h, status, (cudaStream_t)stream);
+    }
     return solve_common(h, 0, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a,
                         I_inj, n_iter_f, n_iter_h, err_h, nullptr, status, err_hist_f, err_hist_h, stream);
+}
+
+int hpf_struct_info(hpf_t* h, int* available, int* nZ, double* pivot_min, double* pivot_max) {
+    int rc = ready(h, "hpf_struct_info", true);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    rc = ensure_struct(h, nullptr);
+    if (rc) return rc;
+    if (available) *available = h->struct_state == 1 ? 1 : 0;
+    if (nZ) *nZ = h->n * h->H - h->m;
+    if (pivot_min) *pivot_min = h->pivot_min;
+    if (pivot_max) *pivot_max = h->pivot_max;
+    return HPF_OK;
+}
+
+int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const double* P,
+                    const double* Q, const double* I_N, double* dx, void* stream) {
+    int rc = ready(h, "hpf_newton_step", true);
+    if (rc) return rc;
+    if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_newton_step: B < 0");
+    if (!V_m || !V_a || !P || !Q || !dx || (h->q > 0 && !I_N))
+        return fail(h, HPF_E_INVALID, "hpf_newton_step: NULL buffer");
+    CK(cudaSetDevice(h->device));
+    rc = ensure_struct(h, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (h->struct_state != 1)
+        return fail(h, HPF_E_UNSUPPORTED, "hpf_newton_step: structured strategy not available for this network");
+    const DevNet net = devnet(h);
+    const StructNet sn = structnet(h);
+    const size_t smem = harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q);
+    int occ = 0;
+    rc = prep_kernel(h, harm_tile_kernel, smem, "hpf_newton_step", &occ, HPF_ST_THREADS);
+    if (rc) return rc;
+    HarmTileArgs ha;
+    ha.B = B; ha.flags = 0; ha.step_only = 1; ha.P = P; ha.Q = Q; ha.I_N = (const double2*)I_N;
+    ha.thresh_h = 0.0; ha.max_h = 1; ha.V_m = const_cast<double*>(V_m); ha.V_a = const_cast<double*>(V_a);
+    ha.I_inj = nullptr; ha.n_iter_h = nullptr; ha.status = nullptr; ha.err_h = nullptr;
+    ha.work_counter = nullptr; ha.dx_out = dx;
+    const unsigned grid = (unsigned)(((long long)B + HPF_T - 1) / HPF_T);
+    harm_tile_kernel<<<grid, HPF_ST_THREADS, smem, (cudaStream_t)stream>>>(net, sn, ha);
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
 }
 
 int hpf_fund_solve(hpf_t* h, int B, const double* P, const double* Q, double thresh_f, int max_iter_f,

@@ -1,0 +1,760 @@
+// Structured Newton step ("strategy 1") - same Newton-Raphson iteration as HG:536-542, the
+// linear solve of HG:476-479 done by exact block elimination instead of a dense LU of J.
+//
+// Why it is the same step.  The current-balance rows of the harmonic mismatch (HG:326-357)
+// are LINEAR in the complex voltages:  f_I = A V + I_N  with the constant complex operator
+//     A = blockdiag_h Y(h)  -  scatter(Y_N)            (rows/cols: stacked index s = h n + i).
+// Their Jacobian rows (HG:403-446) are therefore  A T,  T = dV/d(theta, V_m) the 2x2-block
+// diagonal polar map  dV = E (dV_m + j V_m dtheta),  E = e^{j theta}.  Only the fundamental
+// power rows of the linear buses (HG:451-467) depend on the state.  Partition the stacked
+// indices into  F = {h = 1, linear buses}  (power rows, polar unknowns x_F) and
+// Z = everything else (current rows, full complex unknowns u_Z).  J dx = -f becomes
+//     A_ZZ u_Z + A_ZF T_F x_F = -f_I        =>  u_Z = u0 - G T_F x_F,
+//     u0 = -A_ZZ^{-1} f_I,   G = A_ZZ^{-1} A_ZF      (A_ZZ^{-1}, G: once per network)
+//     J_SF x_F + J_SZ1 T_Z1^{-1} u_Z1 = -f_S        =>  a (2m-1-c)-sized real system for x_F
+// followed by the exact polar conversion  dtheta = Im(conj(E) u)/V_m,  dV_m = Re(conj(E) u).
+// cond(A_ZZ) ~ 1e3..1e5 on the reference networks while cond(J) reaches 2e7..4e9 (the polar
+// scaling), so this step is at least as accurate as an LU of J; round-off differs, exactly
+// as it does between SuperLU and LAPACK.
+//
+// Kernels: struct_assemble / cinv_gj / struct_G (setup, once per network), fund_tile_kernel
+// (fundamental NR, one lane per scenario) and harm_tile_kernel (harmonic NR, 32 scenarios
+// per CTA with lane = scenario; lanes are refilled from a global queue as soon as their
+// scenario finishes because iteration counts differ, 8..34+).
+#pragma once
+#include "hpf_device.cuh"
+
+#define HPF_T 32            // scenarios per tile (= lanes)
+#define HPF_ST_THREADS 256  // 8 warps share a tile
+#define HPF_ST_R 7          // rows of A_ZZ^{-1} per warp pass (register tile)
+#define HPF_ST_MAXPASS 2    // => nZ <= 8 * 7 * 2 = 112
+
+struct StructNet {
+    int nZ, nx;
+    const double2* Ainv;   // [nZ][nZ] row-major
+    const double2* G;      // [nZ][m]
+};
+
+// ---------------------------------------------------------------------------------------
+// setup 1: A_ZZ and A_ZF from Y(h) and Y_N
+__global__ void struct_assemble_kernel(const DevNet net, double2* __restrict__ AZZ,
+                                       double2* __restrict__ AZF) {
+    const int n = net.n, m = net.m, H = net.H, nZ = net.nH - m;
+    const size_t total = (size_t)nZ * (nZ + m);
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t / (nZ + m)), cc = (int)(t - (size_t)r * (nZ + m));
+        const int s = r + m, h = s / n, i = s - h * n;
+        const int sc = (cc < nZ) ? cc + m : cc - nZ;      // column stacked index (Z first, then F)
+        const int hc = sc / n, jc = sc - hc * n;
+        double2 v = make_double2(0.0, 0.0);
+        if (hc == h) v = net.Y[((size_t)h * n + i) * n + jc];
+        if (i >= m && jc == i) {
+            const int dev = net.dev_of_nl[i - m];
+            if (net.coupled) v = csub(v, net.YN[((size_t)dev * H + h) * H + hc]);
+            else if (hc == h) v = csub(v, net.YN[(size_t)dev * H + h]);
+        }
+        if (cc < nZ) AZZ[(size_t)r * nZ + cc] = v;
+        else AZF[(size_t)r * m + (cc - nZ)] = v;
+    }
+}
+
+__device__ __forceinline__ double2 crecip(double2 a) {
+    // 1 / a, scaled (Smith) to avoid overflow
+    if (fabs(a.x) >= fabs(a.y)) {
+        const double r = a.y / a.x, d = 1.0 / (a.x + a.y * r);
+        return make_double2(d, -r * d);
+    }
+    const double r = a.x / a.y, d = 1.0 / (a.y + a.x * r);
+    return make_double2(r * d, -d);
+}
+
+// setup 2: in-place Gauss-Jordan inverse with partial (row) pivoting, complex, one CTA,
+// matrix in global memory (L2 resident).  info[0] = 0 or k+1 (zero pivot);
+// info[1..2] = min / max pivot modulus as doubles (a cheap conditioning indicator).
+__global__ void __launch_bounds__(1024)
+cinv_gj_kernel(int n, double2* __restrict__ A, int* __restrict__ ipiv, int* __restrict__ info,
+               double* __restrict__ pivrange) {
+    __shared__ double redv[33];
+    __shared__ int redi[33];
+    __shared__ double2 spiv;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    double pmin = CUDART_INF, pmax = 0.0;
+    if (tid == 0) info[0] = 0;
+    for (int k = 0; k < n; ++k) {
+        __syncthreads();
+        double best = -1.0;
+        int bi = k;
+        for (int i = k + tid; i < n; i += blockDim.x) {
+            const double2 a = A[(size_t)i * n + k];
+            const double v = hypot(a.x, a.y);
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            best = (lane < nw) ? redv[lane] : -1.0;
+            bi = (lane < nw) ? redi[lane] : 0x7fffffff;
+            for (int o = 16; o; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                redv[32] = best; redi[32] = bi;
+                ipiv[k] = bi;
+                if (!(best > 0.0) || !(best < CUDART_INF)) { if (info[0] == 0) info[0] = k + 1; }
+            }
+        }
+        __syncthreads();
+        const int p = redi[32];
+        pmin = fmin(pmin, redv[32]); pmax = fmax(pmax, redv[32]);
+        if (p != k)
+            for (int j = tid; j < n; j += blockDim.x) {
+                const double2 t = A[(size_t)k * n + j];
+                A[(size_t)k * n + j] = A[(size_t)p * n + j];
+                A[(size_t)p * n + j] = t;
+            }
+        __syncthreads();
+        if (tid == 0) spiv = crecip(A[(size_t)k * n + k]);
+        __syncthreads();
+        const double2 pinv = spiv;
+        for (int j = tid; j < n; j += blockDim.x) {
+            const double2 a = (j == k) ? make_double2(1.0, 0.0) : A[(size_t)k * n + j];
+            A[(size_t)k * n + j] = cmul(a, pinv);
+        }
+        __syncthreads();
+        // eliminate column k from every other row; element (i, j): a_ij -= a_ik * a_kj,
+        // with a_ik first replaced by 0 (its inverse-column value becomes -a_ik * a_kk).
+        // Pass 1 caches the multipliers (column k) in place of nothing: read them on the fly,
+        // but column k itself must be updated LAST (it is the multiplier source).
+        for (size_t t = tid; t < (size_t)n * (n - 1); t += blockDim.x) {
+            const int i = (int)(t / (n - 1));
+            int j = (int)(t - (size_t)i * (n - 1));
+            if (j >= k) ++j;                      // skip column k in this pass
+            if (i == k) continue;
+            const double2 f = A[(size_t)i * n + k];
+            const double2 akj = A[(size_t)k * n + j];
+            A[(size_t)i * n + j] = csub(A[(size_t)i * n + j], cmul(f, akj));
+        }
+        __syncthreads();
+        const double2 akk = A[(size_t)k * n + k];
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x) {
+            if (i == k) continue;
+            const double2 f = A[(size_t)i * n + k];
+            A[(size_t)i * n + k] = cneg(cmul(f, akk));
+        }
+    }
+    __syncthreads();
+    for (int k = n - 1; k >= 0; --k) {            // undo the row interchanges on the columns
+        const int p = ipiv[k];
+        if (p != k)
+            for (int i = tid; i < n; i += blockDim.x) {
+                const double2 t = A[(size_t)i * n + k];
+                A[(size_t)i * n + k] = A[(size_t)i * n + p];
+                A[(size_t)i * n + p] = t;
+            }
+        __syncthreads();
+    }
+    if (tid == 0) { pivrange[0] = pmin; pivrange[1] = pmax; }
+}
+
+// setup 3: G = Ainv * A_ZF
+__global__ void struct_G_kernel(int nZ, int m, const double2* __restrict__ Ainv,
+                                const double2* __restrict__ AZF, double2* __restrict__ G) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nZ * m) return;
+    const int r = t / m, j = t - r * m;
+    double2 acc = make_double2(0.0, 0.0);
+    for (int k = 0; k < nZ; ++k) acc = cadd(acc, cmul(Ainv[(size_t)r * nZ + k], AZF[(size_t)k * m + j]));
+    G[t] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-lane dense solve of a small augmented real system M [nx][nx+1] stored with stride
+// HPF_T (element (r, c) of lane l at M[(r*(nx+1)+c)*HPF_T + l] -> bank = lane, conflict
+// free).  Gaussian elimination with partial pivoting, each lane pivots on its own data.
+// The solution overwrites column nx.  Returns nonzero for a zero / non-finite pivot.
+__device__ __forceinline__ int lane_gauss_solve(double* M, const int nx, const int lane) {
+    const int w = nx + 1;
+    int bad = 0;
+#define MM(r, c) M[((r) * w + (c)) * HPF_T + lane]
+    for (int k = 0; k < nx; ++k) {
+        int p = k;
+        double best = fabs(MM(k, k));
+        for (int i = k + 1; i < nx; ++i) {
+            const double v = fabs(MM(i, k));
+            if (v > best) { best = v; p = i; }
+        }
+        if (!(best > 0.0) || !(best < CUDART_INF)) bad = 1;
+        if (p != k)
+            for (int c = k; c <= nx; ++c) {
+                const double t = MM(k, c);
+                MM(k, c) = MM(p, c);
+                MM(p, c) = t;
+            }
+        const double r = 1.0 / MM(k, k);
+        for (int i = k + 1; i < nx; ++i) {
+            const double l = MM(i, k) * r;
+            for (int c = k + 1; c <= nx; ++c) MM(i, c) -= l * MM(k, c);
+        }
+    }
+    for (int k = nx - 1; k >= 0; --k) {
+        double s = MM(k, nx);
+        for (int c = k + 1; c < nx; ++c) s -= MM(k, c) * MM(c, nx);
+        MM(k, nx) = s / MM(k, k);
+    }
+#undef MM
+    return bad;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fundamental Newton-Raphson (HG:244-275), one lane per scenario, warps independent.
+// Writes the fundamental solution into rows 0..n-1 of V_m / V_a [H, n, B] (the harmonic
+// kernel picks it up there), n_iter_f and a preliminary status.
+struct FundTileArgs {
+    int B;
+    const double *P, *Q;
+    double thresh_f;
+    int max_f;
+    double *V_m, *V_a;
+    int *n_iter_f, *status;
+};
+
+__host__ __device__ inline size_t fund_tile_doubles_per_warp(int n, int Nf) {
+    // Vm, Va, Vre, Vim, Ere, Eim [n]; I1 [n] complex; P, Q [n]; M [Nf][Nf+1]
+    return (size_t)(6 * n + 2 * n + 2 * n + Nf * (Nf + 1)) * HPF_T;
+}
+
+__global__ void __launch_bounds__(128)
+fund_tile_kernel(const DevNet net, const FundTileArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = net.n, c = net.c, Nf = net.Nf;
+    const size_t B = (size_t)a.B;
+    double* base = smem + (size_t)warp * fund_tile_doubles_per_warp(n, Nf);
+    double* Vm = base;            double* Va = Vm + n * HPF_T;
+    double* Vre = Va + n * HPF_T; double* Vim = Vre + n * HPF_T;
+    double* Ere = Vim + n * HPF_T; double* Eim = Ere + n * HPF_T;
+    double2* I1 = reinterpret_cast<double2*>(Eim + n * HPF_T);
+    double* Pl = reinterpret_cast<double*>(I1 + n * HPF_T);
+    double* Ql = Pl + n * HPF_T;
+    double* M = Ql + n * HPF_T;
+    const int w = Nf + 1;
+    for (size_t tile = (size_t)blockIdx.x * nwarp + warp; tile * HPF_T < B; tile += (size_t)gridDim.x * nwarp) {
+        const size_t b = tile * HPF_T + lane;
+        const bool ok = b < B;
+        const size_t bb = ok ? b : B - 1;
+        for (int i = 0; i < n; ++i) {
+            Pl[i * HPF_T + lane] = a.P[i * B + bb];
+            Ql[i * HPF_T + lane] = a.Q[i * B + bb];
+            Vm[i * HPF_T + lane] = 1.0;
+            Va[i * HPF_T + lane] = 0.0;
+        }
+        int it = 0, status = HPF_ST_CONVERGED;
+        bool running = true;
+        double err = 0.0;
+        for (;;) {
+            // mismatch (HG:195-202)
+            for (int i = 0; i < n; ++i)
+                phasor_one<HPF_T>(i, lane, Vm, Va, Vre, Vim, Ere, Eim, true);
+            for (int i = 0; i < n; ++i) I1[i * HPF_T + lane] = ydotv<HPF_T>(net, 0, i, lane, Vre, Vim);
+            double mx = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double2 v = make_double2(Vre[i * HPF_T + lane], Vim[i * HPF_T + lane]);
+                const double2 sl = cmul(v, cconj(I1[i * HPF_T + lane]));
+                const double fr = sl.x + Pl[i * HPF_T + lane], fi = sl.y + Ql[i * HPF_T + lane];
+                if (i >= 1) {
+                    M[((i - 1) * w + Nf) * HPF_T + lane] = fr;
+                    const double x = fabs(fr);
+                    mx = (x != x || x > mx) ? x : mx;
+                }
+                if (i >= c) {
+                    M[(((n - 1) + i - c) * w + Nf) * HPF_T + lane] = fi;
+                    const double x = fabs(fi);
+                    mx = (x != x || x > mx) ? x : mx;
+                }
+            }
+            if (running) {
+                err = mx;
+                running = (err > a.thresh_f) && (it < a.max_f);
+            }
+            if (!__any_sync(0xffffffffu, running)) break;
+            // Jacobian (HG:205-223) into M[:, 0..Nf-1]
+            for (int r = 0; r < Nf; ++r)
+                for (int cc = 0; cc < Nf; ++cc) M[(r * w + cc) * HPF_T + lane] = 0.0;
+            // per-lane arrays are strided: address element i of array X as X[i*HPF_T + lane]
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) {
+                    const double2 y = ldg2(net.Y + (size_t)i * n + j);
+                    if (i != j && y.x == 0.0 && y.y == 0.0) continue;
+                    const double2 vi = make_double2(Vre[i * HPF_T + lane], Vim[i * HPF_T + lane]);
+                    const double2 ei = make_double2(Ere[i * HPF_T + lane], Eim[i * HPF_T + lane]);
+                    const double2 vj = make_double2(Vre[j * HPF_T + lane], Vim[j * HPF_T + lane]);
+                    const double2 ej = make_double2(Ere[j * HPF_T + lane], Eim[j * HPF_T + lane]);
+                    const double2 i1 = I1[i * HPF_T + lane];
+                    const double2 yv = cmul(y, vj);
+                    const double2 d = (i == j) ? csub(i1, yv) : cneg(yv);
+                    const double2 dA = cmul(cmulj(vi), cconj(d));
+                    double2 dV = cmul(vi, cconj(cmul(y, ej)));
+                    if (i == j) dV = cadd(cmul(ei, cconj(i1)), dV);
+                    const int rr = i - 1, ri = (n - 1) + i - c, ca = j - 1, cv = (n - 1) + j - c;
+                    if (i >= 1) {
+                        if (j >= 1) M[(rr * w + ca) * HPF_T + lane] = dA.x;
+                        if (j >= c) M[(rr * w + cv) * HPF_T + lane] = dV.x;
+                    }
+                    if (i >= c) {
+                        if (j >= 1) M[(ri * w + ca) * HPF_T + lane] = dA.y;
+                        if (j >= c) M[(ri * w + cv) * HPF_T + lane] = dV.y;
+                    }
+                }
+            const int bad = lane_gauss_solve(M, Nf, lane);
+            if (running) {
+                if (bad) status = HPF_ST_SINGULAR;
+                for (int t = 0; t < Nf; ++t) {          // x -= dx  (HG:226-235)
+                    const double dx = M[(t * w + Nf) * HPF_T + lane];
+                    if (t < n - 1) Va[(t + 1) * HPF_T + lane] -= dx;
+                    else Vm[(c + t - (n - 1)) * HPF_T + lane] -= dx;
+                }
+                ++it;
+            }
+        }
+        if (it >= a.max_f) status = HPF_ST_MAXITER;
+        if (err != err) status = HPF_ST_NONFINITE;
+        if (ok) {
+            for (int i = 0; i < n; ++i) {
+                a.V_m[i * B + b] = Vm[i * HPF_T + lane];
+                a.V_a[i * B + b] = Va[i * HPF_T + lane];
+            }
+            a.n_iter_f[b] = it;
+            a.status[b] = status;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Harmonic Newton-Raphson, structured step, 32 scenarios per CTA (lane = scenario).
+struct HarmTileArgs {
+    int B, flags, step_only;
+    const double *P, *Q;
+    const double2* I_N;
+    double thresh_h;
+    int max_h;
+    double *V_m, *V_a;       // in: rows 0..n-1 hold the fundamental solution; out: results
+    double2* I_inj;
+    int *n_iter_h, *status;  // status in: fundamental-stage status
+    double* err_h;
+    int* work_counter;
+    double* dx_out;          // step_only: [N, B] the Newton update dx (x_new = x - dx)
+};
+
+__host__ __device__ inline size_t harm_tile_smem_bytes(int n, int H, int m, int c, int q) {
+    const size_t nH = (size_t)n * H, nZ = nH - m, nx = (size_t)(m - 1) + (m - c);
+    const size_t d = 4 * nH + 2 * nZ + 2 * m + 2 * n + 2 * q * H + 2 * m + nx * (nx + 1) + 2 * m +
+                     (HPF_ST_THREADS / 32) + 2;
+    return d * HPF_T * sizeof(double) + 8 * HPF_T * sizeof(int) + 64;
+}
+
+__global__ void __launch_bounds__(HPF_ST_THREADS)
+harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = HPF_ST_THREADS / 32;
+    const int n = net.n, m = net.m, c = net.c, H = net.H, q = net.q, nH = net.nH;
+    const int nZ = sn.nZ, nx = sn.nx;
+    const size_t B = (size_t)a.B;
+#define AT(X, i) X[(i) * HPF_T + lane]
+    double* p = smem;
+    double* Vm = p;  p += nH * HPF_T;
+    double* Va = p;  p += nH * HPF_T;
+    double* Ere = p; p += nH * HPF_T;
+    double* Eim = p; p += nH * HPF_T;
+    double* Ure = p; p += nZ * HPF_T;      // f_I, then u0, then u_Z (index z = s - m)
+    double* Uim = p; p += nZ * HPF_T;
+    double* FSre = p; p += m * HPF_T;      // power mismatch of buses s < m
+    double* FSim = p; p += m * HPF_T;
+    double* I1re = p; p += n * HPF_T;
+    double* I1im = p; p += n * HPF_T;
+    double* IJre = p; p += q * H * HPF_T;
+    double* IJim = p; p += q * H * HPF_T;
+    double* Pl = p;  p += m * HPF_T;
+    double* Ql = p;  p += m * HPF_T;
+    double* M = p;   p += nx * (nx + 1) * HPF_T;
+    double* UFre = p; p += m * HPF_T;
+    double* UFim = p; p += m * HPF_T;
+    double* red = p; p += NW * HPF_T;
+    double* errv = p; p += HPF_T;
+    double* spare = p; p += HPF_T;
+    int* scen = reinterpret_cast<int*>(p);
+    int* itc = scen + HPF_T;
+    int* stat = itc + HPF_T;
+    int* fnew = stat + HPF_T;
+    int* fdone = fnew + HPF_T;
+    int* fstep = fdone + HPF_T;
+    int* ctl = fstep + HPF_T;              // ctl[0] = exit flag
+    (void)spare;
+
+    // ---- initial fill ----
+    if (warp == 0) {
+        int idx;
+        if (a.step_only) {
+            idx = blockIdx.x * HPF_T + lane;
+        } else {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(a.work_counter, HPF_T);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            idx = base + lane;
+        }
+        scen[lane] = ((size_t)idx < B) ? idx : -1;
+        itc[lane] = 0;
+        fnew[lane] = 1;
+        fdone[lane] = 0;
+        fstep[lane] = 0;
+        if (lane == 0) ctl[0] = 0;
+    }
+    __syncthreads();
+
+    for (;;) {
+        // ---- load new scenarios (rows over warps, lanes gather) ----
+        {
+            const int sc = scen[lane];
+            if (fnew[lane] && sc >= 0) {
+                for (int s = warp; s < nH; s += NW) {
+                    if (a.step_only || s < n) {
+                        AT(Vm, s) = a.V_m[(size_t)s * B + sc];
+                        AT(Va, s) = a.V_a[(size_t)s * B + sc];
+                    } else {
+                        AT(Vm, s) = 0.1;       // flat start of the harmonics (HG:183)
+                        AT(Va, s) = 0.0;
+                    }
+                }
+                for (int s = warp; s < m; s += NW) {
+                    AT(Pl, s) = a.P[(size_t)s * B + sc];
+                    AT(Ql, s) = a.Q[(size_t)s * B + sc];
+                }
+                if (warp == 0) stat[lane] = a.step_only ? 0 : a.status[sc];
+            } else if (fnew[lane] && sc < 0) {
+                for (int s = warp; s < nH; s += NW) { AT(Vm, s) = 1.0; AT(Va, s) = 0.0; }
+                for (int s = warp; s < m; s += NW) { AT(Pl, s) = 0.0; AT(Ql, s) = 0.0; }
+            }
+        }
+        __syncthreads();
+        // ---- P1: unit phasors E = e^{j theta};  V = V_m E = (V_m cos, V_m sin) like HG:403 ----
+        for (int s = warp; s < nH; s += NW) {
+            double sn_, cs_;
+            sincos(AT(Va, s), &sn_, &cs_);
+            AT(Ere, s) = cs_;
+            AT(Eim, s) = sn_;
+        }
+        __syncthreads();
+        // ---- P2: I1 = Y1 V1 and Norton injections ----
+        for (int t = warp; t < n + q * H; t += NW) {
+            if (t < n) {
+                const double2* Yrow = net.Y + (size_t)t * n;
+                double2 acc = make_double2(0.0, 0.0);
+                for (int j = 0; j < n; ++j) {
+                    const double vm = AT(Vm, j);
+                    acc = cadd(acc, cmul(ldg2(Yrow + j), make_double2(vm * AT(Ere, j), vm * AT(Eim, j))));
+                }
+                AT(I1re, t) = acc.x; AT(I1im, t) = acc.y;
+            } else {
+                const int u = t - n, k = u / H, h = u - k * H, bus = m + k;
+                const int dev = net.dev_of_nl[k];
+                const int sc = scen[lane];
+                const double2 in = (sc >= 0) ? a.I_N[(size_t)u * B + sc] : make_double2(0.0, 0.0);
+                double2 acc;
+                if (net.coupled) {
+                    const double2* row = net.YN + ((size_t)dev * H + h) * H;
+                    acc = make_double2(0.0, 0.0);
+                    for (int pp = 0; pp < H; ++pp) {
+                        const int t2 = pp * n + bus;
+                        const double vm = AT(Vm, t2);
+                        acc = cadd(acc, cmul(ldg2(row + pp), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                    }
+                } else {
+                    const int t2 = h * n + bus;
+                    const double vm = AT(Vm, t2);
+                    acc = cmul(ldg2(net.YN + (size_t)dev * H + h), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2)));
+                }
+                AT(IJre, u) = in.x - acc.x; AT(IJim, u) = in.y - acc.y;
+            }
+        }
+        __syncthreads();
+        // ---- P3: mismatch rows (HG:360-388) ----
+        {
+            double mx = 0.0;
+            for (int e = warp; e < nH - 1; e += NW) {
+                const int s = e + 1;
+                double2 f;
+                if (s < m) {
+                    const double vm = AT(Vm, s);
+                    const double2 v = make_double2(vm * AT(Ere, s), vm * AT(Eim, s));
+                    const double2 sl = cmul(v, make_double2(AT(I1re, s), -AT(I1im, s)));
+                    f = make_double2(AT(Pl, s) + sl.x, AT(Ql, s) + sl.y);
+                    AT(FSre, s) = f.x; AT(FSim, s) = f.y;
+                } else {
+                    const int h = s / n, i = s - h * n;
+                    if (h == 0) {
+                        f = make_double2(AT(I1re, i), AT(I1im, i));
+                    } else {
+                        const double2* Yrow = net.Y + ((size_t)h * n + i) * n;
+                        f = make_double2(0.0, 0.0);
+                        for (int j = 0; j < n; ++j) {
+                            const int t2 = h * n + j;
+                            const double vm = AT(Vm, t2);
+                            f = cadd(f, cmul(ldg2(Yrow + j), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                        }
+                    }
+                    if (i >= m) { f.x += AT(IJre, (i - m) * H + h); f.y += AT(IJim, (i - m) * H + h); }
+                    AT(Ure, s - m) = f.x; AT(Uim, s - m) = f.y;
+                }
+                double v1 = fabs(f.x);
+                if (e >= c - 1) {
+                    const double v2 = fabs(f.y);
+                    v1 = (v2 != v2 || v2 > v1) ? v2 : v1;
+                }
+                mx = (v1 != v1 || v1 > mx) ? v1 : mx;
+            }
+            AT(red, warp) = mx;
+        }
+        __syncthreads();
+        // ---- control: who continues, who is finished ----
+        if (warp == 0) {
+            double err = 0.0;
+            bool bad = false;
+            for (int w2 = 0; w2 < NW; ++w2) {
+                const double v = AT(red, w2);
+                bad |= (v != v);
+                err = fmax(err, v);
+            }
+            if (bad) err = CUDART_NAN;
+            const bool active = scen[lane] >= 0;
+            const bool cont = active && (err > a.thresh_h) && (itc[lane] < a.max_h);
+            errv[lane] = err;
+            fstep[lane] = (a.step_only ? active : cont) ? 1 : 0;
+            fdone[lane] = (active && !cont && !a.step_only) ? 1 : 0;
+            const unsigned any = __ballot_sync(0xffffffffu, active);
+            if (lane == 0) ctl[0] = (any == 0u) ? 1 : 0;
+        }
+        __syncthreads();
+        if (ctl[0]) break;
+        // ---- finalize finished lanes: post-processing (HG:547-549) + write-out ----
+        if (fdone[lane]) {
+            const int sc = scen[lane];
+            int bad = 0;
+            for (int s = warp; s < nH; s += NW) {
+                double vm = AT(Vm, s), va = AT(Va, s), r = va;
+                if (!(a.flags & HPF_SOLVE_RAW)) {
+                    if (vm < 0.0) va += CUDART_PI;
+                    const double twopi = 2.0 * CUDART_PI;
+                    r = fmod(va, twopi);
+                    if (r != 0.0) { if (r < 0.0) r += twopi; } else r = 0.0;
+                    if (vm < 0.0) vm = -vm;
+                }
+                if (!(vm == vm) || !(r == r) || fabs(vm) == CUDART_INF) bad = 1;
+                a.V_m[(size_t)s * B + sc] = vm;
+                a.V_a[(size_t)s * B + sc] = r;
+            }
+            if (a.I_inj)
+                for (int u = warp; u < q * H; u += NW)
+                    a.I_inj[(size_t)u * B + sc] = make_double2(AT(IJre, u), AT(IJim, u));
+            if (bad) atomicOr(&stat[lane], 0x100);
+        }
+        // ---- P4: u0 = -Ainv f_I  (register tile of R rows per warp pass) ----
+        {
+            double2 acc[HPF_ST_MAXPASS][HPF_ST_R];
+#pragma unroll
+            for (int ps = 0; ps < HPF_ST_MAXPASS; ++ps) {
+                const int r0 = (ps * NW + warp) * HPF_ST_R;
+#pragma unroll
+                for (int r = 0; r < HPF_ST_R; ++r) acc[ps][r] = make_double2(0.0, 0.0);
+                if (r0 < nZ) {
+                    for (int zc = 0; zc < nZ; ++zc) {
+                        const double2 f = make_double2(AT(Ure, zc), AT(Uim, zc));
+#pragma unroll
+                        for (int r = 0; r < HPF_ST_R; ++r) {
+                            if (r0 + r < nZ) {
+                                const double2 av = ldg2(sn.Ainv + (size_t)(r0 + r) * nZ + zc);
+                                acc[ps][r].x += av.x * f.x - av.y * f.y;
+                                acc[ps][r].y += av.x * f.y + av.y * f.x;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();                       // everyone has finished reading f_I
+#pragma unroll
+            for (int ps = 0; ps < HPF_ST_MAXPASS; ++ps) {
+                const int r0 = (ps * NW + warp) * HPF_ST_R;
+#pragma unroll
+                for (int r = 0; r < HPF_ST_R; ++r)
+                    if (r0 + r < nZ) { AT(Ure, r0 + r) = -acc[ps][r].x; AT(Uim, r0 + r) = -acc[ps][r].y; }
+            }
+        }
+        __syncthreads();
+        // ---- P5: border system for the fundamental unknowns of the linear buses ----
+        if (warp == 0) {
+            const int w = nx + 1, nth = m - 1;
+            for (int t = 0; t < nx * w; ++t) AT(M, t) = 0.0;
+            for (int i = 1; i < m; ++i) {
+                const double vmi = AT(Vm, i);
+                const double2 ei = make_double2(AT(Ere, i), AT(Eim, i));
+                const double2 vi = make_double2(vmi * ei.x, vmi * ei.y);
+                const double2 i1 = make_double2(AT(I1re, i), AT(I1im, i));
+                const double2 jvi = cmulj(vi);
+                const int rr = i - 1, ri = nth + (i - c);
+                const bool has_im = (i >= c);
+                // base entries: derivatives w.r.t. the linear buses' own unknowns (HG:457-467)
+                for (int j = 1; j < m; ++j) {
+                    const double2 y = ldg2(net.Y + (size_t)i * n + j);
+                    const double vmj = AT(Vm, j);
+                    const double2 ej = make_double2(AT(Ere, j), AT(Eim, j));
+                    const double2 vj = make_double2(vmj * ej.x, vmj * ej.y);
+                    const double2 yv = cmul(y, vj);
+                    const double2 d = (i == j) ? csub(i1, yv) : cneg(yv);
+                    const double2 dA = cmul(jvi, cconj(d));
+                    AT(M, rr * w + (j - 1)) += dA.x;
+                    if (has_im) AT(M, ri * w + (j - 1)) += dA.y;
+                    if (j >= c) {
+                        double2 dV = cmul(vi, cconj(cmul(y, ej)));
+                        if (i == j) dV = cadd(cmul(ei, cconj(i1)), dV);
+                        AT(M, rr * w + nth + (j - c)) += dV.x;
+                        if (has_im) AT(M, ri * w + nth + (j - c)) += dV.y;
+                    }
+                }
+                double2 rhs = make_double2(-AT(FSre, i), -AT(FSim, i));
+                // nonlinear buses at the fundamental: eliminated through u_Z1 = u0 - G T_F x_F
+                for (int k = 0; k < q; ++k) {
+                    const int bk = m + k;
+                    const double2 y = ldg2(net.Y + (size_t)i * n + bk);
+                    if (y.x == 0.0 && y.y == 0.0) continue;
+                    const double vmb = AT(Vm, bk);
+                    const double2 eb = make_double2(AT(Ere, bk), AT(Eim, bk));
+                    const double2 vb = make_double2(vmb * eb.x, vmb * eb.y);
+                    const double2 ak = cmul(jvi, cconj(cneg(cmul(y, vb))));    // dS_i/dtheta_b
+                    const double2 vk = cmul(vi, cconj(cmul(y, eb)));           // dS_i/dV_m,b
+                    const double rvm = 1.0 / vmb;
+                    const double2 w0 = cmul(cconj(eb), make_double2(AT(Ure, k), AT(Uim, k)));
+                    const double dth0 = w0.y * rvm, dvm0 = w0.x;
+                    rhs.x -= ak.x * dth0 + vk.x * dvm0;
+                    rhs.y -= ak.y * dth0 + vk.y * dvm0;
+                    for (int j = 1; j < m; ++j) {
+                        const double2 g = ldg2(sn.G + (size_t)k * m + j);
+                        const double vmj = AT(Vm, j);
+                        const double2 ej = make_double2(AT(Ere, j), AT(Eim, j));
+                        const double2 vj = make_double2(vmj * ej.x, vmj * ej.y);
+                        {   // theta_j column: W = G (j V_j)
+                            const double2 ce = cmul(cconj(eb), cmul(g, cmulj(vj)));
+                            const double dth = ce.y * rvm, dvm = ce.x;
+                            AT(M, rr * w + (j - 1)) -= ak.x * dth + vk.x * dvm;
+                            if (has_im) AT(M, ri * w + (j - 1)) -= ak.y * dth + vk.y * dvm;
+                        }
+                        if (j >= c) {   // V_m,j column: W = G E_j
+                            const double2 ce = cmul(cconj(eb), cmul(g, ej));
+                            const double dth = ce.y * rvm, dvm = ce.x;
+                            AT(M, rr * w + nth + (j - c)) -= ak.x * dth + vk.x * dvm;
+                            if (has_im) AT(M, ri * w + nth + (j - c)) -= ak.y * dth + vk.y * dvm;
+                        }
+                    }
+                }
+                AT(M, rr * w + nx) = rhs.x;
+                if (has_im) AT(M, ri * w + nx) = rhs.y;
+            }
+            const int bad = (nx > 0) ? lane_gauss_solve(M, nx, lane) : 0;
+            if (bad && fstep[lane]) atomicOr(&stat[lane], 0x200);
+            AT(UFre, 0) = 0.0; AT(UFim, 0) = 0.0;
+            for (int i = 1; i < m; ++i) {
+                const double dth = AT(M, (i - 1) * w + nx);
+                const double dvm = (i >= c) ? AT(M, (nth + i - c) * w + nx) : 0.0;
+                const double vmi = AT(Vm, i);
+                const double2 ei = make_double2(AT(Ere, i), AT(Eim, i));
+                // u_F = (j V_i) dtheta + E_i dV_m
+                AT(UFre, i) = -(vmi * ei.y) * dth + ei.x * dvm;
+                AT(UFim, i) = (vmi * ei.x) * dth + ei.y * dvm;
+            }
+        }
+        __syncthreads();
+        // ---- P6: u_Z = u0 - G u_F, polar conversion, state update (x_new = x + delta) ----
+        {
+            const bool step = fstep[lane] != 0;
+            const int sc = scen[lane];
+            for (int z = warp; z < nZ; z += NW) {
+                double2 u = make_double2(AT(Ure, z), AT(Uim, z));
+                for (int i = 1; i < m; ++i) {
+                    const double2 g = ldg2(sn.G + (size_t)z * m + i);
+                    u = csub(u, cmul(g, make_double2(AT(UFre, i), AT(UFim, i))));
+                }
+                const int s = z + m;
+                const double2 wv = cmul(make_double2(AT(Ere, s), -AT(Eim, s)), u);
+                const double vm = AT(Vm, s);
+                const double dth = wv.y / vm, dvm = wv.x;
+                if (a.step_only) {
+                    if (sc >= 0) {
+                        a.dx_out[(size_t)(s - 1) * B + sc] = -dth;
+                        a.dx_out[(size_t)((nH - 1) + s - c) * B + sc] = -dvm;
+                    }
+                } else if (step) {
+                    AT(Va, s) += dth;
+                    AT(Vm, s) = vm + dvm;
+                }
+            }
+            if (warp == NW - 1) {
+                const int w = nx + 1, nth = m - 1;
+                for (int i = 1; i < m; ++i) {
+                    const double dth = AT(M, (i - 1) * w + nx);
+                    const double dvm = (i >= c) ? AT(M, (nth + i - c) * w + nx) : 0.0;
+                    if (a.step_only) {
+                        if (sc >= 0) {
+                            a.dx_out[(size_t)(i - 1) * B + sc] = -dth;
+                            if (i >= c) a.dx_out[(size_t)((nH - 1) + i - c) * B + sc] = -dvm;
+                        }
+                    } else if (step) {
+                        AT(Va, i) += dth;
+                        if (i >= c) AT(Vm, i) += dvm;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (a.step_only) break;
+        // ---- control 2: bookkeeping, results of finished lanes, refill ----
+        if (warp == 0) {
+            const bool done = fdone[lane] != 0;
+            if (done) {
+                const int sc = scen[lane];
+                int st = stat[lane] & 0xff;
+                const int extra = stat[lane] & ~0xff;
+                const double err = errv[lane];
+                if ((extra & 0x200) && st == HPF_ST_CONVERGED) st = HPF_ST_SINGULAR;
+                if (itc[lane] >= a.max_h && st == HPF_ST_CONVERGED) st = HPF_ST_MAXITER;
+                if (err != err || (extra & 0x100)) st = HPF_ST_NONFINITE;
+                a.n_iter_h[sc] = itc[lane];
+                a.err_h[sc] = err;
+                a.status[sc] = st;
+            }
+            if (fstep[lane]) itc[lane] += 1;
+            fnew[lane] = 0;
+            const unsigned dm = __ballot_sync(0xffffffffu, done);
+            if (dm) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(a.work_counter, __popc(dm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (done) {
+                    const int idx = base + __popc(dm & ((1u << lane) - 1u));
+                    scen[lane] = ((size_t)idx < B) ? idx : -1;
+                    itc[lane] = 0;
+                    fnew[lane] = 1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+#undef AT
+}

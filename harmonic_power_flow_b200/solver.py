@@ -164,7 +164,11 @@ class BatchSolver:
 
     # -- fused solve -------------------------------------------------------------------
     def solve(self, P, Q, I_N=None, thresh_f=1e-6, max_iter_f=30, thresh_h=1e-4, max_iter_h=50,
-              raw=False, want_I_inj=True, history=False, out: BatchResult | None = None) -> BatchResult:
+              raw=False, want_I_inj=True, history=False, dense=False,
+              out: BatchResult | None = None) -> BatchResult:
+        """Fundamental + harmonic Newton-Raphson for the whole batch (hpf_solve).
+        dense=True forces the dense-LU Newton step; the default picks the structured step when
+        the network admits it (``struct_info()``).  history=True implies the dense kernel."""
         P, Q, I_N = self.prepare(P, Q, I_N)
         n = self.net
         B = P.shape[1]
@@ -177,7 +181,7 @@ class BatchSolver:
                 err_hist_h=self._f64(max_iter_h + 1, B) if history else None)
         _lib.check(self._h, self.lib.hpf_solve(
             self._h, B, _ptr(P), _ptr(Q), _ptr(I_N), thresh_f, max_iter_f, thresh_h, max_iter_h,
-            _lib.SOLVE_RAW if raw else 0, _ptr(out.V_m), _ptr(out.V_a), _ptr(out.I_inj),
+            (_lib.SOLVE_RAW if raw else 0) | (_lib.SOLVE_DENSE if dense else 0), _ptr(out.V_m), _ptr(out.V_a), _ptr(out.I_inj),
             _ptr(out.n_iter_f), _ptr(out.n_iter_h), _ptr(out.err_h), _ptr(out.status),
             _ptr(out.err_hist_f), _ptr(out.err_hist_h), self._stream()))
         return out
@@ -211,6 +215,24 @@ class BatchSolver:
                                                     _ptr(V_m), _ptr(V_a), _ptr(nf), _ptr(err), _ptr(hist),
                                                     self._stream()))
         return V_m, V_a, nf, err, hist
+
+    def struct_info(self):
+        """-> dict(available, nZ, pivot_min, pivot_max) of the structured strategy."""
+        av, nz = C.c_int(), C.c_int()
+        pmin, pmax = C.c_double(), C.c_double()
+        _lib.check(self._h, self.lib.hpf_struct_info(self._h, C.byref(av), C.byref(nz), C.byref(pmin),
+                                                     C.byref(pmax)))
+        return dict(available=bool(av.value), nZ=nz.value, pivot_min=pmin.value, pivot_max=pmax.value)
+
+    def newton_step(self, V_m, V_a, P, Q, I_N=None):
+        """One structured Newton step: dx [N, B] with x_new = x - dx (hpf_newton_step)."""
+        V_m, V_a = self._dev(V_m, torch.float64), self._dev(V_a, torch.float64)
+        P, Q, I_N = self.prepare(P, Q, I_N)
+        B = P.shape[1]
+        dx = self._f64(self.N, B)
+        _lib.check(self._h, self.lib.hpf_newton_step(self._h, B, _ptr(V_m), _ptr(V_a), _ptr(P), _ptr(Q),
+                                                     _ptr(I_N), _ptr(dx), self._stream()))
+        return dx
 
     # -- standalone kernels --------------------------------------------------------------
     def mismatch(self, V_m, V_a, P, Q, I_N=None, want_I_inj=False):

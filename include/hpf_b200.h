@@ -55,7 +55,7 @@ typedef struct hpf_handle hpf_t;
 #define HPF_ST_NONFINITE    3   /* NaN/Inf in the mismatch or the state            */
 
 /* ABI version of this header: bumped on any signature change. */
-#define HPF_ABI_VERSION 2
+#define HPF_ABI_VERSION 3
 int hpf_abi_version(void);
 
 /* Lifetime.  `device` is the CUDA ordinal the handle is bound to. */
@@ -100,7 +100,9 @@ int hpf_build_Y(hpf_t* h, double* Y_out, void* stream);
 int hpf_set_Y(hpf_t* h, const double* Y);
 
 /* hpf_solve flags */
-#define HPF_SOLVE_RAW 1   /* skip the post-processing of HG:547-549: return the raw iterate */
+#define HPF_SOLVE_RAW   1 /* skip the post-processing of HG:547-549: return the raw iterate */
+#define HPF_SOLVE_DENSE 2 /* force the dense-LU Newton step (default: structured step when the
+                             network admits it, see hpf_struct_info) */
 
 /*
  * Whole solve for B scenarios: pf() (HG:244-275) followed by the harmonic
@@ -173,6 +175,23 @@ long long hpf_jacobian_stride(const hpf_t* h);
  */
 int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f,
                  double* dx, int* info, void* stream);
+
+/*
+ * Structured Newton step (the default strategy of hpf_solve when available): the
+ * current-balance rows of J are A T with a CONSTANT complex operator
+ * A = blockdiag Y(h) - scatter(Y_N) and the polar map T, so the step of HG:476-479 is
+ * evaluated by block elimination with A_ZZ^{-1} (inverted once per network on the GPU)
+ * plus a (2m-1-c)-sized dense system per scenario; mathematically the same dx = J^{-1} f.
+ * hpf_struct_info: available = 1 if the strategy is set up for this network (0: falls back
+ * to the dense LU: system too large for the tile kernel or A_ZZ singular); nZ = order of
+ * A_ZZ; pivot_min/max = extreme pivot moduli of its Gauss-Jordan inversion.
+ * hpf_newton_step: ONE step for given iterates, dx [N, B] with x_new = x - dx in the
+ * reference's ordering [theta(1..nH-1), V_m(c..nH-1)] - comparable with hpf_lu_solve(J, f).
+ */
+int hpf_struct_info(hpf_t* h, int* available, int* nZ, double* pivot_min, double* pivot_max);
+int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a,
+                    const double* P, const double* Q, const double* I_N,
+                    double* dx, void* stream);
 
 /*
  * Post-processing after the path - get_THD() (HG:563-572): for every bus and scenario

@@ -209,15 +209,18 @@ def test_fused_solve_nominal_cases(solvers, case):
     assert np.abs(thd - d["THD"]).max() < 1e-7
 
 
+@pytest.mark.parametrize("strategy", ["structured", "dense"])
 @pytest.mark.parametrize("name", ["net3_c_h25_tight", "net3_c_h25_wide", "net2ev_c_h19_tight",
                                   "net3_uc_h25_tight"])
-def test_fused_solve_scenario_sets_vs_reference(solvers, name):
+def test_fused_solve_scenario_sets_vs_reference(solvers, name, strategy):
     d = helpers.load_set(name)
     case = name.rsplit("_", 1)[0]
     sol, net, _ = solvers(case)
     S = len(d["seed"])
     P, Q, I_N = d["P"].T.copy(), d["Q"].T.copy(), np.moveaxis(d["I_N"], 0, 2).copy()
-    r = sol.solve(P, Q, I_N).to_host()
+    if strategy == "structured":
+        assert sol.struct_info()["available"]
+    r = sol.solve(P, Q, I_N, dense=(strategy == "dense")).to_host()
     assert (r["n_iter_f"] == d["n_iter_f"]).all()
     assert (r["status"] == 0).all()
     V = np.moveaxis(helpers.phasor(r["V_m"], r["V_a"]), 2, 0)
@@ -227,15 +230,48 @@ def test_fused_solve_scenario_sets_vs_reference(solvers, name):
     floor = (np.abs(Vl - Vg) / np.abs(Vg)).reshape(S, -1).max(1)
     mism = int((r["n_iter_h"] != d["n_iter_h"]).sum())
     floor_mism = int((d["n_iter_h"] != d["n_iter_h_lapack"]).sum())
-    print("\n%s: GPU-vs-reference iteration mismatches %d/%d (reference SuperLU-vs-LAPACK: %d); "
+    print("\n%s [%s]: GPU-vs-reference iteration mismatches %d/%d (reference SuperLU-vs-LAPACK: %d); "
           "phasor rel diff > 1e-9: %d (reference floor: %d); max %.2e (floor %.2e); median %.2e"
-          % (name, mism, S, floor_mism, (rel > 1e-9).sum(), (floor > 1e-9).sum(), rel.max(),
+          % (name, strategy, mism, S, floor_mism, (rel > 1e-9).sum(), (floor > 1e-9).sum(), rel.max(),
              floor.max(), np.median(rel)))
     assert mism <= floor_mism + 1
     assert (rel > 1e-9).sum() <= (floor > 1e-9).sum() + max(2, S // 20)
     assert np.median(rel) < 1e-11
     same = r["n_iter_h"] == d["n_iter_h"]
     assert rel[same].max() < 1e-5
+
+
+@pytest.mark.parametrize("case", SMALL_CASES)
+def test_structured_newton_step_equals_dense_step(solvers, case):
+    """hpf_newton_step (block elimination through A_ZZ^-1) against J^-1 f: the reference's
+    first update x1, and random iterates against numpy on the oracle's Jacobian."""
+    sol, net, d = solvers(case)
+    info = sol.struct_info()
+    assert info["available"] and info["nZ"] == net.n * net.H - net.m
+    Vm, Va = d["V_fund_m"][:, :, None], d["V_fund_a"][:, :, None]
+    dx = sol.newton_step(Vm, Va, net.P[:, None], net.Q[:, None], net.I_N[:, :, None])[:, 0].cpu().numpy()
+    x0 = helpers.state_vectors(d["V_fund_m"], d["V_fund_a"], net.c)
+    assert np.abs((x0 - dx) - d["x1"]).max() <= 1e-8 * np.abs(d["x1"]).max()
+    # residual of the step against the reference's own Jacobian and mismatch
+    Jd = d["J0"]
+    assert np.abs(Jd @ dx - d["f0"]).max() <= 1e-10 * np.abs(d["f0"]).max()
+    on = O.net_from_golden(GOLDEN, str(d["net"]), int(d["h_max"]), bool(d["coupled"]))
+    Y = O.build_admittance_matrices(on)
+    B = 40
+    rng = np.random.default_rng(17)
+    Vmb = rng.uniform(0.05, 0.3, (net.H, net.n, B)) * rng.choice([-1.0, 1.0], (net.H, net.n, B))
+    Vmb[0] = rng.uniform(0.9, 1.1, (net.n, B))
+    Vab = rng.uniform(-3, 3, (net.H, net.n, B)); Vab[0, 0] = 0.0; Vmb[0, 0] = 1.0
+    P = np.repeat(net.P[:, None], B, 1) * rng.uniform(0.8, 1.2, (net.n, B))
+    Q = np.repeat(net.Q[:, None], B, 1) * rng.uniform(0.8, 1.2, (net.n, B))
+    I_N = np.repeat(net.I_N[:, :, None], B, 2) * rng.uniform(0.9, 1.1, (net.q, net.H, B))
+    dxb = sol.newton_step(Vmb, Vab, P, Q, I_N).cpu().numpy()
+    for b in range(0, B, 3):
+        J = O.build_harmonic_jacobian(on, Vmb[:, :, b], Vab[:, :, b], Y)
+        f, _ = O.harmonic_mismatch(on, P[:, b], Q[:, b], Vmb[:, :, b], Vab[:, :, b], Y, I_N[:, :, b])
+        ref = np.linalg.solve(J, f)
+        assert np.abs(dxb[:, b] - ref).max() <= 1e-7 * np.abs(ref).max()
+        assert np.abs(J @ dxb[:, b] - f).max() <= 1e-9 * np.abs(f).max()
 
 
 def test_host_buffer_entry_point_is_bit_identical(solvers):
@@ -255,7 +291,7 @@ def test_fused_solve_equals_stepwise_kernels(solvers):
     d = helpers.load_set("net3_c_h25_tight")
     S = 8
     P, Q, I_N = d["P"][:S].T.copy(), d["Q"][:S].T.copy(), np.moveaxis(d["I_N"][:S], 0, 2).copy()
-    fused = sol.solve(P, Q, I_N, raw=True).to_host()
+    fused = sol.solve(P, Q, I_N, raw=True, dense=True).to_host()
     V_m, V_a, nf, _, _ = sol.fund_solve(P, Q)
     nH, c = net.n * net.H, net.c
     for b in range(S):
@@ -273,9 +309,12 @@ def test_fused_solve_equals_stepwise_kernels(solvers):
         assert np.array_equal(va[:, :, 0].cpu().numpy(), fused["V_a"][:, :, b])
 
 
-def test_status_words_and_edge_batches(solvers):
+@pytest.mark.parametrize("dense", [False, True])
+def test_status_words_and_edge_batches(solvers, dense):
     sol, net, d = solvers("net3_c_h25")
     P, Q, I_N = net.P[:, None], net.Q[:, None], net.I_N[:, :, None]
+    _solve = sol.solve
+    sol = type("S", (), {"solve": staticmethod(lambda *a_, **k: _solve(*a_, dense=dense, **k))})()
     r = sol.solve(P, Q, I_N, max_iter_h=3)
     assert int(r.n_iter_h.item()) == 3 and int(r.status.item()) == 1      # HG:558: max-iter
     r = sol.solve(P, Q, I_N, max_iter_h=int(d["n_iter_h"]))              # converges ON the cap
