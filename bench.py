@@ -11,8 +11,9 @@ net3, coupled SMPS Norton equivalent, fundamental + odd harmonics to the 25th (N
 independent, each rank solves its own block, no data-path collective).  One "step" = one
 complete solve of the batch: fundamental NR + harmonic NR + post-processing.
 
-Keys: `value` = converged solves/s, inputs resident in HBM, CUDA-event timed on the launch
-stream, max over ranks.  `e2e` = the same through the host-buffer C-ABI entry point
+Keys: `value` = converged solves/s with the default (structured Newton step) strategy, inputs
+resident in HBM, CUDA-event timed on the launch stream, max over ranks; `dense_lu_path` = the
+same workload forced through the dense shared-memory LU kernel (HPF_SOLVE_DENSE).  `e2e` = the same through the host-buffer C-ABI entry point
 (hpf_solve_host): pinned host inputs -> H2D -> solve -> D2H of every result, plus (N > 1) the
 final NCCL gather of flags and results.  `roofline` = the dominant kernel (fused Newton
 kernel) against the FP64 pipe; `roofline_kernels` = the standalone mismatch / Jacobian kernels
@@ -255,25 +256,48 @@ def run_ours(a):
     out = None
     for _ in range(a.warmup):
         out = sol.solve(dP, dQ, dI, out=out)
+    sol.set_profiling(True)
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     l0 = sol.launch_count
-    ev = []
+    ev, kms = [], []
     t_wall0 = time.perf_counter()
     for _ in range(a.steps):
         flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); out = sol.solve(dP, dQ, dI, out=out); e1.record()
         ev.append((e0, e1))
+        kms.append(sol.last_kernel_ms())          # waits for this step's kernels
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = sol.launch_count - l0
     ms = sum(x.elapsed_time(y) for x, y in ev)
     clk = clocks.stop()
+    ms_fund = sum(k[0] for k in kms) / a.steps
+    ms_harm = sum(k[1] for k in kms) / a.steps
     conv = int((out.status == 0).sum().item())
     it_h = out.n_iter_h.double().sum().item()
     it_f = out.n_iter_f.double().sum().item()
+    strategy = "structured" if sol.struct_info()["available"] else "dense"
+
+    # ---- the same workload forced through the dense-LU kernel ----
+    dense_info = None
+    if rank == 0 and not a.no_dense:
+        od = sol.solve(dP, dQ, dI, dense=True)
+        torch.cuda.synchronize()
+        tot, kd = 0.0, 0.0
+        nd = 2
+        for _ in range(nd):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); od = sol.solve(dP, dQ, dI, dense=True, out=od); e1.record(); torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1); kd += sol.last_kernel_ms()[1]
+        dense_info = dict(ms=tot / nd, kernel_ms=kd / nd, conv=int((od.status == 0).sum().item()),
+                          it_h=od.n_iter_h.double().sum().item(), it_f=od.n_iter_f.double().sum().item(),
+                          iter_mismatch_vs_structured=int((od.n_iter_h != out.n_iter_h).sum().item()))
+        del od
+    sol.set_profiling(False)
 
     # ---- end to end through the host-buffer C-ABI entry point (e2e) ----
     npP, npQ, npI = hP.numpy(), hQ.numpy(), hI.numpy()
@@ -354,34 +378,59 @@ def run_ours(a):
     if rank == 0:
         value = conv_tot * a.steps / (ms_max / 1e3)
         e2e_v = conv_e2e_tot * a.steps / e2e_max
-        # algorithmic FP64 work of one launch of the fused kernel (DESIGN.md "Roofline accounting")
-        fl_iter = 8 * (H * n * n + q * H * H + (m - 1) * n) + 16 * (H * n * n + q * H * H) + \
-            2.0 / 3.0 * N ** 3 + 2.0 * N * N
+        # algorithmic FP64 work per Newton iteration of one scenario (DESIGN.md "Roofline accounting")
+        nZ = n * H - m
+        fl_mis = 8 * (H * n * n + q * H * H + (m - 1) * n)
+        fl_struct = fl_mis + 8 * nZ * nZ + 8 * nZ * (m - 1) + 10 * n * H
+        fl_dense = fl_mis + 16 * (H * n * n + q * H * H) + 2.0 / 3.0 * N ** 3 + 2.0 * N * N
         fl_f = 24 * n * n + 2.0 / 3.0 * Nf ** 3 + 2.0 * Nf * Nf
-        flops = (it_h / 1.0) * fl_iter + it_f * fl_f              # this rank's launch
-        t_kernel = ms / a.steps / 1e3
+        if strategy == "structured":
+            kname = "harm_tile_kernel (harmonic Newton, structured step, 32 scenarios per CTA)"
+            flops = (it_h + B) * fl_mis + it_h * (fl_struct - fl_mis)   # n_iter+1 mismatches, n_iter steps
+            t_kernel = ms_harm / 1e3
+            fl_iter = fl_struct
+        else:
+            kname = "solve_kernel<false> (fused fundamental + harmonic Newton, dense LU)"
+            flops = it_h * fl_dense + it_f * fl_f
+            t_kernel = ms_harm / 1e3
+            fl_iter = fl_dense
         ach = flops / t_kernel / 1e12
+        by_solve = 16 * n + 16 * q * H + 16 * n * H + 16 * q * H + 24 + 2 * 16 * n   # in + out + fundamental hand-over
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config_dict(world),
+                "config": config_dict(world), "strategy": strategy,
                 "converged_fraction": conv_tot / (B * world),
                 "mean_nr_iterations": {"fundamental": it_f_tot / (B * world), "harmonic": it_h_tot / (B * world)},
                 "us_per_nr_iteration": (ms_max / a.steps) * 1e3 / max(it_h / 1.0, 1.0),
                 "gpu_launches": int(launches),
+                "kernel_ms_per_step": {"fundamental_stage": ms_fund, "harmonic_stage": ms_harm},
                 "wall_s_timed_region": t_wall,
                 "clocks": clk,
                 "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_max / a.steps * 1e3,
                         "path": "BatchSolver.solve_host -> hpf_solve_host (C ABI, host buffers)"
                                 + (" + NCCL all_gather of flags and results" if world > 1 else "")},
-                "roofline": {"kernel": "solve_kernel<false> (fused fundamental + harmonic Newton)",
-                             "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                             "frac": (ach / fp64_peak) if fp64_peak else None, "traffic": None,
+                "roofline": {"kernel": kname, "bound": "fp64", "achieved": ach, "peak": fp64_peak,
+                             "unit": "TFLOP/s", "frac": (ach / fp64_peak) if fp64_peak else None,
+                             "traffic": None,
                              "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (no FP64 figure "
                                             "in MEASURED_PEAKS.json)",
-                             "flops_per_nr_iteration": fl_iter},
+                             "flops_per_nr_iteration": fl_iter,
+                             "hbm_bytes_per_scenario": by_solve,
+                             "hbm_gbs_of_whole_solve": by_solve * B / (ms / a.steps) / 1e6},
                 "roofline_kernels": kernels, "hbm_peak_source": hbm_src}
+        if dense_info is not None:
+            fld = dense_info["it_h"] * fl_dense + dense_info["it_f"] * fl_f
+            achd = fld / (dense_info["kernel_ms"] / 1e3) / 1e12
+            line["dense_lu_path"] = {
+                "value": dense_info["conv"] / (dense_info["ms"] / 1e3), "unit": UNIT,
+                "ms_per_step": dense_info["ms"],
+                "iteration_count_mismatches_vs_structured": dense_info["iter_mismatch_vs_structured"],
+                "roofline": {"kernel": "solve_kernel<false> (fused Newton, dense smem LU, warp-shuffle pivoting)",
+                             "bound": "fp64", "achieved": achd, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": achd / fp64_peak if fp64_peak else None,
+                             "flops_per_nr_iteration": fl_dense}}
         if cpu_pool is not None:
             cores = cpu_pool.procs
             nscen = 1024 * cores
@@ -401,11 +450,12 @@ def run_ours(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="scenarios per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-LU comparison leg")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

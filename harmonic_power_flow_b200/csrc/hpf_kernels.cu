@@ -10,6 +10,7 @@
 // used; the arithmetic is restated from the formulas (see hpf_device.cuh).
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -628,8 +629,14 @@ struct hpf_handle {
     size_t io_doubles = 0;
     // structured strategy: 0 = not set up yet, 1 = ready, -1 = not available for this network
     int struct_state = 0;
-    double2 *d_Ainv = nullptr, *d_Gz = nullptr;
+    double2 *d_Ainv = nullptr, *d_Gz = nullptr, *d_WNL = nullptr, *d_wN = nullptr;
+    size_t wN_elems = 0;
+    int harm_warps = 8;           // warps per 32-scenario tile of the harmonic kernel (8 or 16)
+    int harm_minb = 1;
     double pivot_min = 0.0, pivot_max = 0.0;
+    int profiling = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    int ev_valid = 0;             // 0 none, 1 structured (3 events), 2 dense (ev[1], ev[2])
     long long launches = 0;
     std::string err;
 };
@@ -743,10 +750,11 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
         rc = ensure_workspace(h, (size_t)grid * odd_ld(net.N) * (net.N + 1));
         if (rc) return rc;
         a.workspace = h->d_work;
-        solve_kernel<true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, a);
-    } else {
-        solve_kernel<false><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, a);
     }
+    if (h->profiling) { CK(cudaEventRecord(h->ev[1], st)); }
+    if (gm) solve_kernel<true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, a);
+    else solve_kernel<false><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, a);
+    if (h->profiling) { CK(cudaEventRecord(h->ev[2], st)); h->ev_valid = 2; }
     h->launches++;
     CK(cudaGetLastError());
     return HPF_OK;
@@ -759,6 +767,7 @@ static StructNet structnet(const hpf_t* h) {
     s.nx = (h->m - 1) + (h->m - h->c);
     s.Ainv = h->d_Ainv;
     s.G = h->d_Gz;
+    s.WNL = h->d_WNL;
     return s;
 }
 
@@ -767,13 +776,17 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     h->struct_state = -1;
     const DevNet net = devnet(h);
     const int nZ = net.nH - net.m;
-    if (nZ < 1 || nZ > (HPF_ST_THREADS / 32) * HPF_ST_R * HPF_ST_MAXPASS) return HPF_OK;
-    if (harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q) > (size_t)h->smem_optin) return HPF_OK;
+    if (nZ < 1 || nZ > HPF_ST_MAXNZ) return HPF_OK;
+    if (harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, h->harm_warps) > (size_t)h->smem_optin)
+        return HPF_OK;
     if (fund_tile_doubles_per_warp(net.n, net.Nf) * sizeof(double) > (size_t)h->smem_optin) return HPF_OK;
     double2* AZF = nullptr;
     int* ipiv = nullptr;
     double* pr = nullptr;
-    cudaFree(h->d_Ainv); cudaFree(h->d_Gz); h->d_Ainv = nullptr; h->d_Gz = nullptr;
+    cudaFree(h->d_Ainv); cudaFree(h->d_Gz); cudaFree(h->d_WNL);
+    h->d_Ainv = nullptr; h->d_Gz = nullptr; h->d_WNL = nullptr;
+    const int qH = net.q * net.H;
+    CK(cudaMalloc((void**)&h->d_WNL, (size_t)(nZ * qH + 1) * sizeof(double2)));
     CK(cudaMalloc((void**)&h->d_Ainv, (size_t)nZ * nZ * sizeof(double2)));
     CK(cudaMalloc((void**)&h->d_Gz, (size_t)nZ * net.m * sizeof(double2)));
     CK(cudaMalloc((void**)&AZF, (size_t)nZ * net.m * sizeof(double2)));
@@ -782,7 +795,8 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     struct_assemble_kernel<<<64, 256, 0, st>>>(net, h->d_Ainv, AZF);
     cinv_gj_kernel<<<1, 1024, 0, st>>>(nZ, h->d_Ainv, ipiv, ipiv + nZ, pr);
     struct_G_kernel<<<(nZ * net.m + 127) / 128, 128, 0, st>>>(nZ, net.m, h->d_Ainv, AZF, h->d_Gz);
-    h->launches += 3;
+    if (qH > 0) struct_WNL_kernel<<<(nZ * qH + 127) / 128, 128, 0, st>>>(net, nZ, h->d_Ainv, h->d_WNL);
+    h->launches += 4;
     int info = -1;
     double prh[2] = {0.0, 0.0};
     cudaError_t e = cudaMemcpyAsync(&info, ipiv + nZ, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -796,12 +810,68 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     return HPF_OK;
 }
 
+static int launch_wn(hpf_t* h, const DevNet& net, const StructNet& sn, int B, const double* I_N,
+                     cudaStream_t st) {
+    const size_t need = (size_t)sn.nZ * B;
+    if (need > h->wN_elems) {
+        if (h->d_wN) { CK(cudaDeviceSynchronize()); cudaFree(h->d_wN); h->d_wN = nullptr; h->wN_elems = 0; }
+        CK(cudaMalloc((void**)&h->d_wN, need * sizeof(double2)));
+        h->wN_elems = need;
+    }
+    const int qH = net.q * net.H;
+    if (qH == 0) { CK(cudaMemsetAsync(h->d_wN, 0, need * sizeof(double2), st)); return HPF_OK; }
+    WnArgs wa;
+    wa.B = B; wa.I_N = (const double2*)I_N; wa.wN = h->d_wN;
+    const size_t smem = (size_t)qH * HPF_T * sizeof(double2) + 16;
+    int occ = 0;
+    int rc = prep_kernel(h, wn_tile_kernel, smem, "hpf_solve", &occ, 256);
+    if (rc) return rc;
+    const long long tiles = ((long long)B + HPF_T - 1) / HPF_T;
+    long long grid = (long long)occ * h->sm_count;
+    if (grid > tiles) grid = tiles;
+    wn_tile_kernel<<<(unsigned)grid, 256, smem, st>>>(net, sn, sn.WNL, wa);
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+template <int NW, int MAXROWS, int MINB>
+static int launch_harm_t(hpf_t* h, const DevNet& net, const StructNet& sn, const HarmTileArgs& ha,
+                         bool persistent, cudaStream_t st) {
+    const size_t smem = harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, NW);
+    int occ = 0;
+    int rc = prep_kernel(h, harm_tile_kernel<NW, MAXROWS, MINB>, smem, "hpf_solve", &occ, NW * 32);
+    if (rc) return rc;
+    const long long tiles = ((long long)ha.B + HPF_T - 1) / HPF_T;
+    long long grid = tiles;
+    if (persistent && grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
+    harm_tile_kernel<NW, MAXROWS, MINB><<<(unsigned)grid, NW * 32, smem, st>>>(net, sn, ha);
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+// Variants: (warps per tile, rows of Z per warp in registers, min CTAs per SM).
+static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const HarmTileArgs& ha,
+                       bool persistent, cudaStream_t st) {
+    const int nw = h->harm_warps, nZ = sn.nZ;
+    if (nw == 16) {
+        if (nZ <= 64) return h->harm_minb == 2 ? launch_harm_t<16, 4, 2>(h, net, sn, ha, persistent, st)
+                                               : launch_harm_t<16, 4, 1>(h, net, sn, ha, persistent, st);
+        return launch_harm_t<16, 7, 1>(h, net, sn, ha, persistent, st);
+    }
+    if (nZ <= 56) return launch_harm_t<8, 7, 2>(h, net, sn, ha, persistent, st);
+    return launch_harm_t<8, 14, 1>(h, net, sn, ha, persistent, st);
+}
+
 static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, const double* I_N,
                             double thresh_f, int max_f, double thresh_h, int max_h, int flags,
                             double* V_m, double* V_a, double* I_inj, int* n_iter_f, int* n_iter_h,
                             double* err_h, int* status, cudaStream_t st) {
     const DevNet net = devnet(h);
     const StructNet sn = structnet(h);
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
+    if (h->profiling) { CK(cudaEventRecord(h->ev[0], st)); }
     // fundamental stage: one lane per scenario
     {
         const size_t per_warp = fund_tile_doubles_per_warp(net.n, net.Nf) * sizeof(double);
@@ -822,25 +892,21 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
         h->launches++;
         CK(cudaGetLastError());
     }
-    // harmonic stage
+    if (h->profiling) { CK(cudaEventRecord(h->ev[1], st)); }
+    // per-scenario constant w_N = A_ZZ^-1 I_N,Z, then the harmonic stage
     {
-        const size_t smem = harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q);
-        int occ = 0;
-        int rc = prep_kernel(h, harm_tile_kernel, smem, "hpf_solve", &occ, HPF_ST_THREADS);
+        int rc = launch_wn(h, net, sn, B, I_N, st);
         if (rc) return rc;
         HarmTileArgs ha;
         ha.B = B; ha.flags = flags; ha.step_only = 0; ha.P = P; ha.Q = Q; ha.I_N = (const double2*)I_N;
+        ha.wN = h->d_wN;
         ha.thresh_h = thresh_h; ha.max_h = max_h; ha.V_m = V_m; ha.V_a = V_a; ha.I_inj = (double2*)I_inj;
         ha.n_iter_h = n_iter_h; ha.status = status; ha.err_h = err_h; ha.work_counter = h->d_counter;
         ha.dx_out = nullptr;
-        CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
-        const long long tiles = ((long long)B + HPF_T - 1) / HPF_T;
-        long long grid = (long long)occ * h->sm_count;
-        if (grid > tiles) grid = tiles;
-        harm_tile_kernel<<<(unsigned)grid, HPF_ST_THREADS, smem, st>>>(net, sn, ha);
-        h->launches++;
-        CK(cudaGetLastError());
+        rc = launch_harm(h, net, sn, ha, true, st);
+        if (rc) return rc;
     }
+    if (h->profiling) { CK(cudaEventRecord(h->ev[2], st)); h->ev_valid = 1; }
     return HPF_OK;
 }
 
@@ -873,6 +939,8 @@ int hpf_create(hpf_t** out, int device) {
         delete h;
         return fail(nullptr, HPF_E_UNSUPPORTED, "hpf_create: this library is built for sm_100a (B200) only");
     }
+    if (const char* ev = getenv("HPF_HARM_WARPS")) h->harm_warps = (atoi(ev) == 16) ? 16 : 8;
+    if (const char* ev = getenv("HPF_HARM_MINB")) h->harm_minb = (atoi(ev) == 2) ? 2 : 1;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     e = cudaMalloc((void**)&h->d_counter, sizeof(int));
@@ -891,6 +959,8 @@ int hpf_destroy(hpf_t* h) {
     cudaFree(h->d_harm); cudaFree(h->d_from); cudaFree(h->d_to); cudaFree(h->d_devof);
     cudaFree(h->d_R); cudaFree(h->d_X); cudaFree(h->d_G); cudaFree(h->d_B); cudaFree(h->d_Xsh);
     cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work); cudaFree(h->d_io); cudaFree(h->d_Ainv); cudaFree(h->d_Gz);
+    cudaFree(h->d_WNL); cudaFree(h->d_wN);
+    for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return HPF_OK;
 }
@@ -987,6 +1057,28 @@ int hpf_thd(hpf_t* h, int B, const double* V_m, double* thd, void* stream) {
     return HPF_OK;
 }
 
+int hpf_set_profiling(hpf_t* h, int enabled) {
+    if (!h) return HPF_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (enabled)
+        for (int i = 0; i < 3; ++i)
+            if (!h->ev[i]) CK(cudaEventCreate(&h->ev[i]));
+    h->profiling = enabled ? 1 : 0;
+    h->ev_valid = 0;
+    return HPF_OK;
+}
+
+int hpf_last_kernel_ms(hpf_t* h, double* ms) {
+    if (!h || !ms) return HPF_E_INVALID;
+    if (!h->profiling || !h->ev_valid) return fail(h, HPF_E_INVALID, "hpf_last_kernel_ms: no profiled solve");
+    CK(cudaEventSynchronize(h->ev[2]));
+    float a = 0.f, b = 0.f;
+    if (h->ev_valid == 1) CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+    CK(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+    ms[0] = a; ms[1] = b;
+    return HPF_OK;
+}
+
 int hpf_dim_N(const hpf_t* h) { return (h && h->have_net) ? 2 * h->n * h->H - 1 - h->c : 0; }
 int hpf_dim_Nf(const hpf_t* h) { return (h && h->have_net) ? 2 * h->n - 1 - h->c : 0; }
 long long hpf_launch_count(const hpf_t* h) { return h ? h->launches : 0; }
@@ -1046,20 +1138,15 @@ int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const
         return fail(h, HPF_E_UNSUPPORTED, "hpf_newton_step: structured strategy not available for this network");
     const DevNet net = devnet(h);
     const StructNet sn = structnet(h);
-    const size_t smem = harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q);
-    int occ = 0;
-    rc = prep_kernel(h, harm_tile_kernel, smem, "hpf_newton_step", &occ, HPF_ST_THREADS);
+    rc = launch_wn(h, net, sn, B, I_N, (cudaStream_t)stream);
     if (rc) return rc;
     HarmTileArgs ha;
     ha.B = B; ha.flags = 0; ha.step_only = 1; ha.P = P; ha.Q = Q; ha.I_N = (const double2*)I_N;
+    ha.wN = h->d_wN;
     ha.thresh_h = 0.0; ha.max_h = 1; ha.V_m = const_cast<double*>(V_m); ha.V_a = const_cast<double*>(V_a);
     ha.I_inj = nullptr; ha.n_iter_h = nullptr; ha.status = nullptr; ha.err_h = nullptr;
     ha.work_counter = nullptr; ha.dx_out = dx;
-    const unsigned grid = (unsigned)(((long long)B + HPF_T - 1) / HPF_T);
-    harm_tile_kernel<<<grid, HPF_ST_THREADS, smem, (cudaStream_t)stream>>>(net, sn, ha);
-    h->launches++;
-    CK(cudaGetLastError());
-    return HPF_OK;
+    return launch_harm(h, net, sn, ha, false, (cudaStream_t)stream);
 }
 
 int hpf_fund_solve(hpf_t* h, int B, const double* P, const double* Q, double thresh_f, int max_iter_f,

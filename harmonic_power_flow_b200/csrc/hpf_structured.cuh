@@ -25,14 +25,12 @@
 #include "hpf_device.cuh"
 
 #define HPF_T 32            // scenarios per tile (= lanes)
-#define HPF_ST_THREADS 256  // 8 warps share a tile
-#define HPF_ST_R 7          // rows of A_ZZ^{-1} per warp pass (register tile)
-#define HPF_ST_MAXPASS 2    // => nZ <= 8 * 7 * 2 = 112
 
 struct StructNet {
     int nZ, nx;
     const double2* Ainv;   // [nZ][nZ] row-major
     const double2* G;      // [nZ][m]
+    const double2* WNL;    // [nZ][qH]  columns of Ainv that multiply the Norton currents
 };
 
 // ---------------------------------------------------------------------------------------
@@ -340,11 +338,66 @@ fund_tile_kernel(const DevNet net, const FundTileArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// setup 4: W_NL = columns of Ainv that multiply Norton currents: W_NL[z][u] = Ainv[z][z(u)],
+// u = k*H + h  <->  stacked s = h*n + m + k.
+__global__ void struct_WNL_kernel(const DevNet net, int nZ, const double2* __restrict__ Ainv,
+                                  double2* __restrict__ WNL) {
+    const int qH = net.q * net.H;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nZ * qH) return;
+    const int z = t / qH, u = t - z * qH, k = u / net.H, h = u - k * net.H;
+    const int zc = h * net.n + net.m + k - net.m;
+    WNL[t] = Ainv[(size_t)z * nZ + zc];
+}
+
+// Per-scenario constant of the harmonic stage:  w_N = A_ZZ^{-1} I_N,Z  (I_N enters the
+// current balance additively, HG:351-354).  One lane per scenario, rows over warps,
+// fully coalesced: wN [nZ, B] complex.
+struct WnArgs {
+    int B;
+    const double2* I_N;   // [qH, B]
+    double2* wN;          // [nZ, B]
+};
+
+__global__ void __launch_bounds__(256)
+wn_tile_kernel(const DevNet net, const StructNet sn, const double2* __restrict__ WNL, const WnArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+    const int qH = net.q * net.H, nZ = sn.nZ;
+    const size_t B = (size_t)a.B;
+    double2* IN = reinterpret_cast<double2*>(smem);          // [qH][32]
+    for (size_t tile = blockIdx.x; tile * HPF_T < B; tile += gridDim.x) {
+        const size_t b = tile * HPF_T + lane;
+        const bool ok = b < B;
+        const size_t bb = ok ? b : B - 1;
+        __syncthreads();
+        for (int u = warp; u < qH; u += NW) IN[u * HPF_T + lane] = a.I_N[(size_t)u * B + bb];
+        __syncthreads();
+        for (int z = warp; z < nZ; z += NW) {
+            const double2* row = WNL + (size_t)z * qH;
+            double2 acc = make_double2(0.0, 0.0);
+            for (int u = 0; u < qH; ++u) acc = cadd(acc, cmul(ldg2(row + u), IN[u * HPF_T + lane]));
+            if (ok) a.wN[(size_t)z * B + b] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Harmonic Newton-Raphson, structured step, 32 scenarios per CTA (lane = scenario).
+//
+// Because f_I = A_ZZ V_Z + A_ZF V_F + I_N,Z is linear in V, the product -A_ZZ^{-1} f_I of the
+// step has the closed form   u0 = -V_Z - G V_F - w_N   (w_N per scenario, see above): no
+// matrix-vector product with A_ZZ^{-1} is left inside the Newton loop.  One round =
+//   A  load refilled lanes, unit phasors E = e^{j theta}                       | barrier
+//   B  mismatch rows (HG:360-388) incl. the Norton contraction, ||f||_inf       | barrier
+//   C  decisions; results of finished lanes; t = u0 rows in registers;
+//      last warp: border system for the linear buses' fundamental unknowns      | barrier
+//   D  u_Z = t - G u_F, polar conversion, state update; warp 0: lane refill     | barrier
 struct HarmTileArgs {
     int B, flags, step_only;
     const double *P, *Q;
     const double2* I_N;
+    const double2* wN;       // [nZ, B]
     double thresh_h;
     int max_h;
     double *V_m, *V_a;       // in: rows 0..n-1 hold the fundamental solution; out: results
@@ -355,18 +408,20 @@ struct HarmTileArgs {
     double* dx_out;          // step_only: [N, B] the Newton update dx (x_new = x - dx)
 };
 
-__host__ __device__ inline size_t harm_tile_smem_bytes(int n, int H, int m, int c, int q) {
+#define HPF_ST_MAXNZ 112     // rows of Z kept in registers: HPF_ST_MAXNZ / (warps per tile) per warp
+
+__host__ __device__ inline size_t harm_tile_smem_bytes(int n, int H, int m, int c, int q, int nwarps) {
     const size_t nH = (size_t)n * H, nZ = nH - m, nx = (size_t)(m - 1) + (m - c);
     const size_t d = 4 * nH + 2 * nZ + 2 * m + 2 * n + 2 * q * H + 2 * m + nx * (nx + 1) + 2 * m +
-                     (HPF_ST_THREADS / 32) + 2;
+                     nwarps + 2;
     return d * HPF_T * sizeof(double) + 8 * HPF_T * sizeof(int) + 64;
 }
 
-__global__ void __launch_bounds__(HPF_ST_THREADS)
+template <int NW, int MAXROWS, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int NW = HPF_ST_THREADS / 32;
     const int n = net.n, m = net.m, c = net.c, H = net.H, q = net.q, nH = net.nH;
     const int nZ = sn.nZ, nx = sn.nx;
     const size_t B = (size_t)a.B;
@@ -376,13 +431,13 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     double* Va = p;  p += nH * HPF_T;
     double* Ere = p; p += nH * HPF_T;
     double* Eim = p; p += nH * HPF_T;
-    double* Ure = p; p += nZ * HPF_T;      // f_I, then u0, then u_Z (index z = s - m)
-    double* Uim = p; p += nZ * HPF_T;
+    double* Wre = p; p += nZ * HPF_T;      // w_N (index z = s - m), constant per scenario
+    double* Wim = p; p += nZ * HPF_T;
     double* FSre = p; p += m * HPF_T;      // power mismatch of buses s < m
     double* FSim = p; p += m * HPF_T;
-    double* I1re = p; p += n * HPF_T;
+    double* I1re = p; p += n * HPF_T;      // (Y1 V1)_i, rows i < m are used by the border system
     double* I1im = p; p += n * HPF_T;
-    double* IJre = p; p += q * H * HPF_T;
+    double* IJre = p; p += q * H * HPF_T;  // Norton injections (result I_inj)
     double* IJim = p; p += q * H * HPF_T;
     double* Pl = p;  p += m * HPF_T;
     double* Ql = p;  p += m * HPF_T;
@@ -391,15 +446,11 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     double* UFim = p; p += m * HPF_T;
     double* red = p; p += NW * HPF_T;
     double* errv = p; p += HPF_T;
-    double* spare = p; p += HPF_T;
+    p += HPF_T;
     int* scen = reinterpret_cast<int*>(p);
     int* itc = scen + HPF_T;
     int* stat = itc + HPF_T;
     int* fnew = stat + HPF_T;
-    int* fdone = fnew + HPF_T;
-    int* fstep = fdone + HPF_T;
-    int* ctl = fstep + HPF_T;              // ctl[0] = exit flag
-    (void)spare;
 
     // ---- initial fill ----
     if (warp == 0) {
@@ -415,108 +466,108 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
         scen[lane] = ((size_t)idx < B) ? idx : -1;
         itc[lane] = 0;
         fnew[lane] = 1;
-        fdone[lane] = 0;
-        fstep[lane] = 0;
-        if (lane == 0) ctl[0] = 0;
+        stat[lane] = 0;
     }
     __syncthreads();
 
     for (;;) {
-        // ---- load new scenarios (rows over warps, lanes gather) ----
+        // ================= A: load refilled lanes, unit phasors =================
         {
             const int sc = scen[lane];
-            if (fnew[lane] && sc >= 0) {
-                for (int s = warp; s < nH; s += NW) {
-                    if (a.step_only || s < n) {
-                        AT(Vm, s) = a.V_m[(size_t)s * B + sc];
-                        AT(Va, s) = a.V_a[(size_t)s * B + sc];
-                    } else {
-                        AT(Vm, s) = 0.1;       // flat start of the harmonics (HG:183)
-                        AT(Va, s) = 0.0;
+            const bool isnew = fnew[lane] != 0;
+            if (isnew) {
+                if (sc >= 0) {
+                    for (int s = warp; s < nH; s += NW) {
+                        if (a.step_only || s < n) {
+                            AT(Vm, s) = a.V_m[(size_t)s * B + sc];
+                            AT(Va, s) = a.V_a[(size_t)s * B + sc];
+                        } else {
+                            AT(Vm, s) = 0.1;       // flat start of the harmonics (HG:183)
+                            AT(Va, s) = 0.0;
+                        }
                     }
+                    for (int z = warp; z < nZ; z += NW) {
+                        const double2 w = a.wN[(size_t)z * B + sc];
+                        AT(Wre, z) = w.x; AT(Wim, z) = w.y;
+                    }
+                    for (int s = warp; s < m; s += NW) {
+                        AT(Pl, s) = a.P[(size_t)s * B + sc];
+                        AT(Ql, s) = a.Q[(size_t)s * B + sc];
+                    }
+                    if (warp == 0) stat[lane] = a.step_only ? 0 : a.status[sc];
+                } else {
+                    for (int s = warp; s < nH; s += NW) { AT(Vm, s) = 1.0; AT(Va, s) = 0.0; }
+                    for (int z = warp; z < nZ; z += NW) { AT(Wre, z) = 0.0; AT(Wim, z) = 0.0; }
+                    for (int s = warp; s < m; s += NW) { AT(Pl, s) = 0.0; AT(Ql, s) = 0.0; }
                 }
-                for (int s = warp; s < m; s += NW) {
-                    AT(Pl, s) = a.P[(size_t)s * B + sc];
-                    AT(Ql, s) = a.Q[(size_t)s * B + sc];
-                }
-                if (warp == 0) stat[lane] = a.step_only ? 0 : a.status[sc];
-            } else if (fnew[lane] && sc < 0) {
-                for (int s = warp; s < nH; s += NW) { AT(Vm, s) = 1.0; AT(Va, s) = 0.0; }
-                for (int s = warp; s < m; s += NW) { AT(Pl, s) = 0.0; AT(Ql, s) = 0.0; }
+            }
+            for (int s = warp; s < nH; s += NW) {
+                double sn_, cs_;
+                sincos(AT(Va, s), &sn_, &cs_);
+                AT(Ere, s) = cs_;
+                AT(Eim, s) = sn_;
             }
         }
         __syncthreads();
-        // ---- P1: unit phasors E = e^{j theta};  V = V_m E = (V_m cos, V_m sin) like HG:403 ----
-        for (int s = warp; s < nH; s += NW) {
-            double sn_, cs_;
-            sincos(AT(Va, s), &sn_, &cs_);
-            AT(Ere, s) = cs_;
-            AT(Eim, s) = sn_;
-        }
-        __syncthreads();
-        // ---- P2: I1 = Y1 V1 and Norton injections ----
-        for (int t = warp; t < n + q * H; t += NW) {
-            if (t < n) {
-                const double2* Yrow = net.Y + (size_t)t * n;
-                double2 acc = make_double2(0.0, 0.0);
-                for (int j = 0; j < n; ++j) {
-                    const double vm = AT(Vm, j);
-                    acc = cadd(acc, cmul(ldg2(Yrow + j), make_double2(vm * AT(Ere, j), vm * AT(Eim, j))));
-                }
-                AT(I1re, t) = acc.x; AT(I1im, t) = acc.y;
-            } else {
-                const int u = t - n, k = u / H, h = u - k * H, bus = m + k;
+        // ================= B: mismatch rows (HG:360-388) =================
+        {
+            double mx = 0.0;
+            const int sc = scen[lane];
+            // heavy rows first: nonlinear buses, (Y_h V_h)_i + I_N - sum_p Y_N[h][p] V_p,i
+            for (int u = warp; u < q * H; u += NW) {
+                const int k = u / H, h = u - k * H, i = m + k, s = h * n + i;
                 const int dev = net.dev_of_nl[k];
-                const int sc = scen[lane];
                 const double2 in = (sc >= 0) ? a.I_N[(size_t)u * B + sc] : make_double2(0.0, 0.0);
                 double2 acc;
                 if (net.coupled) {
                     const double2* row = net.YN + ((size_t)dev * H + h) * H;
                     acc = make_double2(0.0, 0.0);
                     for (int pp = 0; pp < H; ++pp) {
-                        const int t2 = pp * n + bus;
+                        const int t2 = pp * n + i;
                         const double vm = AT(Vm, t2);
                         acc = cadd(acc, cmul(ldg2(row + pp), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
                     }
                 } else {
-                    const int t2 = h * n + bus;
-                    const double vm = AT(Vm, t2);
-                    acc = cmul(ldg2(net.YN + (size_t)dev * H + h), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2)));
-                }
-                AT(IJre, u) = in.x - acc.x; AT(IJim, u) = in.y - acc.y;
-            }
-        }
-        __syncthreads();
-        // ---- P3: mismatch rows (HG:360-388) ----
-        {
-            double mx = 0.0;
-            for (int e = warp; e < nH - 1; e += NW) {
-                const int s = e + 1;
-                double2 f;
-                if (s < m) {
                     const double vm = AT(Vm, s);
-                    const double2 v = make_double2(vm * AT(Ere, s), vm * AT(Eim, s));
-                    const double2 sl = cmul(v, make_double2(AT(I1re, s), -AT(I1im, s)));
-                    f = make_double2(AT(Pl, s) + sl.x, AT(Ql, s) + sl.y);
-                    AT(FSre, s) = f.x; AT(FSim, s) = f.y;
-                } else {
-                    const int h = s / n, i = s - h * n;
-                    if (h == 0) {
-                        f = make_double2(AT(I1re, i), AT(I1im, i));
-                    } else {
-                        const double2* Yrow = net.Y + ((size_t)h * n + i) * n;
-                        f = make_double2(0.0, 0.0);
-                        for (int j = 0; j < n; ++j) {
-                            const int t2 = h * n + j;
-                            const double vm = AT(Vm, t2);
-                            f = cadd(f, cmul(ldg2(Yrow + j), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
-                        }
-                    }
-                    if (i >= m) { f.x += AT(IJre, (i - m) * H + h); f.y += AT(IJim, (i - m) * H + h); }
-                    AT(Ure, s - m) = f.x; AT(Uim, s - m) = f.y;
+                    acc = cmul(ldg2(net.YN + (size_t)dev * H + h), make_double2(vm * AT(Ere, s), vm * AT(Eim, s)));
+                }
+                const double2 inj = csub(in, acc);
+                AT(IJre, u) = inj.x; AT(IJim, u) = inj.y;
+                const double2* Yrow = net.Y + ((size_t)h * n + i) * n;
+                double2 f = make_double2(0.0, 0.0);
+                for (int j = 0; j < n; ++j) {
+                    const int t2 = h * n + j;
+                    const double vm = AT(Vm, t2);
+                    f = cadd(f, cmul(ldg2(Yrow + j), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                }
+                if (h == 0) { AT(I1re, i) = f.x; AT(I1im, i) = f.y; }
+                f = cadd(f, inj);
+                const double v1 = fabs(f.x), v2 = fabs(f.y);      // s >= m >= c: both parts are rows
+                const double v = (v2 != v2 || v2 > v1) ? v2 : v1;
+                mx = (v != v || v > mx) ? v : mx;
+            }
+            // light rows: linear buses at every harmonic
+            const int nlin = m * H;
+            for (int t = warp; t < nlin; t += NW) {
+                const int h = t / m, i = t - h * m, s = h * n + i;
+                const double2* Yrow = net.Y + ((size_t)h * n + i) * n;
+                double2 f = make_double2(0.0, 0.0);
+                for (int j = 0; j < n; ++j) {
+                    const int t2 = h * n + j;
+                    const double vm = AT(Vm, t2);
+                    f = cadd(f, cmul(ldg2(Yrow + j), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                }
+                if (h == 0) {
+                    AT(I1re, i) = f.x; AT(I1im, i) = f.y;
+                    if (i == 0) continue;                            // slack: no row
+                    const double vm = AT(Vm, i);
+                    const double2 v = make_double2(vm * AT(Ere, i), vm * AT(Eim, i));
+                    const double2 sl = cmul(v, make_double2(f.x, -f.y));
+                    f = make_double2(AT(Pl, i) + sl.x, AT(Ql, i) + sl.y);
+                    AT(FSre, i) = f.x; AT(FSim, i) = f.y;
                 }
                 double v1 = fabs(f.x);
-                if (e >= c - 1) {
+                if (s - 1 >= c - 1) {
                     const double v2 = fabs(f.y);
                     v1 = (v2 != v2 || v2 > v1) ? v2 : v1;
                 }
@@ -525,10 +576,13 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
             AT(red, warp) = mx;
         }
         __syncthreads();
-        // ---- control: who continues, who is finished ----
-        if (warp == 0) {
-            double err = 0.0;
+        // ================= C: decisions (every warp, same result), finished lanes =================
+        bool step, done;
+        double err;
+        {
+            err = 0.0;
             bool bad = false;
+#pragma unroll
             for (int w2 = 0; w2 < NW; ++w2) {
                 const double v = AT(red, w2);
                 bad |= (v != v);
@@ -537,70 +591,55 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
             if (bad) err = CUDART_NAN;
             const bool active = scen[lane] >= 0;
             const bool cont = active && (err > a.thresh_h) && (itc[lane] < a.max_h);
-            errv[lane] = err;
-            fstep[lane] = (a.step_only ? active : cont) ? 1 : 0;
-            fdone[lane] = (active && !cont && !a.step_only) ? 1 : 0;
-            const unsigned any = __ballot_sync(0xffffffffu, active);
-            if (lane == 0) ctl[0] = (any == 0u) ? 1 : 0;
+            step = a.step_only ? active : cont;
+            done = active && !cont && !a.step_only;
+            if (__ballot_sync(0xffffffffu, active) == 0u) break;      // uniform over the CTA
         }
-        __syncthreads();
-        if (ctl[0]) break;
-        // ---- finalize finished lanes: post-processing (HG:547-549) + write-out ----
-        if (fdone[lane]) {
+        const unsigned donemask = __ballot_sync(0xffffffffu, done);
+        if (donemask) {
+            // post-processing (HG:547-549) + write-out of the finished lanes
             const int sc = scen[lane];
             int bad = 0;
-            for (int s = warp; s < nH; s += NW) {
-                double vm = AT(Vm, s), va = AT(Va, s), r = va;
-                if (!(a.flags & HPF_SOLVE_RAW)) {
-                    if (vm < 0.0) va += CUDART_PI;
-                    const double twopi = 2.0 * CUDART_PI;
-                    r = fmod(va, twopi);
-                    if (r != 0.0) { if (r < 0.0) r += twopi; } else r = 0.0;
-                    if (vm < 0.0) vm = -vm;
-                }
-                if (!(vm == vm) || !(r == r) || fabs(vm) == CUDART_INF) bad = 1;
-                a.V_m[(size_t)s * B + sc] = vm;
-                a.V_a[(size_t)s * B + sc] = r;
-            }
-            if (a.I_inj)
-                for (int u = warp; u < q * H; u += NW)
-                    a.I_inj[(size_t)u * B + sc] = make_double2(AT(IJre, u), AT(IJim, u));
-            if (bad) atomicOr(&stat[lane], 0x100);
-        }
-        // ---- P4: u0 = -Ainv f_I  (register tile of R rows per warp pass) ----
-        {
-            double2 acc[HPF_ST_MAXPASS][HPF_ST_R];
-#pragma unroll
-            for (int ps = 0; ps < HPF_ST_MAXPASS; ++ps) {
-                const int r0 = (ps * NW + warp) * HPF_ST_R;
-#pragma unroll
-                for (int r = 0; r < HPF_ST_R; ++r) acc[ps][r] = make_double2(0.0, 0.0);
-                if (r0 < nZ) {
-                    for (int zc = 0; zc < nZ; ++zc) {
-                        const double2 f = make_double2(AT(Ure, zc), AT(Uim, zc));
-#pragma unroll
-                        for (int r = 0; r < HPF_ST_R; ++r) {
-                            if (r0 + r < nZ) {
-                                const double2 av = ldg2(sn.Ainv + (size_t)(r0 + r) * nZ + zc);
-                                acc[ps][r].x += av.x * f.x - av.y * f.y;
-                                acc[ps][r].y += av.x * f.y + av.y * f.x;
-                            }
-                        }
+            if (done) {
+                for (int s = warp; s < nH; s += NW) {
+                    double vm = AT(Vm, s), va = AT(Va, s), r = va;
+                    if (!(a.flags & HPF_SOLVE_RAW)) {
+                        if (vm < 0.0) va += CUDART_PI;
+                        const double twopi = 2.0 * CUDART_PI;
+                        r = fmod(va, twopi);
+                        if (r != 0.0) { if (r < 0.0) r += twopi; } else r = 0.0;
+                        if (vm < 0.0) vm = -vm;
                     }
+                    if (!(vm == vm) || !(r == r) || fabs(vm) == CUDART_INF) bad = 1;
+                    a.V_m[(size_t)s * B + sc] = vm;
+                    a.V_a[(size_t)s * B + sc] = r;
                 }
-            }
-            __syncthreads();                       // everyone has finished reading f_I
-#pragma unroll
-            for (int ps = 0; ps < HPF_ST_MAXPASS; ++ps) {
-                const int r0 = (ps * NW + warp) * HPF_ST_R;
-#pragma unroll
-                for (int r = 0; r < HPF_ST_R; ++r)
-                    if (r0 + r < nZ) { AT(Ure, r0 + r) = -acc[ps][r].x; AT(Uim, r0 + r) = -acc[ps][r].y; }
+                if (a.I_inj)
+                    for (int u = warp; u < q * H; u += NW)
+                        a.I_inj[(size_t)u * B + sc] = make_double2(AT(IJre, u), AT(IJim, u));
+                if (bad) atomicOr(&stat[lane], 0x100);
+                if (warp == 0) errv[lane] = err;
             }
         }
-        __syncthreads();
-        // ---- P5: border system for the fundamental unknowns of the linear buses ----
-        if (warp == 0) {
+        // t_z = u0_z = -V_z - sum_i G[z][i] V_i - w_N,z for this warp's rows (registers)
+        double2 tz[MAXROWS];
+#pragma unroll
+        for (int r = 0; r < MAXROWS; ++r) {
+            const int z = warp + r * NW;
+            tz[r] = make_double2(0.0, 0.0);
+            if (z < nZ) {
+                const int s = z + m;
+                const double vm = AT(Vm, s);
+                double2 acc = make_double2(vm * AT(Ere, s) + AT(Wre, z), vm * AT(Eim, s) + AT(Wim, z));
+                for (int i = 0; i < m; ++i) {
+                    const double vi = AT(Vm, i);
+                    acc = cadd(acc, cmul(ldg2(sn.G + (size_t)z * m + i), make_double2(vi * AT(Ere, i), vi * AT(Eim, i))));
+                }
+                tz[r] = cneg(acc);
+            }
+        }
+        // border system for the fundamental unknowns of the linear buses (last warp)
+        if (warp == NW - 1) {
             const int w = nx + 1, nth = m - 1;
             for (int t = 0; t < nx * w; ++t) AT(M, t) = 0.0;
             for (int i = 1; i < m; ++i) {
@@ -611,8 +650,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 const double2 jvi = cmulj(vi);
                 const int rr = i - 1, ri = nth + (i - c);
                 const bool has_im = (i >= c);
-                // base entries: derivatives w.r.t. the linear buses' own unknowns (HG:457-467)
-                for (int j = 1; j < m; ++j) {
+                for (int j = 1; j < m; ++j) {                         // HG:457-467
                     const double2 y = ldg2(net.Y + (size_t)i * n + j);
                     const double vmj = AT(Vm, j);
                     const double2 ej = make_double2(AT(Ere, j), AT(Eim, j));
@@ -630,8 +668,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     }
                 }
                 double2 rhs = make_double2(-AT(FSre, i), -AT(FSim, i));
-                // nonlinear buses at the fundamental: eliminated through u_Z1 = u0 - G T_F x_F
-                for (int k = 0; k < q; ++k) {
+                for (int k = 0; k < q; ++k) {     // fundamental nonlinear buses, eliminated via u_Z1
                     const int bk = m + k;
                     const double2 y = ldg2(net.Y + (size_t)i * n + bk);
                     if (y.x == 0.0 && y.y == 0.0) continue;
@@ -641,7 +678,14 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     const double2 ak = cmul(jvi, cconj(cneg(cmul(y, vb))));    // dS_i/dtheta_b
                     const double2 vk = cmul(vi, cconj(cmul(y, eb)));           // dS_i/dV_m,b
                     const double rvm = 1.0 / vmb;
-                    const double2 w0 = cmul(cconj(eb), make_double2(AT(Ure, k), AT(Uim, k)));
+                    // u0 of row z = k (closed form, same expression as tz)
+                    double2 u0 = make_double2(vb.x + AT(Wre, k), vb.y + AT(Wim, k));
+                    for (int i2 = 0; i2 < m; ++i2) {
+                        const double v2 = AT(Vm, i2);
+                        u0 = cadd(u0, cmul(ldg2(sn.G + (size_t)k * m + i2), make_double2(v2 * AT(Ere, i2), v2 * AT(Eim, i2))));
+                    }
+                    u0 = cneg(u0);
+                    const double2 w0 = cmul(cconj(eb), u0);
                     const double dth0 = w0.y * rvm, dvm0 = w0.x;
                     rhs.x -= ak.x * dth0 + vk.x * dvm0;
                     rhs.y -= ak.y * dth0 + vk.y * dvm0;
@@ -667,42 +711,42 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 AT(M, rr * w + nx) = rhs.x;
                 if (has_im) AT(M, ri * w + nx) = rhs.y;
             }
-            const int bad = (nx > 0) ? lane_gauss_solve(M, nx, lane) : 0;
-            if (bad && fstep[lane]) atomicOr(&stat[lane], 0x200);
+            const int badp = (nx > 0) ? lane_gauss_solve(M, nx, lane) : 0;
+            if (badp && step) atomicOr(&stat[lane], 0x200);
             AT(UFre, 0) = 0.0; AT(UFim, 0) = 0.0;
             for (int i = 1; i < m; ++i) {
                 const double dth = AT(M, (i - 1) * w + nx);
                 const double dvm = (i >= c) ? AT(M, (nth + i - c) * w + nx) : 0.0;
                 const double vmi = AT(Vm, i);
                 const double2 ei = make_double2(AT(Ere, i), AT(Eim, i));
-                // u_F = (j V_i) dtheta + E_i dV_m
-                AT(UFre, i) = -(vmi * ei.y) * dth + ei.x * dvm;
+                AT(UFre, i) = -(vmi * ei.y) * dth + ei.x * dvm;      // u_F = (j V_i) dtheta + E_i dV_m
                 AT(UFim, i) = (vmi * ei.x) * dth + ei.y * dvm;
             }
         }
         __syncthreads();
-        // ---- P6: u_Z = u0 - G u_F, polar conversion, state update (x_new = x + delta) ----
+        // ================= D: u_Z = t - G u_F, polar conversion, state update =================
         {
-            const bool step = fstep[lane] != 0;
             const int sc = scen[lane];
-            for (int z = warp; z < nZ; z += NW) {
-                double2 u = make_double2(AT(Ure, z), AT(Uim, z));
-                for (int i = 1; i < m; ++i) {
-                    const double2 g = ldg2(sn.G + (size_t)z * m + i);
-                    u = csub(u, cmul(g, make_double2(AT(UFre, i), AT(UFim, i))));
-                }
-                const int s = z + m;
-                const double2 wv = cmul(make_double2(AT(Ere, s), -AT(Eim, s)), u);
-                const double vm = AT(Vm, s);
-                const double dth = wv.y / vm, dvm = wv.x;
-                if (a.step_only) {
-                    if (sc >= 0) {
-                        a.dx_out[(size_t)(s - 1) * B + sc] = -dth;
-                        a.dx_out[(size_t)((nH - 1) + s - c) * B + sc] = -dvm;
+#pragma unroll
+            for (int r = 0; r < MAXROWS; ++r) {
+                const int z = warp + r * NW;
+                if (z < nZ) {
+                    double2 u = tz[r];
+                    for (int i = 1; i < m; ++i)
+                        u = csub(u, cmul(ldg2(sn.G + (size_t)z * m + i), make_double2(AT(UFre, i), AT(UFim, i))));
+                    const int s = z + m;
+                    const double2 wv = cmul(make_double2(AT(Ere, s), -AT(Eim, s)), u);
+                    const double vm = AT(Vm, s);
+                    const double dth = wv.y / vm, dvm = wv.x;
+                    if (a.step_only) {
+                        if (sc >= 0) {
+                            a.dx_out[(size_t)(s - 1) * B + sc] = -dth;
+                            a.dx_out[(size_t)((nH - 1) + s - c) * B + sc] = -dvm;
+                        }
+                    } else if (step) {
+                        AT(Va, s) += dth;
+                        AT(Vm, s) = vm + dvm;
                     }
-                } else if (step) {
-                    AT(Va, s) += dth;
-                    AT(Vm, s) = vm + dvm;
                 }
             }
             if (warp == NW - 1) {
@@ -721,36 +765,32 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     }
                 }
             }
-        }
-        __syncthreads();
-        if (a.step_only) break;
-        // ---- control 2: bookkeeping, results of finished lanes, refill ----
-        if (warp == 0) {
-            const bool done = fdone[lane] != 0;
-            if (done) {
-                const int sc = scen[lane];
-                int st = stat[lane] & 0xff;
-                const int extra = stat[lane] & ~0xff;
-                const double err = errv[lane];
-                if ((extra & 0x200) && st == HPF_ST_CONVERGED) st = HPF_ST_SINGULAR;
-                if (itc[lane] >= a.max_h && st == HPF_ST_CONVERGED) st = HPF_ST_MAXITER;
-                if (err != err || (extra & 0x100)) st = HPF_ST_NONFINITE;
-                a.n_iter_h[sc] = itc[lane];
-                a.err_h[sc] = err;
-                a.status[sc] = st;
-            }
-            if (fstep[lane]) itc[lane] += 1;
-            fnew[lane] = 0;
-            const unsigned dm = __ballot_sync(0xffffffffu, done);
-            if (dm) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(a.work_counter, __popc(dm));
-                base = __shfl_sync(0xffffffffu, base, 0);
+            if (a.step_only) break;
+            // bookkeeping + refill (warp 0).  Nobody reads scen/itc/fnew/stat in phase D.
+            if (warp == 0) {
                 if (done) {
-                    const int idx = base + __popc(dm & ((1u << lane) - 1u));
-                    scen[lane] = ((size_t)idx < B) ? idx : -1;
-                    itc[lane] = 0;
-                    fnew[lane] = 1;
+                    int st = stat[lane] & 0xff;
+                    const int extra = stat[lane] & ~0xff;
+                    if ((extra & 0x200) && st == HPF_ST_CONVERGED) st = HPF_ST_SINGULAR;
+                    if (itc[lane] >= a.max_h && st == HPF_ST_CONVERGED) st = HPF_ST_MAXITER;
+                    if (err != err || (extra & 0x100)) st = HPF_ST_NONFINITE;
+                    a.n_iter_h[sc] = itc[lane];
+                    a.err_h[sc] = err;
+                    a.status[sc] = st;
+                }
+                if (step) itc[lane] += 1;
+                fnew[lane] = 0;
+                if (donemask) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(a.work_counter, __popc(donemask));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (done) {
+                        const int idx = base + __popc(donemask & ((1u << lane) - 1u));
+                        scen[lane] = ((size_t)idx < B) ? idx : -1;
+                        itc[lane] = 0;
+                        fnew[lane] = 1;
+                        stat[lane] = 0;
+                    }
                 }
             }
         }

@@ -193,10 +193,14 @@ class BatchSolver:
         Q = np.ascontiguousarray(Q, dtype=np.float64)
         B = P.shape[1]
         I_N = np.ascontiguousarray(I_N, dtype=np.complex128) if n.q > 0 else np.zeros(0, np.complex128)
-        V_m = np.empty((n.H, n.n, B)); V_a = np.empty((n.H, n.n, B))
-        I_inj = np.empty((n.q, n.H, B), dtype=np.complex128)
-        nf = np.empty(B, np.int32); nh = np.empty(B, np.int32); st = np.empty(B, np.int32)
-        err = np.empty(B)
+        key = (B,)
+        if getattr(self, "_host_out_key", None) != key:      # pinned result buffers, reused
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+            self._host_out = (pin((n.H, n.n, B), torch.float64), pin((n.H, n.n, B), torch.float64),
+                              pin((n.q, n.H, B), torch.complex128), pin((B,), torch.int32),
+                              pin((B,), torch.int32), pin((B,), torch.int32), pin((B,), torch.float64))
+            self._host_out_key = key
+        V_m, V_a, I_inj, nf, nh, st, err = self._host_out
         vp = lambda a: C.c_void_p(a.ctypes.data)
         _lib.check(self._h, self.lib.hpf_solve_host(
             self._h, B, vp(P), vp(Q), vp(I_N), thresh_f, max_iter_f, thresh_h, max_iter_h,
@@ -215,6 +219,15 @@ class BatchSolver:
                                                     _ptr(V_m), _ptr(V_a), _ptr(nf), _ptr(err), _ptr(hist),
                                                     self._stream()))
         return V_m, V_a, nf, err, hist
+
+    def set_profiling(self, enabled=True):
+        _lib.check(self._h, self.lib.hpf_set_profiling(self._h, int(enabled)))
+
+    def last_kernel_ms(self):
+        """(fundamental-stage kernel ms, harmonic / fused kernel ms) of the last solve."""
+        ms = (C.c_double * 2)()
+        _lib.check(self._h, self.lib.hpf_last_kernel_ms(self._h, ms))
+        return float(ms[0]), float(ms[1])
 
     def struct_info(self):
         """-> dict(available, nZ, pivot_min, pivot_max) of the structured strategy."""

@@ -55,7 +55,7 @@ typedef struct hpf_handle hpf_t;
 #define HPF_ST_NONFINITE    3   /* NaN/Inf in the mismatch or the state            */
 
 /* ABI version of this header: bumped on any signature change. */
-#define HPF_ABI_VERSION 3
+#define HPF_ABI_VERSION 4
 int hpf_abi_version(void);
 
 /* Lifetime.  `device` is the CUDA ordinal the handle is bound to. */
@@ -199,6 +199,15 @@ int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a,
  *   in : V_m [H, n, B];  out: thd [2, n, B]  (plane 0 = THD_F, plane 1 = THD_R)
  */
 int hpf_thd(hpf_t* h, int B, const double* V_m, double* thd, void* stream);
+
+/*
+ * Per-kernel device timing of hpf_solve (for roofline accounting): when enabled, CUDA events
+ * are recorded on the launch stream around each kernel of a solve.  hpf_last_kernel_ms
+ * waits for the last solve and returns ms[0] = fundamental-stage kernel, ms[1] = harmonic
+ * kernel (structured strategy) or ms[0] = 0, ms[1] = fused kernel (dense strategy).
+ */
+int hpf_set_profiling(hpf_t* h, int enabled);
+int hpf_last_kernel_ms(hpf_t* h, double* ms /* [2] */);
 
 /* Dimensions derived by hpf_set_network (0 before it). */
 int hpf_dim_N(const hpf_t* h);
