@@ -768,6 +768,7 @@ static StructNet structnet(const hpf_t* h) {
     s.Ainv = h->d_Ainv;
     s.G = h->d_Gz;
     s.WNL = h->d_WNL;
+    s.yn_elems = h->n_dev * (h->coupled ? h->H * h->H : h->H);
     return s;
 }
 
@@ -777,7 +778,8 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     const DevNet net = devnet(h);
     const int nZ = net.nH - net.m;
     if (nZ < 1 || nZ > HPF_ST_MAXNZ) return HPF_OK;
-    if (harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, h->harm_warps) > (size_t)h->smem_optin)
+    if (harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, h->harm_warps,
+                             h->n_dev * (h->coupled ? h->H * h->H : h->H)) > (size_t)h->smem_optin)
         return HPF_OK;
     if (fund_tile_doubles_per_warp(net.n, net.Nf) * sizeof(double) > (size_t)h->smem_optin) return HPF_OK;
     double2* AZF = nullptr;
@@ -838,7 +840,7 @@ static int launch_wn(hpf_t* h, const DevNet& net, const StructNet& sn, int B, co
 template <int NW, int MAXROWS, int MINB>
 static int launch_harm_t(hpf_t* h, const DevNet& net, const StructNet& sn, const HarmTileArgs& ha,
                          bool persistent, cudaStream_t st) {
-    const size_t smem = harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, NW);
+    const size_t smem = harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, NW, sn.yn_elems);
     int occ = 0;
     int rc = prep_kernel(h, harm_tile_kernel<NW, MAXROWS, MINB>, smem, "hpf_solve", &occ, NW * 32);
     if (rc) return rc;
@@ -851,17 +853,17 @@ static int launch_harm_t(hpf_t* h, const DevNet& net, const StructNet& sn, const
     return HPF_OK;
 }
 
-// Variants: (warps per tile, rows of Z per warp in registers, min CTAs per SM).
+// Variants: (warps per tile, Z rows per Z warp in registers, min CTAs per SM).
 static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const HarmTileArgs& ha,
                        bool persistent, cudaStream_t st) {
     const int nw = h->harm_warps, nZ = sn.nZ;
     if (nw == 16) {
-        if (nZ <= 64) return h->harm_minb == 2 ? launch_harm_t<16, 4, 2>(h, net, sn, ha, persistent, st)
+        if (nZ <= 60) return h->harm_minb == 2 ? launch_harm_t<16, 4, 2>(h, net, sn, ha, persistent, st)
                                                : launch_harm_t<16, 4, 1>(h, net, sn, ha, persistent, st);
         return launch_harm_t<16, 7, 1>(h, net, sn, ha, persistent, st);
     }
-    if (nZ <= 56) return launch_harm_t<8, 7, 2>(h, net, sn, ha, persistent, st);
-    return launch_harm_t<8, 14, 1>(h, net, sn, ha, persistent, st);
+    if (nZ <= 49) return launch_harm_t<8, 7, 2>(h, net, sn, ha, persistent, st);
+    return launch_harm_t<8, 15, 1>(h, net, sn, ha, persistent, st);
 }
 
 static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, const double* I_N,

@@ -31,6 +31,7 @@ struct StructNet {
     const double2* Ainv;   // [nZ][nZ] row-major
     const double2* G;      // [nZ][m]
     const double2* WNL;    // [nZ][qH]  columns of Ainv that multiply the Norton currents
+    int yn_elems;          // complex entries of the Y_N table
 };
 
 // ---------------------------------------------------------------------------------------
@@ -383,16 +384,66 @@ wn_tile_kernel(const DevNet net, const StructNet sn, const double2* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------
+// Small per-lane dense solve in REGISTERS (NX known at compile time): loads the augmented
+// system from the strided smem array, Gaussian elimination with partial pivoting (per lane),
+// leaves the solution in x[].  Returns nonzero for a zero / non-finite pivot.
+template <int NX>
+__device__ __forceinline__ int lane_gauss_solve_reg(const double* M, const int lane, double* x) {
+    double A[NX][NX + 1];
+#pragma unroll
+    for (int r = 0; r < NX; ++r)
+#pragma unroll
+        for (int cc = 0; cc <= NX; ++cc) A[r][cc] = M[(r * (NX + 1) + cc) * HPF_T + lane];
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < NX; ++k) {
+        // partial pivoting without dynamic register indexing: bubble the largest row up
+#pragma unroll
+        for (int i = k + 1; i < NX; ++i) {
+            const bool sw = fabs(A[i][k]) > fabs(A[k][k]);
+#pragma unroll
+            for (int cc = k; cc <= NX; ++cc) {
+                const double t0 = A[k][cc], t1 = A[i][cc];
+                A[k][cc] = sw ? t1 : t0;
+                A[i][cc] = sw ? t0 : t1;
+            }
+        }
+        const double pv = fabs(A[k][k]);
+        if (!(pv > 0.0) || !(pv < CUDART_INF)) bad = 1;
+        const double r = 1.0 / A[k][k];
+#pragma unroll
+        for (int i = k + 1; i < NX; ++i) {
+            const double l = A[i][k] * r;
+#pragma unroll
+            for (int cc = k + 1; cc <= NX; ++cc) A[i][cc] -= l * A[k][cc];
+        }
+    }
+#pragma unroll
+    for (int k = NX - 1; k >= 0; --k) {
+        double sv = A[k][NX];
+#pragma unroll
+        for (int cc = k + 1; cc < NX; ++cc) sv -= A[k][cc] * x[cc];
+        x[k] = sv / A[k][k];
+    }
+    return bad;
+}
+
+// ---------------------------------------------------------------------------------------
 // Harmonic Newton-Raphson, structured step, 32 scenarios per CTA (lane = scenario).
 //
 // Because f_I = A_ZZ V_Z + A_ZF V_F + I_N,Z is linear in V, the product -A_ZZ^{-1} f_I of the
 // step has the closed form   u0 = -V_Z - G V_F - w_N   (w_N per scenario, see above): no
-// matrix-vector product with A_ZZ^{-1} is left inside the Newton loop.  One round =
-//   A  load refilled lanes, unit phasors E = e^{j theta}                       | barrier
-//   B  mismatch rows (HG:360-388) incl. the Norton contraction, ||f||_inf       | barrier
-//   C  decisions; results of finished lanes; t = u0 rows in registers;
-//      last warp: border system for the linear buses' fundamental unknowns      | barrier
-//   D  u_Z = t - G u_F, polar conversion, state update; warp 0: lane refill     | barrier
+// matrix-vector product with A_ZZ^{-1} is left inside the Newton loop.
+//
+// Warp roles: the LAST warp is the "border warp": it owns the fundamental rows of the linear
+// buses (F: state, power mismatch, the (2m-1-c)-sized border system, lane bookkeeping and
+// refill); the other NW-1 warps own the Z rows.  One round:
+//   A  load refilled lanes; F rows: apply the pending update; unit phasors E = e^{j theta}  | barrier
+//   B  Z warps: current-mismatch rows (HG:326-357) incl. the Norton contraction
+//      border warp: power mismatch (HG:372-380) and the border system -> u_F               | barrier
+//   C  decisions (every warp, same result); results of finished lanes; Z warps:
+//      u_Z = -V_Z - G (V_F + u_F) - w_N, polar conversion, state update;
+//      border warp: status words, iteration counters, refill from the global queue          | barrier
 struct HarmTileArgs {
     int B, flags, step_only;
     const double *P, *Q;
@@ -408,52 +459,71 @@ struct HarmTileArgs {
     double* dx_out;          // step_only: [N, B] the Newton update dx (x_new = x - dx)
 };
 
-#define HPF_ST_MAXNZ 112     // rows of Z kept in registers: HPF_ST_MAXNZ / (warps per tile) per warp
+#define HPF_ST_MAXNZ 105     // Z rows are held in registers: <= 15 rows per Z warp, 7 Z warps
 
-__host__ __device__ inline size_t harm_tile_smem_bytes(int n, int H, int m, int c, int q, int nwarps) {
+__host__ __device__ inline size_t harm_tile_const_doubles(int n, int H, int m, int yn_elems) {
+    const size_t nH = (size_t)n * H, nZ = nH - m;
+    return 2 * ((size_t)H * n * n + yn_elems + nZ * m);
+}
+
+__host__ __device__ inline size_t harm_tile_smem_bytes(int n, int H, int m, int c, int q, int nwarps,
+                                                       int yn_elems) {
     const size_t nH = (size_t)n * H, nZ = nH - m, nx = (size_t)(m - 1) + (m - c);
-    const size_t d = 4 * nH + 2 * nZ + 2 * m + 2 * n + 2 * q * H + 2 * m + nx * (nx + 1) + 2 * m +
-                     nwarps + 2;
-    return d * HPF_T * sizeof(double) + 8 * HPF_T * sizeof(int) + 64;
+    // per lane: Vm, Va, Ere, Eim [nH]; w_N [2 nZ]; I_N, I_inj [2 qH each]; FS, I1, PQ, UF [2 m each];
+    // M [nx (nx+1)]; DXF [nx]; red [nwarps]
+    const size_t d = 4 * nH + 2 * nZ + 4 * (size_t)q * H + 8 * m + nx * (nx + 1) + nx + nwarps;
+    return (d * HPF_T + harm_tile_const_doubles(n, H, m, yn_elems)) * sizeof(double) +
+           8 * HPF_T * sizeof(int) + 64;
 }
 
 template <int NW, int MAXROWS, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     extern __shared__ __align__(16) double smem[];
+    constexpr int CW = NW - 1;                     // Z ("compute") warps
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool border = (warp == NW - 1);
     const int n = net.n, m = net.m, c = net.c, H = net.H, q = net.q, nH = net.nH;
-    const int nZ = sn.nZ, nx = sn.nx;
+    const int nZ = sn.nZ, nx = sn.nx, nth = m - 1;
     const size_t B = (size_t)a.B;
 #define AT(X, i) X[(i) * HPF_T + lane]
-    double* p = smem;
+    // ---- shared memory: network constants, then per-lane arrays ----
+    double2* sY = reinterpret_cast<double2*>(smem);
+    double2* sYN = sY + (size_t)H * n * n;
+    double2* sG = sYN + sn.yn_elems;
+    double* p = reinterpret_cast<double*>(sG + (size_t)nZ * m);
     double* Vm = p;  p += nH * HPF_T;
     double* Va = p;  p += nH * HPF_T;
     double* Ere = p; p += nH * HPF_T;
     double* Eim = p; p += nH * HPF_T;
     double* Wre = p; p += nZ * HPF_T;      // w_N (index z = s - m), constant per scenario
     double* Wim = p; p += nZ * HPF_T;
-    double* FSre = p; p += m * HPF_T;      // power mismatch of buses s < m
-    double* FSim = p; p += m * HPF_T;
-    double* I1re = p; p += n * HPF_T;      // (Y1 V1)_i, rows i < m are used by the border system
-    double* I1im = p; p += n * HPF_T;
+    double* INre = p; p += q * H * HPF_T;  // I_N of the lane's scenario
+    double* INim = p; p += q * H * HPF_T;
     double* IJre = p; p += q * H * HPF_T;  // Norton injections (result I_inj)
     double* IJim = p; p += q * H * HPF_T;
+    double* FSre = p; p += m * HPF_T;      // power mismatch of buses s < m
+    double* FSim = p; p += m * HPF_T;
+    double* I1re = p; p += m * HPF_T;      // (Y1 V1)_i, i < m
+    double* I1im = p; p += m * HPF_T;
     double* Pl = p;  p += m * HPF_T;
     double* Ql = p;  p += m * HPF_T;
-    double* M = p;   p += nx * (nx + 1) * HPF_T;
     double* UFre = p; p += m * HPF_T;
     double* UFim = p; p += m * HPF_T;
+    double* M = p;   p += nx * (nx + 1) * HPF_T;
+    double* DXF = p; p += nx * HPF_T;
     double* red = p; p += NW * HPF_T;
-    double* errv = p; p += HPF_T;
-    p += HPF_T;
-    int* scen = reinterpret_cast<int*>(p);
-    int* itc = scen + HPF_T;
+    int* scen2 = reinterpret_cast<int*>(p);        // [2][32] double-buffered scenario index
+    int* itc = scen2 + 2 * HPF_T;
     int* stat = itc + HPF_T;
     int* fnew = stat + HPF_T;
 
+    for (int t = threadIdx.x; t < H * n * n; t += NW * 32) sY[t] = net.Y[t];
+    for (int t = threadIdx.x; t < sn.yn_elems; t += NW * 32) sYN[t] = net.YN[t];
+    for (int t = threadIdx.x; t < nZ * m; t += NW * 32) sG[t] = sn.G[t];
+
     // ---- initial fill ----
-    if (warp == 0) {
+    if (border) {
         int idx;
         if (a.step_only) {
             idx = blockIdx.x * HPF_T + lane;
@@ -463,124 +533,238 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
             base = __shfl_sync(0xffffffffu, base, 0);
             idx = base + lane;
         }
-        scen[lane] = ((size_t)idx < B) ? idx : -1;
+        scen2[lane] = ((size_t)idx < B) ? idx : -1;
         itc[lane] = 0;
         fnew[lane] = 1;
         stat[lane] = 0;
     }
     __syncthreads();
+    int cur = 0;
+    bool pendF = false;                            // border warp: F-row update of the last step pending
 
     for (;;) {
+        const int* scen = scen2 + cur * HPF_T;
+        const int sc = scen[lane];
+        const int itv = itc[lane];          // read before barrier A; the border warp updates it in C
         // ================= A: load refilled lanes, unit phasors =================
         {
-            const int sc = scen[lane];
             const bool isnew = fnew[lane] != 0;
-            if (isnew) {
-                if (sc >= 0) {
-                    for (int s = warp; s < nH; s += NW) {
-                        if (a.step_only || s < n) {
-                            AT(Vm, s) = a.V_m[(size_t)s * B + sc];
-                            AT(Va, s) = a.V_a[(size_t)s * B + sc];
+            if (border) {
+                // F rows (s < m): state, P, Q, status; pending update; sincos
+                if (isnew) {
+                    for (int s = 0; s < m; ++s) {
+                        AT(Vm, s) = (sc >= 0) ? __ldcs(a.V_m + (size_t)s * B + sc) : 1.0;
+                        AT(Va, s) = (sc >= 0) ? __ldcs(a.V_a + (size_t)s * B + sc) : 0.0;
+                        AT(Pl, s) = (sc >= 0) ? __ldcs(a.P + (size_t)s * B + sc) : 0.0;
+                        AT(Ql, s) = (sc >= 0) ? __ldcs(a.Q + (size_t)s * B + sc) : 0.0;
+                    }
+                    stat[lane] = (sc >= 0 && !a.step_only) ? a.status[sc] : 0;
+                } else if (pendF) {
+                    for (int i = 1; i < m; ++i) {                 // x_new = x + delta (HG:476-485)
+                        AT(Va, i) += AT(DXF, i - 1);
+                        if (i >= c) AT(Vm, i) += AT(DXF, nth + (i - c));
+                    }
+                }
+                for (int s = 0; s < m; ++s) {
+                    double sn_, cs_;
+                    sincos(AT(Va, s), &sn_, &cs_);
+                    AT(Ere, s) = cs_;
+                    AT(Eim, s) = sn_;
+                }
+            } else {
+                if (isnew) {
+                    for (int s = m + warp; s < nH; s += CW) {
+                        if (sc >= 0 && (a.step_only || s < n)) {
+                            AT(Vm, s) = __ldcs(a.V_m + (size_t)s * B + sc);
+                            AT(Va, s) = __ldcs(a.V_a + (size_t)s * B + sc);
                         } else {
-                            AT(Vm, s) = 0.1;       // flat start of the harmonics (HG:183)
+                            AT(Vm, s) = (sc >= 0) ? 0.1 : 1.0;     // flat start of the harmonics (HG:183)
                             AT(Va, s) = 0.0;
                         }
                     }
-                    for (int z = warp; z < nZ; z += NW) {
-                        const double2 w = a.wN[(size_t)z * B + sc];
+                    for (int z = warp; z < nZ; z += CW) {
+                        double2 w = make_double2(0.0, 0.0);
+                        if (sc >= 0) w = __ldcs(a.wN + (size_t)z * B + sc);
                         AT(Wre, z) = w.x; AT(Wim, z) = w.y;
                     }
-                    for (int s = warp; s < m; s += NW) {
-                        AT(Pl, s) = a.P[(size_t)s * B + sc];
-                        AT(Ql, s) = a.Q[(size_t)s * B + sc];
+                    for (int u = warp; u < q * H; u += CW) {
+                        double2 w = make_double2(0.0, 0.0);
+                        if (sc >= 0) w = __ldcs(a.I_N + (size_t)u * B + sc);
+                        AT(INre, u) = w.x; AT(INim, u) = w.y;
                     }
-                    if (warp == 0) stat[lane] = a.step_only ? 0 : a.status[sc];
-                } else {
-                    for (int s = warp; s < nH; s += NW) { AT(Vm, s) = 1.0; AT(Va, s) = 0.0; }
-                    for (int z = warp; z < nZ; z += NW) { AT(Wre, z) = 0.0; AT(Wim, z) = 0.0; }
-                    for (int s = warp; s < m; s += NW) { AT(Pl, s) = 0.0; AT(Ql, s) = 0.0; }
                 }
-            }
-            for (int s = warp; s < nH; s += NW) {
-                double sn_, cs_;
-                sincos(AT(Va, s), &sn_, &cs_);
-                AT(Ere, s) = cs_;
-                AT(Eim, s) = sn_;
+                for (int s = m + warp; s < nH; s += CW) {
+                    double sn_, cs_;
+                    sincos(AT(Va, s), &sn_, &cs_);
+                    AT(Ere, s) = cs_;
+                    AT(Eim, s) = sn_;
+                }
             }
         }
         __syncthreads();
-        // ================= B: mismatch rows (HG:360-388) =================
+        // ================= B: mismatch rows (HG:360-388); border system =================
         {
             double mx = 0.0;
-            const int sc = scen[lane];
-            // heavy rows first: nonlinear buses, (Y_h V_h)_i + I_N - sum_p Y_N[h][p] V_p,i
-            for (int u = warp; u < q * H; u += NW) {
-                const int k = u / H, h = u - k * H, i = m + k, s = h * n + i;
-                const int dev = net.dev_of_nl[k];
-                const double2 in = (sc >= 0) ? a.I_N[(size_t)u * B + sc] : make_double2(0.0, 0.0);
-                double2 acc;
-                if (net.coupled) {
-                    const double2* row = net.YN + ((size_t)dev * H + h) * H;
-                    acc = make_double2(0.0, 0.0);
-                    for (int pp = 0; pp < H; ++pp) {
-                        const int t2 = pp * n + i;
-                        const double vm = AT(Vm, t2);
-                        acc = cadd(acc, cmul(ldg2(row + pp), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+            if (!border) {
+                // heavy rows first: nonlinear buses, (Y_h V_h)_i + I_N - sum_p Y_N[h][p] V_p,i
+                for (int u = warp; u < q * H; u += CW) {
+                    const int k = u / H, h = u - k * H, i = m + k, s = h * n + i;
+                    const int dev = net.dev_of_nl[k];
+                    double2 acc;
+                    if (net.coupled) {
+                        const double2* row = sYN + ((size_t)dev * H + h) * H;
+                        acc = make_double2(0.0, 0.0);
+                        for (int pp = 0; pp < H; ++pp) {
+                            const int t2 = pp * n + i;
+                            const double vm = AT(Vm, t2);
+                            acc = cadd(acc, cmul(row[pp], make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                        }
+                    } else {
+                        const double vm = AT(Vm, s);
+                        acc = cmul(sYN[(size_t)dev * H + h], make_double2(vm * AT(Ere, s), vm * AT(Eim, s)));
                     }
-                } else {
-                    const double vm = AT(Vm, s);
-                    acc = cmul(ldg2(net.YN + (size_t)dev * H + h), make_double2(vm * AT(Ere, s), vm * AT(Eim, s)));
+                    const double2 inj = make_double2(AT(INre, u) - acc.x, AT(INim, u) - acc.y);
+                    AT(IJre, u) = inj.x; AT(IJim, u) = inj.y;
+                    const double2* Yrow = sY + ((size_t)h * n + i) * n;
+                    double2 f = make_double2(0.0, 0.0);
+                    for (int j = 0; j < n; ++j) {
+                        const int t2 = h * n + j;
+                        const double vm = AT(Vm, t2);
+                        f = cadd(f, cmul(Yrow[j], make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                    }
+                    f = cadd(f, inj);
+                    const double v1 = fabs(f.x), v2 = fabs(f.y);      // s >= m >= c: both parts are rows
+                    const double v = (v2 != v2 || v2 > v1) ? v2 : v1;
+                    mx = (v != v || v > mx) ? v : mx;
                 }
-                const double2 inj = csub(in, acc);
-                AT(IJre, u) = inj.x; AT(IJim, u) = inj.y;
-                const double2* Yrow = net.Y + ((size_t)h * n + i) * n;
-                double2 f = make_double2(0.0, 0.0);
-                for (int j = 0; j < n; ++j) {
-                    const int t2 = h * n + j;
-                    const double vm = AT(Vm, t2);
-                    f = cadd(f, cmul(ldg2(Yrow + j), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                // light rows: linear buses at the harmonics h >= 1 (index)
+                const int nlin = m * (H - 1);
+                for (int t = warp; t < nlin; t += CW) {
+                    const int h = 1 + t / m, i = t - (h - 1) * m;
+                    const double2* Yrow = sY + ((size_t)h * n + i) * n;
+                    double2 f = make_double2(0.0, 0.0);
+                    for (int j = 0; j < n; ++j) {
+                        const int t2 = h * n + j;
+                        const double vm = AT(Vm, t2);
+                        f = cadd(f, cmul(Yrow[j], make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                    }
+                    const double v1 = fabs(f.x), v2 = fabs(f.y);
+                    const double v = (v2 != v2 || v2 > v1) ? v2 : v1;
+                    mx = (v != v || v > mx) ? v : mx;
                 }
-                if (h == 0) { AT(I1re, i) = f.x; AT(I1im, i) = f.y; }
-                f = cadd(f, inj);
-                const double v1 = fabs(f.x), v2 = fabs(f.y);      // s >= m >= c: both parts are rows
-                const double v = (v2 != v2 || v2 > v1) ? v2 : v1;
-                mx = (v != v || v > mx) ? v : mx;
-            }
-            // light rows: linear buses at every harmonic
-            const int nlin = m * H;
-            for (int t = warp; t < nlin; t += NW) {
-                const int h = t / m, i = t - h * m, s = h * n + i;
-                const double2* Yrow = net.Y + ((size_t)h * n + i) * n;
-                double2 f = make_double2(0.0, 0.0);
-                for (int j = 0; j < n; ++j) {
-                    const int t2 = h * n + j;
-                    const double vm = AT(Vm, t2);
-                    f = cadd(f, cmul(ldg2(Yrow + j), make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
-                }
-                if (h == 0) {
+            } else {
+                // ---- border warp: power mismatch of the linear buses (HG:372-380) ----
+                for (int i = 0; i < m; ++i) {
+                    const double2* Yrow = sY + (size_t)i * n;
+                    double2 f = make_double2(0.0, 0.0);
+                    for (int j = 0; j < n; ++j) {
+                        const double vm = AT(Vm, j);
+                        f = cadd(f, cmul(Yrow[j], make_double2(vm * AT(Ere, j), vm * AT(Eim, j))));
+                    }
                     AT(I1re, i) = f.x; AT(I1im, i) = f.y;
                     if (i == 0) continue;                            // slack: no row
                     const double vm = AT(Vm, i);
                     const double2 v = make_double2(vm * AT(Ere, i), vm * AT(Eim, i));
                     const double2 sl = cmul(v, make_double2(f.x, -f.y));
-                    f = make_double2(AT(Pl, i) + sl.x, AT(Ql, i) + sl.y);
-                    AT(FSre, i) = f.x; AT(FSim, i) = f.y;
+                    const double2 fs = make_double2(AT(Pl, i) + sl.x, AT(Ql, i) + sl.y);
+                    AT(FSre, i) = fs.x; AT(FSim, i) = fs.y;
+                    double v1 = fabs(fs.x);
+                    if (i >= c) {
+                        const double v2 = fabs(fs.y);
+                        v1 = (v2 != v2 || v2 > v1) ? v2 : v1;
+                    }
+                    mx = (v1 != v1 || v1 > mx) ? v1 : mx;
                 }
-                double v1 = fabs(f.x);
-                if (s - 1 >= c - 1) {
-                    const double v2 = fabs(f.y);
-                    v1 = (v2 != v2 || v2 > v1) ? v2 : v1;
+                // ---- border system for x_F: every entry is accumulated in registers ----
+                const int w = nx + 1;
+                for (int i = 1; i < m; ++i) {
+                    const double vmi = AT(Vm, i);
+                    const double2 ei = make_double2(AT(Ere, i), AT(Eim, i));
+                    const double2 vi = make_double2(vmi * ei.x, vmi * ei.y);
+                    const double2 i1 = make_double2(AT(I1re, i), AT(I1im, i));
+                    const double2 jvi = cmulj(vi);
+                    const int rr = i - 1, ri = nth + (i - c);
+                    const bool has_im = (i >= c);
+                    for (int col = 0; col <= nx; ++col) {
+                        double2 e;
+                        const bool is_rhs = (col == nx);
+                        const bool is_v = (col >= nth);
+                        const int j = is_rhs ? 0 : (is_v ? c + (col - nth) : col + 1);
+                        double2 vj = make_double2(0.0, 0.0), ej = vj;
+                        if (is_rhs) {
+                            e = make_double2(-AT(FSre, i), -AT(FSim, i));
+                        } else {
+                            const double2 y = sY[(size_t)i * n + j];
+                            const double vmj = AT(Vm, j);
+                            ej = make_double2(AT(Ere, j), AT(Eim, j));
+                            vj = make_double2(vmj * ej.x, vmj * ej.y);
+                            if (is_v) {                               // dS_i/dV_m,j  (HG:458-459)
+                                e = cmul(vi, cconj(cmul(y, ej)));
+                                if (i == j) e = cadd(cmul(ei, cconj(i1)), e);
+                            } else {                                  // dS_i/dtheta_j (HG:457)
+                                const double2 yv = cmul(y, vj);
+                                e = cmul(jvi, cconj((i == j) ? csub(i1, yv) : cneg(yv)));
+                            }
+                        }
+                        // fundamental nonlinear buses, eliminated through u_Z1 = u0 - G T_F x_F
+                        for (int k = 0; k < q; ++k) {
+                            const int bk = m + k;
+                            const double2 y = sY[(size_t)i * n + bk];
+                            if (y.x == 0.0 && y.y == 0.0) continue;
+                            const double vmb = AT(Vm, bk);
+                            const double2 eb = make_double2(AT(Ere, bk), AT(Eim, bk));
+                            const double2 vb = make_double2(vmb * eb.x, vmb * eb.y);
+                            const double2 ak = cmul(jvi, cconj(cneg(cmul(y, vb))));    // dS_i/dtheta_b
+                            const double2 vk = cmul(vi, cconj(cmul(y, eb)));           // dS_i/dV_m,b
+                            double2 uu;
+                            if (is_rhs) {            // u0 of row z = k (closed form)
+                                uu = make_double2(vb.x + AT(Wre, k), vb.y + AT(Wim, k));
+                                for (int i2 = 0; i2 < m; ++i2) {
+                                    const double v2 = AT(Vm, i2);
+                                    uu = cadd(uu, cmul(sG[(size_t)k * m + i2], make_double2(v2 * AT(Ere, i2), v2 * AT(Eim, i2))));
+                                }
+                                uu = cneg(uu);
+                            } else {                 // column of G T_F: G (j V_j) or G E_j
+                                uu = cmul(sG[(size_t)k * m + j], is_v ? ej : cmulj(vj));
+                            }
+                            const double2 ce = cmul(cconj(eb), uu);
+                            const double dth = ce.y / vmb, dvm = ce.x;
+                            e.x -= ak.x * dth + vk.x * dvm;
+                            e.y -= ak.y * dth + vk.y * dvm;
+                        }
+                        AT(M, rr * w + col) = e.x;
+                        if (has_im) AT(M, ri * w + col) = e.y;
+                    }
                 }
-                mx = (v1 != v1 || v1 > mx) ? v1 : mx;
+                int badp = 0;
+                double xs[4] = {0.0, 0.0, 0.0, 0.0};
+                switch (nx) {
+                    case 0: break;
+                    case 1: badp = lane_gauss_solve_reg<1>(M, lane, xs); break;
+                    case 2: badp = lane_gauss_solve_reg<2>(M, lane, xs); break;
+                    case 3: badp = lane_gauss_solve_reg<3>(M, lane, xs); break;
+                    case 4: badp = lane_gauss_solve_reg<4>(M, lane, xs); break;
+                    default: badp = lane_gauss_solve(M, nx, lane); break;
+                }
+                if (nx <= 4) { for (int t = 0; t < nx; ++t) AT(DXF, t) = xs[t]; }
+                else { for (int t = 0; t < nx; ++t) AT(DXF, t) = AT(M, t * w + nx); }
+                if (badp) stat[lane] |= 0x200;
+                AT(UFre, 0) = 0.0; AT(UFim, 0) = 0.0;
+                for (int i = 1; i < m; ++i) {
+                    const double dth = AT(DXF, i - 1);
+                    const double dvm = (i >= c) ? AT(DXF, nth + i - c) : 0.0;
+                    const double vmi = AT(Vm, i);
+                    const double2 ei = make_double2(AT(Ere, i), AT(Eim, i));
+                    AT(UFre, i) = -(vmi * ei.y) * dth + ei.x * dvm;      // u_F = (j V_i) dtheta + E_i dV_m
+                    AT(UFim, i) = (vmi * ei.x) * dth + ei.y * dvm;
+                }
             }
             AT(red, warp) = mx;
         }
         __syncthreads();
-        // ================= C: decisions (every warp, same result), finished lanes =================
-        bool step, done;
-        double err;
+        // ================= C: decisions, finished lanes, update, refill =================
+        double err = 0.0;
         {
-            err = 0.0;
             bool bad = false;
 #pragma unroll
             for (int w2 = 0; w2 < NW; ++w2) {
@@ -589,154 +773,48 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 err = fmax(err, v);
             }
             if (bad) err = CUDART_NAN;
-            const bool active = scen[lane] >= 0;
-            const bool cont = active && (err > a.thresh_h) && (itc[lane] < a.max_h);
-            step = a.step_only ? active : cont;
-            done = active && !cont && !a.step_only;
-            if (__ballot_sync(0xffffffffu, active) == 0u) break;      // uniform over the CTA
         }
+        const bool active = sc >= 0;
+        const bool cont = active && (err > a.thresh_h) && (itv < a.max_h);
+        const bool step = a.step_only ? active : cont;
+        const bool done = active && !cont && !a.step_only;
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;          // uniform over the CTA
         const unsigned donemask = __ballot_sync(0xffffffffu, done);
-        if (donemask) {
-            // post-processing (HG:547-549) + write-out of the finished lanes
-            const int sc = scen[lane];
-            int bad = 0;
-            if (done) {
-                for (int s = warp; s < nH; s += NW) {
-                    double vm = AT(Vm, s), va = AT(Va, s), r = va;
-                    if (!(a.flags & HPF_SOLVE_RAW)) {
-                        if (vm < 0.0) va += CUDART_PI;
-                        const double twopi = 2.0 * CUDART_PI;
-                        r = fmod(va, twopi);
-                        if (r != 0.0) { if (r < 0.0) r += twopi; } else r = 0.0;
-                        if (vm < 0.0) vm = -vm;
-                    }
-                    if (!(vm == vm) || !(r == r) || fabs(vm) == CUDART_INF) bad = 1;
-                    a.V_m[(size_t)s * B + sc] = vm;
-                    a.V_a[(size_t)s * B + sc] = r;
+        if (donemask && done) {
+            // post-processing (HG:547-549) + write-out of the finished lanes (rows over all warps)
+            for (int s = warp; s < nH; s += NW) {
+                double vm = AT(Vm, s), va = AT(Va, s), r = va;
+                if (!(a.flags & HPF_SOLVE_RAW)) {
+                    if (vm < 0.0) va += CUDART_PI;
+                    const double twopi = 2.0 * CUDART_PI;
+                    r = fmod(va, twopi);
+                    if (r != 0.0) { if (r < 0.0) r += twopi; } else r = 0.0;
+                    if (vm < 0.0) vm = -vm;
                 }
-                if (a.I_inj)
-                    for (int u = warp; u < q * H; u += NW)
-                        a.I_inj[(size_t)u * B + sc] = make_double2(AT(IJre, u), AT(IJim, u));
-                if (bad) atomicOr(&stat[lane], 0x100);
-                if (warp == 0) errv[lane] = err;
+                a.V_m[(size_t)s * B + sc] = vm;
+                a.V_a[(size_t)s * B + sc] = r;
             }
+            if (a.I_inj)
+                for (int u = warp; u < q * H; u += NW)
+                    a.I_inj[(size_t)u * B + sc] = make_double2(AT(IJre, u), AT(IJim, u));
         }
-        // t_z = u0_z = -V_z - sum_i G[z][i] V_i - w_N,z for this warp's rows (registers)
-        double2 tz[MAXROWS];
-#pragma unroll
-        for (int r = 0; r < MAXROWS; ++r) {
-            const int z = warp + r * NW;
-            tz[r] = make_double2(0.0, 0.0);
-            if (z < nZ) {
-                const int s = z + m;
-                const double vm = AT(Vm, s);
-                double2 acc = make_double2(vm * AT(Ere, s) + AT(Wre, z), vm * AT(Eim, s) + AT(Wim, z));
-                for (int i = 0; i < m; ++i) {
-                    const double vi = AT(Vm, i);
-                    acc = cadd(acc, cmul(ldg2(sn.G + (size_t)z * m + i), make_double2(vi * AT(Ere, i), vi * AT(Eim, i))));
-                }
-                tz[r] = cneg(acc);
-            }
-        }
-        // border system for the fundamental unknowns of the linear buses (last warp)
-        if (warp == NW - 1) {
-            const int w = nx + 1, nth = m - 1;
-            for (int t = 0; t < nx * w; ++t) AT(M, t) = 0.0;
-            for (int i = 1; i < m; ++i) {
-                const double vmi = AT(Vm, i);
-                const double2 ei = make_double2(AT(Ere, i), AT(Eim, i));
-                const double2 vi = make_double2(vmi * ei.x, vmi * ei.y);
-                const double2 i1 = make_double2(AT(I1re, i), AT(I1im, i));
-                const double2 jvi = cmulj(vi);
-                const int rr = i - 1, ri = nth + (i - c);
-                const bool has_im = (i >= c);
-                for (int j = 1; j < m; ++j) {                         // HG:457-467
-                    const double2 y = ldg2(net.Y + (size_t)i * n + j);
-                    const double vmj = AT(Vm, j);
-                    const double2 ej = make_double2(AT(Ere, j), AT(Eim, j));
-                    const double2 vj = make_double2(vmj * ej.x, vmj * ej.y);
-                    const double2 yv = cmul(y, vj);
-                    const double2 d = (i == j) ? csub(i1, yv) : cneg(yv);
-                    const double2 dA = cmul(jvi, cconj(d));
-                    AT(M, rr * w + (j - 1)) += dA.x;
-                    if (has_im) AT(M, ri * w + (j - 1)) += dA.y;
-                    if (j >= c) {
-                        double2 dV = cmul(vi, cconj(cmul(y, ej)));
-                        if (i == j) dV = cadd(cmul(ei, cconj(i1)), dV);
-                        AT(M, rr * w + nth + (j - c)) += dV.x;
-                        if (has_im) AT(M, ri * w + nth + (j - c)) += dV.y;
-                    }
-                }
-                double2 rhs = make_double2(-AT(FSre, i), -AT(FSim, i));
-                for (int k = 0; k < q; ++k) {     // fundamental nonlinear buses, eliminated via u_Z1
-                    const int bk = m + k;
-                    const double2 y = ldg2(net.Y + (size_t)i * n + bk);
-                    if (y.x == 0.0 && y.y == 0.0) continue;
-                    const double vmb = AT(Vm, bk);
-                    const double2 eb = make_double2(AT(Ere, bk), AT(Eim, bk));
-                    const double2 vb = make_double2(vmb * eb.x, vmb * eb.y);
-                    const double2 ak = cmul(jvi, cconj(cneg(cmul(y, vb))));    // dS_i/dtheta_b
-                    const double2 vk = cmul(vi, cconj(cmul(y, eb)));           // dS_i/dV_m,b
-                    const double rvm = 1.0 / vmb;
-                    // u0 of row z = k (closed form, same expression as tz)
-                    double2 u0 = make_double2(vb.x + AT(Wre, k), vb.y + AT(Wim, k));
-                    for (int i2 = 0; i2 < m; ++i2) {
-                        const double v2 = AT(Vm, i2);
-                        u0 = cadd(u0, cmul(ldg2(sn.G + (size_t)k * m + i2), make_double2(v2 * AT(Ere, i2), v2 * AT(Eim, i2))));
-                    }
-                    u0 = cneg(u0);
-                    const double2 w0 = cmul(cconj(eb), u0);
-                    const double dth0 = w0.y * rvm, dvm0 = w0.x;
-                    rhs.x -= ak.x * dth0 + vk.x * dvm0;
-                    rhs.y -= ak.y * dth0 + vk.y * dvm0;
-                    for (int j = 1; j < m; ++j) {
-                        const double2 g = ldg2(sn.G + (size_t)k * m + j);
-                        const double vmj = AT(Vm, j);
-                        const double2 ej = make_double2(AT(Ere, j), AT(Eim, j));
-                        const double2 vj = make_double2(vmj * ej.x, vmj * ej.y);
-                        {   // theta_j column: W = G (j V_j)
-                            const double2 ce = cmul(cconj(eb), cmul(g, cmulj(vj)));
-                            const double dth = ce.y * rvm, dvm = ce.x;
-                            AT(M, rr * w + (j - 1)) -= ak.x * dth + vk.x * dvm;
-                            if (has_im) AT(M, ri * w + (j - 1)) -= ak.y * dth + vk.y * dvm;
-                        }
-                        if (j >= c) {   // V_m,j column: W = G E_j
-                            const double2 ce = cmul(cconj(eb), cmul(g, ej));
-                            const double dth = ce.y * rvm, dvm = ce.x;
-                            AT(M, rr * w + nth + (j - c)) -= ak.x * dth + vk.x * dvm;
-                            if (has_im) AT(M, ri * w + nth + (j - c)) -= ak.y * dth + vk.y * dvm;
-                        }
-                    }
-                }
-                AT(M, rr * w + nx) = rhs.x;
-                if (has_im) AT(M, ri * w + nx) = rhs.y;
-            }
-            const int badp = (nx > 0) ? lane_gauss_solve(M, nx, lane) : 0;
-            if (badp && step) atomicOr(&stat[lane], 0x200);
-            AT(UFre, 0) = 0.0; AT(UFim, 0) = 0.0;
-            for (int i = 1; i < m; ++i) {
-                const double dth = AT(M, (i - 1) * w + nx);
-                const double dvm = (i >= c) ? AT(M, (nth + i - c) * w + nx) : 0.0;
-                const double vmi = AT(Vm, i);
-                const double2 ei = make_double2(AT(Ere, i), AT(Eim, i));
-                AT(UFre, i) = -(vmi * ei.y) * dth + ei.x * dvm;      // u_F = (j V_i) dtheta + E_i dV_m
-                AT(UFim, i) = (vmi * ei.x) * dth + ei.y * dvm;
-            }
-        }
-        __syncthreads();
-        // ================= D: u_Z = t - G u_F, polar conversion, state update =================
-        {
-            const int sc = scen[lane];
+        if (!border) {
+            // u_z = -V_z - sum_i G[z][i] (V_i + u_F,i) - w_N,z ; polar conversion; update
 #pragma unroll
             for (int r = 0; r < MAXROWS; ++r) {
-                const int z = warp + r * NW;
+                const int z = warp + r * CW;
                 if (z < nZ) {
-                    double2 u = tz[r];
-                    for (int i = 1; i < m; ++i)
-                        u = csub(u, cmul(ldg2(sn.G + (size_t)z * m + i), make_double2(AT(UFre, i), AT(UFim, i))));
                     const int s = z + m;
-                    const double2 wv = cmul(make_double2(AT(Ere, s), -AT(Eim, s)), u);
                     const double vm = AT(Vm, s);
+                    const double2 es = make_double2(AT(Ere, s), AT(Eim, s));
+                    double2 acc = make_double2(vm * es.x + AT(Wre, z), vm * es.y + AT(Wim, z));
+                    for (int i = 0; i < m; ++i) {
+                        const double vi = AT(Vm, i);
+                        const double2 tot = make_double2(vi * AT(Ere, i) + AT(UFre, i), vi * AT(Eim, i) + AT(UFim, i));
+                        acc = cadd(acc, cmul(sG[(size_t)z * m + i], tot));
+                    }
+                    const double2 u = cneg(acc);
+                    const double2 wv = cmul(make_double2(es.x, -es.y), u);
                     const double dth = wv.y / vm, dvm = wv.x;
                     if (a.step_only) {
                         if (sc >= 0) {
@@ -749,52 +827,47 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     }
                 }
             }
-            if (warp == NW - 1) {
-                const int w = nx + 1, nth = m - 1;
-                for (int i = 1; i < m; ++i) {
-                    const double dth = AT(M, (i - 1) * w + nx);
-                    const double dvm = (i >= c) ? AT(M, (nth + i - c) * w + nx) : 0.0;
-                    if (a.step_only) {
-                        if (sc >= 0) {
-                            a.dx_out[(size_t)(i - 1) * B + sc] = -dth;
-                            if (i >= c) a.dx_out[(size_t)((nH - 1) + i - c) * B + sc] = -dvm;
-                        }
-                    } else if (step) {
-                        AT(Va, i) += dth;
-                        if (i >= c) AT(Vm, i) += dvm;
+        } else {
+            if (a.step_only) {
+                if (sc >= 0)
+                    for (int i = 1; i < m; ++i) {
+                        a.dx_out[(size_t)(i - 1) * B + sc] = -AT(DXF, i - 1);
+                        if (i >= c) a.dx_out[(size_t)((nH - 1) + i - c) * B + sc] = -AT(DXF, nth + i - c);
                     }
-                }
-            }
-            if (a.step_only) break;
-            // bookkeeping + refill (warp 0).  Nobody reads scen/itc/fnew/stat in phase D.
-            if (warp == 0) {
+            } else {
+                // status words, iteration counters, refill (only this warp touches itc/stat/fnew)
+                int* scen_next = scen2 + (cur ^ 1) * HPF_T;
+                int nsc = sc;
                 if (done) {
                     int st = stat[lane] & 0xff;
-                    const int extra = stat[lane] & ~0xff;
-                    if ((extra & 0x200) && st == HPF_ST_CONVERGED) st = HPF_ST_SINGULAR;
-                    if (itc[lane] >= a.max_h && st == HPF_ST_CONVERGED) st = HPF_ST_MAXITER;
-                    if (err != err || (extra & 0x100)) st = HPF_ST_NONFINITE;
-                    a.n_iter_h[sc] = itc[lane];
+                    if ((stat[lane] & 0x200) && st == HPF_ST_CONVERGED) st = HPF_ST_SINGULAR;
+                    if (itv >= a.max_h && st == HPF_ST_CONVERGED) st = HPF_ST_MAXITER;
+                    if (!(err < CUDART_INF)) st = HPF_ST_NONFINITE;     // NaN or Inf mismatch
+                    a.n_iter_h[sc] = itv;
                     a.err_h[sc] = err;
                     a.status[sc] = st;
                 }
-                if (step) itc[lane] += 1;
+                if (step) itc[lane] = itv + 1;
                 fnew[lane] = 0;
+                pendF = step;
                 if (donemask) {
                     int base = 0;
                     if (lane == 0) base = atomicAdd(a.work_counter, __popc(donemask));
                     base = __shfl_sync(0xffffffffu, base, 0);
                     if (done) {
                         const int idx = base + __popc(donemask & ((1u << lane) - 1u));
-                        scen[lane] = ((size_t)idx < B) ? idx : -1;
+                        nsc = ((size_t)idx < B) ? idx : -1;
                         itc[lane] = 0;
                         fnew[lane] = 1;
                         stat[lane] = 0;
                     }
                 }
+                scen_next[lane] = nsc;
             }
         }
+        if (a.step_only) break;
         __syncthreads();
+        cur ^= 1;
     }
 #undef AT
 }
