@@ -383,6 +383,21 @@ wn_tile_kernel(const DevNet net, const StructNet sn, const double2* __restrict__
     }
 }
 
+// Out-of-line transcendental helpers: one copy each keeps the Newton loop inside the
+// instruction cache (the inlined versions made the kernel 150 KB of SASS).
+__device__ __noinline__ double2 sincos_ol(double x) {
+    double sn_, cs_;
+    sincos(x, &sn_, &cs_);
+    return make_double2(cs_, sn_);
+}
+// numpy's float remainder a % (2 pi): fmod, then the divisor's sign (HG:548)
+__device__ __noinline__ double mod_twopi(double va) {
+    const double twopi = 2.0 * CUDART_PI;
+    double r = fmod(va, twopi);
+    if (r != 0.0) { if (r < 0.0) r += twopi; } else r = 0.0;
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------
 // Small per-lane dense solve in REGISTERS (NX known at compile time): loads the augmented
 // system from the strided smem array, Gaussian elimination with partial pivoting (per lane),
@@ -494,8 +509,8 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     double* p = reinterpret_cast<double*>(sG + (size_t)nZ * m);
     double* Vm = p;  p += nH * HPF_T;
     double* Va = p;  p += nH * HPF_T;
-    double* Ere = p; p += nH * HPF_T;
-    double* Eim = p; p += nH * HPF_T;
+    double* Vre = p; p += nH * HPF_T;
+    double* Vim = p; p += nH * HPF_T;
     double* Wre = p; p += nZ * HPF_T;      // w_N (index z = s - m), constant per scenario
     double* Wim = p; p += nZ * HPF_T;
     double* INre = p; p += q * H * HPF_T;  // I_N of the lane's scenario
@@ -566,10 +581,10 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     }
                 }
                 for (int s = 0; s < m; ++s) {
-                    double sn_, cs_;
-                    sincos(AT(Va, s), &sn_, &cs_);
-                    AT(Ere, s) = cs_;
-                    AT(Eim, s) = sn_;
+                    const double2 e = sincos_ol(AT(Va, s));
+                    const double vm = AT(Vm, s);
+                    AT(Vre, s) = vm * e.x;                        // V = V_m e^{j theta} (HG:403)
+                    AT(Vim, s) = vm * e.y;
                 }
             } else {
                 if (isnew) {
@@ -594,10 +609,10 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     }
                 }
                 for (int s = m + warp; s < nH; s += CW) {
-                    double sn_, cs_;
-                    sincos(AT(Va, s), &sn_, &cs_);
-                    AT(Ere, s) = cs_;
-                    AT(Eim, s) = sn_;
+                    const double2 e = sincos_ol(AT(Va, s));
+                    const double vm = AT(Vm, s);
+                    AT(Vre, s) = vm * e.x;
+                    AT(Vim, s) = vm * e.y;
                 }
             }
         }
@@ -616,12 +631,10 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                         acc = make_double2(0.0, 0.0);
                         for (int pp = 0; pp < H; ++pp) {
                             const int t2 = pp * n + i;
-                            const double vm = AT(Vm, t2);
-                            acc = cadd(acc, cmul(row[pp], make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                            acc = cadd(acc, cmul(row[pp], make_double2(AT(Vre, t2), AT(Vim, t2))));
                         }
                     } else {
-                        const double vm = AT(Vm, s);
-                        acc = cmul(sYN[(size_t)dev * H + h], make_double2(vm * AT(Ere, s), vm * AT(Eim, s)));
+                        acc = cmul(sYN[(size_t)dev * H + h], make_double2(AT(Vre, s), AT(Vim, s)));
                     }
                     const double2 inj = make_double2(AT(INre, u) - acc.x, AT(INim, u) - acc.y);
                     AT(IJre, u) = inj.x; AT(IJim, u) = inj.y;
@@ -629,8 +642,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     double2 f = make_double2(0.0, 0.0);
                     for (int j = 0; j < n; ++j) {
                         const int t2 = h * n + j;
-                        const double vm = AT(Vm, t2);
-                        f = cadd(f, cmul(Yrow[j], make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                        f = cadd(f, cmul(Yrow[j], make_double2(AT(Vre, t2), AT(Vim, t2))));
                     }
                     f = cadd(f, inj);
                     const double v1 = fabs(f.x), v2 = fabs(f.y);      // s >= m >= c: both parts are rows
@@ -645,8 +657,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     double2 f = make_double2(0.0, 0.0);
                     for (int j = 0; j < n; ++j) {
                         const int t2 = h * n + j;
-                        const double vm = AT(Vm, t2);
-                        f = cadd(f, cmul(Yrow[j], make_double2(vm * AT(Ere, t2), vm * AT(Eim, t2))));
+                        f = cadd(f, cmul(Yrow[j], make_double2(AT(Vre, t2), AT(Vim, t2))));
                     }
                     const double v1 = fabs(f.x), v2 = fabs(f.y);
                     const double v = (v2 != v2 || v2 > v1) ? v2 : v1;
@@ -657,14 +668,10 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 for (int i = 0; i < m; ++i) {
                     const double2* Yrow = sY + (size_t)i * n;
                     double2 f = make_double2(0.0, 0.0);
-                    for (int j = 0; j < n; ++j) {
-                        const double vm = AT(Vm, j);
-                        f = cadd(f, cmul(Yrow[j], make_double2(vm * AT(Ere, j), vm * AT(Eim, j))));
-                    }
+                    for (int j = 0; j < n; ++j) f = cadd(f, cmul(Yrow[j], make_double2(AT(Vre, j), AT(Vim, j))));
                     AT(I1re, i) = f.x; AT(I1im, i) = f.y;
                     if (i == 0) continue;                            // slack: no row
-                    const double vm = AT(Vm, i);
-                    const double2 v = make_double2(vm * AT(Ere, i), vm * AT(Eim, i));
+                    const double2 v = make_double2(AT(Vre, i), AT(Vim, i));
                     const double2 sl = cmul(v, make_double2(f.x, -f.y));
                     const double2 fs = make_double2(AT(Pl, i) + sl.x, AT(Ql, i) + sl.y);
                     AT(FSre, i) = fs.x; AT(FSim, i) = fs.y;
@@ -678,9 +685,9 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 // ---- border system for x_F: every entry is accumulated in registers ----
                 const int w = nx + 1;
                 for (int i = 1; i < m; ++i) {
-                    const double vmi = AT(Vm, i);
-                    const double2 ei = make_double2(AT(Ere, i), AT(Eim, i));
-                    const double2 vi = make_double2(vmi * ei.x, vmi * ei.y);
+                    const double rvi = 1.0 / AT(Vm, i);
+                    const double2 vi = make_double2(AT(Vre, i), AT(Vim, i));
+                    const double2 ei = make_double2(vi.x * rvi, vi.y * rvi);         // V / V_m (HG:455)
                     const double2 i1 = make_double2(AT(I1re, i), AT(I1im, i));
                     const double2 jvi = cmulj(vi);
                     const int rr = i - 1, ri = nth + (i - c);
@@ -695,9 +702,9 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                             e = make_double2(-AT(FSre, i), -AT(FSim, i));
                         } else {
                             const double2 y = sY[(size_t)i * n + j];
-                            const double vmj = AT(Vm, j);
-                            ej = make_double2(AT(Ere, j), AT(Eim, j));
-                            vj = make_double2(vmj * ej.x, vmj * ej.y);
+                            const double rvj = 1.0 / AT(Vm, j);
+                            vj = make_double2(AT(Vre, j), AT(Vim, j));
+                            ej = make_double2(vj.x * rvj, vj.y * rvj);
                             if (is_v) {                               // dS_i/dV_m,j  (HG:458-459)
                                 e = cmul(vi, cconj(cmul(y, ej)));
                                 if (i == j) e = cadd(cmul(ei, cconj(i1)), e);
@@ -711,24 +718,22 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                             const int bk = m + k;
                             const double2 y = sY[(size_t)i * n + bk];
                             if (y.x == 0.0 && y.y == 0.0) continue;
-                            const double vmb = AT(Vm, bk);
-                            const double2 eb = make_double2(AT(Ere, bk), AT(Eim, bk));
-                            const double2 vb = make_double2(vmb * eb.x, vmb * eb.y);
+                            const double vmb = AT(Vm, bk), rvb = 1.0 / vmb;
+                            const double2 vb = make_double2(AT(Vre, bk), AT(Vim, bk));
+                            const double2 eb = make_double2(vb.x * rvb, vb.y * rvb);
                             const double2 ak = cmul(jvi, cconj(cneg(cmul(y, vb))));    // dS_i/dtheta_b
                             const double2 vk = cmul(vi, cconj(cmul(y, eb)));           // dS_i/dV_m,b
                             double2 uu;
                             if (is_rhs) {            // u0 of row z = k (closed form)
                                 uu = make_double2(vb.x + AT(Wre, k), vb.y + AT(Wim, k));
-                                for (int i2 = 0; i2 < m; ++i2) {
-                                    const double v2 = AT(Vm, i2);
-                                    uu = cadd(uu, cmul(sG[(size_t)k * m + i2], make_double2(v2 * AT(Ere, i2), v2 * AT(Eim, i2))));
-                                }
+                                for (int i2 = 0; i2 < m; ++i2)
+                                    uu = cadd(uu, cmul(sG[(size_t)k * m + i2], make_double2(AT(Vre, i2), AT(Vim, i2))));
                                 uu = cneg(uu);
                             } else {                 // column of G T_F: G (j V_j) or G E_j
                                 uu = cmul(sG[(size_t)k * m + j], is_v ? ej : cmulj(vj));
                             }
                             const double2 ce = cmul(cconj(eb), uu);
-                            const double dth = ce.y / vmb, dvm = ce.x;
+                            const double dth = ce.y * rvb, dvm = ce.x;
                             e.x -= ak.x * dth + vk.x * dvm;
                             e.y -= ak.y * dth + vk.y * dvm;
                         }
@@ -753,10 +758,10 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 for (int i = 1; i < m; ++i) {
                     const double dth = AT(DXF, i - 1);
                     const double dvm = (i >= c) ? AT(DXF, nth + i - c) : 0.0;
-                    const double vmi = AT(Vm, i);
-                    const double2 ei = make_double2(AT(Ere, i), AT(Eim, i));
-                    AT(UFre, i) = -(vmi * ei.y) * dth + ei.x * dvm;      // u_F = (j V_i) dtheta + E_i dV_m
-                    AT(UFim, i) = (vmi * ei.x) * dth + ei.y * dvm;
+                    const double rvi = 1.0 / AT(Vm, i);
+                    const double2 vi = make_double2(AT(Vre, i), AT(Vim, i));
+                    AT(UFre, i) = -vi.y * dth + (vi.x * rvi) * dvm;      // u_F = (j V_i) dtheta + E_i dV_m
+                    AT(UFim, i) = vi.x * dth + (vi.y * rvi) * dvm;
                 }
             }
             AT(red, warp) = mx;
@@ -780,51 +785,53 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
         const bool done = active && !cont && !a.step_only;
         if (__ballot_sync(0xffffffffu, active) == 0u) break;          // uniform over the CTA
         const unsigned donemask = __ballot_sync(0xffffffffu, done);
-        if (donemask && done) {
-            // post-processing (HG:547-549) + write-out of the finished lanes (rows over all warps)
-            for (int s = warp; s < nH; s += NW) {
-                double vm = AT(Vm, s), va = AT(Va, s), r = va;
-                if (!(a.flags & HPF_SOLVE_RAW)) {
-                    if (vm < 0.0) va += CUDART_PI;
-                    const double twopi = 2.0 * CUDART_PI;
-                    r = fmod(va, twopi);
-                    if (r != 0.0) { if (r < 0.0) r += twopi; } else r = 0.0;
-                    if (vm < 0.0) vm = -vm;
+        if (donemask) {
+            // post-processing (HG:547-549) + write-out: finished lanes are few (about 2 of 32
+            // per round), so each one is written by ONE warp with its 32 lanes over the rows
+            unsigned dm = donemask;
+            int jd = 0;
+            while (dm) {
+                const int l = __ffs(dm) - 1;
+                dm &= dm - 1;
+                if ((jd++ % NW) != warp) continue;
+                const int scl = scen[l];
+                for (int s = lane; s < nH; s += 32) {
+                    double vm = Vm[s * HPF_T + l], va = Va[s * HPF_T + l];
+                    if (!(a.flags & HPF_SOLVE_RAW)) {
+                        if (vm < 0.0) va += CUDART_PI;
+                        va = mod_twopi(va);
+                        if (vm < 0.0) vm = -vm;
+                    }
+                    a.V_m[(size_t)s * B + scl] = vm;
+                    a.V_a[(size_t)s * B + scl] = va;
                 }
-                a.V_m[(size_t)s * B + sc] = vm;
-                a.V_a[(size_t)s * B + sc] = r;
+                if (a.I_inj)
+                    for (int u = lane; u < q * H; u += 32)
+                        a.I_inj[(size_t)u * B + scl] = make_double2(IJre[u * HPF_T + l], IJim[u * HPF_T + l]);
             }
-            if (a.I_inj)
-                for (int u = warp; u < q * H; u += NW)
-                    a.I_inj[(size_t)u * B + sc] = make_double2(AT(IJre, u), AT(IJim, u));
         }
         if (!border) {
             // u_z = -V_z - sum_i G[z][i] (V_i + u_F,i) - w_N,z ; polar conversion; update
-#pragma unroll
-            for (int r = 0; r < MAXROWS; ++r) {
-                const int z = warp + r * CW;
-                if (z < nZ) {
-                    const int s = z + m;
-                    const double vm = AT(Vm, s);
-                    const double2 es = make_double2(AT(Ere, s), AT(Eim, s));
-                    double2 acc = make_double2(vm * es.x + AT(Wre, z), vm * es.y + AT(Wim, z));
-                    for (int i = 0; i < m; ++i) {
-                        const double vi = AT(Vm, i);
-                        const double2 tot = make_double2(vi * AT(Ere, i) + AT(UFre, i), vi * AT(Eim, i) + AT(UFim, i));
-                        acc = cadd(acc, cmul(sG[(size_t)z * m + i], tot));
+            for (int z = warp; z < nZ; z += CW) {
+                const int s = z + m;
+                const double2 vs = make_double2(AT(Vre, s), AT(Vim, s));
+                double2 acc = make_double2(vs.x + AT(Wre, z), vs.y + AT(Wim, z));
+                for (int i = 0; i < m; ++i) {
+                    const double2 tot = make_double2(AT(Vre, i) + AT(UFre, i), AT(Vim, i) + AT(UFim, i));
+                    acc = cadd(acc, cmul(sG[(size_t)z * m + i], tot));
+                }
+                // conj(E) u with E = V / V_m:  dV_m = Re(conj(V) u) / V_m,  dtheta = Im(conj(V) u) / V_m^2
+                const double2 cv = cmul(make_double2(vs.x, -vs.y), cneg(acc));
+                const double vm = AT(Vm, s), rv = 1.0 / vm;
+                const double dvm = cv.x * rv, dth = (cv.y * rv) * rv;
+                if (a.step_only) {
+                    if (sc >= 0) {
+                        a.dx_out[(size_t)(s - 1) * B + sc] = -dth;
+                        a.dx_out[(size_t)((nH - 1) + s - c) * B + sc] = -dvm;
                     }
-                    const double2 u = cneg(acc);
-                    const double2 wv = cmul(make_double2(es.x, -es.y), u);
-                    const double dth = wv.y / vm, dvm = wv.x;
-                    if (a.step_only) {
-                        if (sc >= 0) {
-                            a.dx_out[(size_t)(s - 1) * B + sc] = -dth;
-                            a.dx_out[(size_t)((nH - 1) + s - c) * B + sc] = -dvm;
-                        }
-                    } else if (step) {
-                        AT(Va, s) += dth;
-                        AT(Vm, s) = vm + dvm;
-                    }
+                } else if (step) {
+                    AT(Va, s) += dth;
+                    AT(Vm, s) = vm + dvm;
                 }
             }
         } else {
