@@ -22,6 +22,14 @@ struct DevNet {
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+// acc + a*b with fused multiply-adds (4 FP64 instructions per complex MAC)
+__device__ __forceinline__ double2 cfma(double2 acc, double2 a, double2 b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+    return acc;
+}
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
@@ -60,7 +68,7 @@ __device__ __forceinline__ double2 ydotv(const DevNet& net, int h, int i, int of
     for (int j = 0; j < n; ++j) {
         const double2 y = ldg2(Yrow + j);
         const double2 v = make_double2(Vre[(h * n + j) * VS + off], Vim[(h * n + j) * VS + off]);
-        acc = cadd(acc, cmul(y, v));
+        acc = cfma(acc, y, v);
     }
     return acc;
 }
@@ -78,7 +86,7 @@ __device__ __forceinline__ double2 norton_injection(const DevNet& net, int k, in
         acc = make_double2(0.0, 0.0);
         for (int p = 0; p < H; ++p) {
             const double2 v = make_double2(Vre[(p * n + bus) * VS + off], Vim[(p * n + bus) * VS + off]);
-            acc = cadd(acc, cmul(ldg2(row + p), v));
+            acc = cfma(acc, ldg2(row + p), v);
         }
     } else {
         const double2 v = make_double2(Vre[(h * n + bus) * VS + off], Vim[(h * n + bus) * VS + off]);

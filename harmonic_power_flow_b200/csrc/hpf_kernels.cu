@@ -369,10 +369,26 @@ struct MismatchArgs {
 
 __host__ __device__ inline size_t tile_smem_bytes(int n, int H, int q) {
     const size_t nH = (size_t)n * H;
-    // Vre, Vim [nH][32]; I1 [n][32] c128; Iinj [qH][32] c128; red [8][32]
-    return (2 * nH + 2 * n + 2 * (size_t)q * H + 8) * HPF_TILE * sizeof(double) + 16;
+    // V (re, im) [nH][32]; I_N, I_inj [qH][32] c128; I1 [n][32] c128; P, Q [n][32]; red [8][32]
+    return (2 * nH + 4 * (size_t)q * H + 2 * n + 2 * n + 8) * HPF_TILE * sizeof(double) + 16;
 }
 
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// The whole input tile (V_m, V_a, P, Q, I_N of 32 scenarios) is requested with asynchronous
+// copies (LDGSTS) before anything is computed, so every byte of the tile is in flight at once
+// (the first version loaded row by row between sincos calls and was latency-bound at 25 % of
+// HBM bandwidth).
 __global__ void __launch_bounds__(HPF_THREADS)
 mismatch_tile_kernel(const DevNet net, const MismatchArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -380,21 +396,36 @@ mismatch_tile_kernel(const DevNet net, const MismatchArgs a) {
     const int n = net.n, H = net.H, nH = net.nH, q = net.q, c = net.c, m = net.m;
     const size_t B = (size_t)a.B;
     double2* I1 = reinterpret_cast<double2*>(smem);
-    double2* Iinj = I1 + (size_t)n * HPF_TILE;
-    double* Vre = reinterpret_cast<double*>(Iinj + (size_t)q * H * HPF_TILE);
-    double* Vim = Vre + (size_t)nH * HPF_TILE;
-    double* red = Vim + (size_t)nH * HPF_TILE;
+    double2* IN = I1 + (size_t)n * HPF_TILE;
+    double2* Iinj = IN + (size_t)q * H * HPF_TILE;
+    double* Vre = reinterpret_cast<double*>(Iinj + (size_t)q * H * HPF_TILE);   // raw V_m, then Re V
+    double* Vim = Vre + (size_t)nH * HPF_TILE;                                   // raw V_a, then Im V
+    double* Pl = Vim + (size_t)nH * HPF_TILE;
+    double* Ql = Pl + (size_t)n * HPF_TILE;
+    double* red = Ql + (size_t)n * HPF_TILE;
 
     for (size_t tile = blockIdx.x; tile * HPF_TILE < B; tile += gridDim.x) {
         const size_t b = tile * HPF_TILE + lane;
         const bool ok = b < B;
         const size_t bb = ok ? b : B - 1;            // clamp: compute, do not store
         __syncthreads();
-        // phase A: phasors
+        // phase L: request the tile
         for (int t = warp; t < nH; t += nw) {
-            const double vm = a.V_m[t * B + bb];
+            cp_async8(Vre + t * HPF_TILE + lane, a.V_m + t * B + bb);
+            cp_async8(Vim + t * HPF_TILE + lane, a.V_a + t * B + bb);
+        }
+        for (int t = 1 + warp; t < m; t += nw) {
+            cp_async8(Pl + t * HPF_TILE + lane, a.P + t * B + bb);
+            cp_async8(Ql + t * HPF_TILE + lane, a.Q + t * B + bb);
+        }
+        for (int u = warp; u < q * H; u += nw) cp_async16(IN + u * HPF_TILE + lane, a.I_N + u * B + bb);
+        cp_async_wait_all();
+        __syncthreads();
+        // phase A: phasors in place
+        for (int t = warp; t < nH; t += nw) {
+            const double vm = Vre[t * HPF_TILE + lane];
             double sn, cs;
-            sincos(a.V_a[t * B + bb], &sn, &cs);
+            sincos(Vim[t * HPF_TILE + lane], &sn, &cs);
             Vre[t * HPF_TILE + lane] = vm * cs;
             Vim[t * HPF_TILE + lane] = vm * sn;
         }
@@ -405,8 +436,7 @@ mismatch_tile_kernel(const DevNet net, const MismatchArgs a) {
                 I1[t * HPF_TILE + lane] = ydotv<HPF_TILE>(net, 0, t, lane, Vre, Vim);
             } else {
                 const int u = t - n, k = u / H, h = u - k * H;
-                const double2 in = a.I_N[u * B + bb];
-                const double2 inj = norton_injection<HPF_TILE>(net, k, h, lane, Vre, Vim, in);
+                const double2 inj = norton_injection<HPF_TILE>(net, k, h, lane, Vre, Vim, IN[u * HPF_TILE + lane]);
                 Iinj[u * HPF_TILE + lane] = inj;
                 if (a.I_inj && ok) a.I_inj[u * B + b] = inj;
             }
@@ -415,19 +445,11 @@ mismatch_tile_kernel(const DevNet net, const MismatchArgs a) {
         // phase C: mismatch rows
         double mx = 0.0;
         for (int e = warp; e < nH - 1; e += nw) {
-            double2 f;
-            const int s = e + 1;
-            if (s < m) {
-                const double2 v = make_double2(Vre[s * HPF_TILE + lane], Vim[s * HPF_TILE + lane]);
-                const double2 sl = cmul(v, cconj(I1[s * HPF_TILE + lane]));
-                f = make_double2(a.P[s * B + bb] + sl.x, a.Q[s * B + bb] + sl.y);
-            } else {
-                f = harmonic_mismatch_entry<HPF_TILE>(net, e, lane, Vre, Vim, I1, Iinj, nullptr, nullptr);
-            }
+            const double2 f = harmonic_mismatch_entry<HPF_TILE>(net, e, lane, Vre, Vim, I1, Iinj, Pl, Ql);
             double v1 = fabs(f.x);
-            if (ok) a.f[(size_t)h_row_re(net, e) * B + b] = f.x;
+            if (ok) __stcs(a.f + (size_t)h_row_re(net, e) * B + b, f.x);
             if (e >= c - 1) {
-                if (ok) a.f[(size_t)h_row_im(net, e) * B + b] = f.y;
+                if (ok) __stcs(a.f + (size_t)h_row_im(net, e) * B + b, f.y);
                 const double v2 = fabs(f.y);
                 v1 = (v2 != v2 || v2 > v1) ? v2 : v1;
             }
@@ -506,23 +528,42 @@ __host__ __device__ inline size_t jac_smem_bytes(int n, int H, int q, int N, lon
     return (size_t)stride * sizeof(double) + scn_smem_bytes(n, H, q, N, false) + 16;
 }
 
-__global__ void __launch_bounds__(HPF_THREADS)
+#define HPF_JAC_THREADS 512
+__global__ void __launch_bounds__(HPF_JAC_THREADS)
 jacobian_kernel(const DevNet net, const JacobianArgs a) {
     extern __shared__ __align__(16) double smem[];
     double* Jt = smem;                                   // stride doubles, 16-byte aligned
     const ScnSmem s = carve(smem + a.stride, net, false);
     const int nH = net.nH, N = net.N;
     const size_t B = (size_t)a.B;
+    // The sparsity pattern of J is fixed by the network (positions where Y(h) or Y_N are
+    // zero never change), so the tile is zero-filled ONCE; every scenario overwrites the
+    // same non-zero positions.
+    cta_zero(Jt, (size_t)a.stride);
+    // software pipeline: the state of the NEXT scenario is fetched into registers while the
+    // current matrix is assembled (nH <= 2 * blockDim.x entries per thread pair)
+    double pvm = 0.0, pva = 0.0;
+    const bool own = (int)threadIdx.x < nH;
+    if (own && (int)blockIdx.x < a.B) {
+        pvm = __ldcs(a.V_m + threadIdx.x * B + blockIdx.x);
+        pva = __ldcs(a.V_a + threadIdx.x * B + blockIdx.x);
+    }
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-        for (int t = threadIdx.x; t < nH; t += blockDim.x) {
-            s.Vm[t] = a.V_m[t * B + b];
-            s.Va[t] = a.V_a[t * B + b];
+        if (own) { s.Vm[threadIdx.x] = pvm; s.Va[threadIdx.x] = pva; }
+        for (int t = threadIdx.x + blockDim.x; t < nH; t += blockDim.x) {   // (large networks)
+            s.Vm[t] = __ldcs(a.V_m + t * B + b);
+            s.Va[t] = __ldcs(a.V_a + t * B + b);
         }
+        const int bn = b + gridDim.x;
+        if (own && bn < a.B) {
+            pvm = __ldcs(a.V_m + threadIdx.x * B + bn);
+            pva = __ldcs(a.V_a + threadIdx.x * B + bn);
+        }
+        __syncthreads();
+        cta_phasors(s, 0, nH, false);                    // (contains a barrier)
+        cta_currents(net, s, false);                     // overlaps the previous bulk store
         if (threadIdx.x == 0) bulk_store_wait_read();   // previous matrix has left smem
         __syncthreads();
-        cta_zero(Jt, (size_t)a.stride);
-        cta_phasors(s, 0, nH, false);                    // (contains a barrier)
-        cta_currents(net, s, false);
         cta_harmonic_jacobian(net, s, Jt, (size_t)N, 1);
         fence_proxy_async_smem();                        // generic-proxy writes -> async proxy
         __syncthreads();
@@ -1248,11 +1289,11 @@ int hpf_jacobian(hpf_t* h, int B, const double* V_m, const double* V_a, double* 
     size_t smem = jac_smem_bytes(net.n, net.H, net.q, net.N, a.stride);
     int occ = 0;
     if (smem <= (size_t)h->smem_optin) {
-        rc = prep_kernel(h, jacobian_kernel, smem, "hpf_jacobian", &occ);
+        rc = prep_kernel(h, jacobian_kernel, smem, "hpf_jacobian", &occ, HPF_JAC_THREADS);
         if (rc) return rc;
         long long grid = (long long)occ * h->sm_count;
         if (grid > B) grid = B;
-        jacobian_kernel<<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a);
+        jacobian_kernel<<<(unsigned)grid, HPF_JAC_THREADS, smem, (cudaStream_t)stream>>>(net, a);
     } else {
         smem = scn_smem_bytes(net.n, net.H, net.q, net.N, false);
         rc = prep_kernel(h, jacobian_gmem_kernel, smem, "hpf_jacobian", &occ);

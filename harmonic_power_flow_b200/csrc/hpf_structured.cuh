@@ -631,7 +631,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                         acc = make_double2(0.0, 0.0);
                         for (int pp = 0; pp < H; ++pp) {
                             const int t2 = pp * n + i;
-                            acc = cadd(acc, cmul(row[pp], make_double2(AT(Vre, t2), AT(Vim, t2))));
+                            acc = cfma(acc, row[pp], make_double2(AT(Vre, t2), AT(Vim, t2)));
                         }
                     } else {
                         acc = cmul(sYN[(size_t)dev * H + h], make_double2(AT(Vre, s), AT(Vim, s)));
@@ -642,7 +642,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     double2 f = make_double2(0.0, 0.0);
                     for (int j = 0; j < n; ++j) {
                         const int t2 = h * n + j;
-                        f = cadd(f, cmul(Yrow[j], make_double2(AT(Vre, t2), AT(Vim, t2))));
+                        f = cfma(f, Yrow[j], make_double2(AT(Vre, t2), AT(Vim, t2)));
                     }
                     f = cadd(f, inj);
                     const double v1 = fabs(f.x), v2 = fabs(f.y);      // s >= m >= c: both parts are rows
@@ -657,7 +657,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     double2 f = make_double2(0.0, 0.0);
                     for (int j = 0; j < n; ++j) {
                         const int t2 = h * n + j;
-                        f = cadd(f, cmul(Yrow[j], make_double2(AT(Vre, t2), AT(Vim, t2))));
+                        f = cfma(f, Yrow[j], make_double2(AT(Vre, t2), AT(Vim, t2)));
                     }
                     const double v1 = fabs(f.x), v2 = fabs(f.y);
                     const double v = (v2 != v2 || v2 > v1) ? v2 : v1;
@@ -668,7 +668,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 for (int i = 0; i < m; ++i) {
                     const double2* Yrow = sY + (size_t)i * n;
                     double2 f = make_double2(0.0, 0.0);
-                    for (int j = 0; j < n; ++j) f = cadd(f, cmul(Yrow[j], make_double2(AT(Vre, j), AT(Vim, j))));
+                    for (int j = 0; j < n; ++j) f = cfma(f, Yrow[j], make_double2(AT(Vre, j), AT(Vim, j)));
                     AT(I1re, i) = f.x; AT(I1im, i) = f.y;
                     if (i == 0) continue;                            // slack: no row
                     const double2 v = make_double2(AT(Vre, i), AT(Vim, i));
@@ -727,7 +727,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                             if (is_rhs) {            // u0 of row z = k (closed form)
                                 uu = make_double2(vb.x + AT(Wre, k), vb.y + AT(Wim, k));
                                 for (int i2 = 0; i2 < m; ++i2)
-                                    uu = cadd(uu, cmul(sG[(size_t)k * m + i2], make_double2(AT(Vre, i2), AT(Vim, i2))));
+                                    uu = cfma(uu, sG[(size_t)k * m + i2], make_double2(AT(Vre, i2), AT(Vim, i2)));
                                 uu = cneg(uu);
                             } else {                 // column of G T_F: G (j V_j) or G E_j
                                 uu = cmul(sG[(size_t)k * m + j], is_v ? ej : cmulj(vj));
@@ -818,7 +818,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 double2 acc = make_double2(vs.x + AT(Wre, z), vs.y + AT(Wim, z));
                 for (int i = 0; i < m; ++i) {
                     const double2 tot = make_double2(AT(Vre, i) + AT(UFre, i), AT(Vim, i) + AT(UFim, i));
-                    acc = cadd(acc, cmul(sG[(size_t)z * m + i], tot));
+                    acc = cfma(acc, sG[(size_t)z * m + i], tot);
                 }
                 // conj(E) u with E = V / V_m:  dV_m = Re(conj(V) u) / V_m,  dtheta = Im(conj(V) u) / V_m^2
                 const double2 cv = cmul(make_double2(vs.x, -vs.y), cneg(acc));
