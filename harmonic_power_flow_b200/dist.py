@@ -26,30 +26,45 @@ def shard_inputs(rank, world, *arrays):
     return [None if a is None else a[..., lo:hi] for a in arrays]
 
 
-def gather_last_axis(t: torch.Tensor, B: int, group=None) -> torch.Tensor:
-    """All-gather a batch-innermost tensor [..., B_local] into [..., B] on every rank.
-    Shards are padded to ceil(B/world) so one fixed-size collective serves ragged tails."""
+def gather_rank_major(t: torch.Tensor, B: int, group=None) -> torch.Tensor:
+    """All-gather a batch-innermost tensor [..., B_local] into a RANK-MAJOR stack
+    [world, ..., ceil(B/world)] with one collective and no re-layout copy (the tail of the
+    last shard is padding when world does not divide B).  Scenario s is element
+    [s // per, ..., s % per]; ``unshard`` gives the [..., B] view-copy when it is wanted."""
     world = dist.get_world_size(group)
     per = shard_size(B, world)
-    lead = t.shape[:-1]
     is_c = t.is_complex()
     x = torch.view_as_real(t) if is_c else t            # NCCL has no complex dtypes
-    x = x.movedim(len(lead), 0).contiguous()            # [B_local, ...]
-    pad = per - x.shape[0]
-    if pad:
-        x = torch.cat([x, x.new_zeros((pad,) + tuple(x.shape[1:]))], 0)
-    out = x.new_empty((world * per,) + tuple(x.shape[1:]))
-    dist.all_gather_into_tensor(out, x, group=group)
-    out = out[:B].movedim(0, len(lead))
     if is_c:
-        out = torch.view_as_complex(out.contiguous())
-    return out.contiguous()
+        x = x.movedim(-1, 0)                            # keep the batch axis innermost: [2, ..., B_local]
+    x = x.contiguous()
+    if x.shape[-1] != per:
+        x = torch.cat([x, x.new_zeros(tuple(x.shape[:-1]) + (per - x.shape[-1],))], -1)
+    flat = x.new_empty((world * x.shape[0],) + tuple(x.shape[1:]))     # concatenation along dim 0
+    dist.all_gather_into_tensor(flat, x, group=group)
+    out = flat.view((world,) + tuple(x.shape))
+    if is_c:
+        out = torch.view_as_complex(out.movedim(1, -1).contiguous())
+    return out
 
 
-def gather_result(res, B: int, group=None) -> dict:
-    """Gather every field of a BatchResult (flags first, then results) -> dict of [.., B] tensors."""
+def unshard(stacked: torch.Tensor, B: int) -> torch.Tensor:
+    """[world, ..., per] rank-major stack -> [..., B] (copies)."""
+    world, per = stacked.shape[0], stacked.shape[-1]
+    return stacked.movedim(0, -2).reshape(tuple(stacked.shape[1:-1]) + (world * per,))[..., :B].contiguous()
+
+
+def gather_last_axis(t: torch.Tensor, B: int, group=None) -> torch.Tensor:
+    """All-gather a batch-innermost tensor [..., B_local] into [..., B] on every rank."""
+    return unshard(gather_rank_major(t, B, group), B)
+
+
+def gather_result(res, B: int, group=None, rank_major: bool = False) -> dict:
+    """The single collective step of the path: gather every field of a BatchResult (flags
+    first, then results).  rank_major=True keeps the [world, ..., per] stacks (no copies)."""
     out = {}
+    f = gather_rank_major if rank_major else gather_last_axis
     for k in ("status", "n_iter_f", "n_iter_h", "err_h", "V_m", "V_a", "I_inj"):
         v = getattr(res, k)
-        out[k] = None if v is None else gather_last_axis(v, B, group)
+        out[k] = None if v is None else f(v, B, group)
     return out

@@ -45,6 +45,22 @@ class BatchResult:
     def converged(self):
         return self.status == _lib.ST_CONVERGED
 
+    def to_pinned(self, cache: dict):
+        """Device -> pinned host buffers (kept in ``cache``), one synchronisation."""
+        out = {}
+        for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status"):
+            v = getattr(self, k)
+            if v is None:
+                out[k] = None
+                continue
+            buf = cache.get(k)
+            if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                buf = cache[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+            buf.copy_(v, non_blocking=True)
+            out[k] = buf
+        torch.cuda.current_stream(self.status.device).synchronize()
+        return {k: (None if b is None else b.numpy()) for k, b in out.items()}
+
     def to_host(self):
         out = {}
         for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status",
