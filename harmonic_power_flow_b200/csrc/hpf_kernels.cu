@@ -674,6 +674,7 @@ struct hpf_handle {
     size_t wN_elems = 0;
     int harm_warps = 8;           // warps per 32-scenario tile of the harmonic kernel (8 or 16)
     int harm_minb = 1;
+    int no_specialise = 0;        // $HPF_NO_SPECIALISE=1: always use the runtime-dimension kernels
     double pivot_min = 0.0, pivot_max = 0.0;
     int profiling = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -818,7 +819,7 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     h->struct_state = -1;
     const DevNet net = devnet(h);
     const int nZ = net.nH - net.m;
-    if (nZ < 1 || nZ > HPF_ST_MAXNZ) return HPF_OK;
+    if (nZ < 1) return HPF_OK;
     if (harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, h->harm_warps,
                              h->n_dev * (h->coupled ? h->H * h->H : h->H)) > (size_t)h->smem_optin)
         return HPF_OK;
@@ -878,33 +879,37 @@ static int launch_wn(hpf_t* h, const DevNet& net, const StructNet& sn, int B, co
     return HPF_OK;
 }
 
-template <int NW, int MAXROWS, int MINB>
+template <int NW, int MINB, class D>
 static int launch_harm_t(hpf_t* h, const DevNet& net, const StructNet& sn, const HarmTileArgs& ha,
                          bool persistent, cudaStream_t st) {
     const size_t smem = harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, NW, sn.yn_elems);
     int occ = 0;
-    int rc = prep_kernel(h, harm_tile_kernel<NW, MAXROWS, MINB>, smem, "hpf_solve", &occ, NW * 32);
+    int rc = prep_kernel(h, harm_tile_kernel<NW, MINB, D>, smem, "hpf_solve", &occ, NW * 32);
     if (rc) return rc;
     const long long tiles = ((long long)ha.B + HPF_T - 1) / HPF_T;
     long long grid = tiles;
     if (persistent && grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
-    harm_tile_kernel<NW, MAXROWS, MINB><<<(unsigned)grid, NW * 32, smem, st>>>(net, sn, ha);
+    harm_tile_kernel<NW, MINB, D><<<(unsigned)grid, NW * 32, smem, st>>>(net, sn, ha);
     h->launches++;
     CK(cudaGetLastError());
     return HPF_OK;
 }
 
-// Variants: (warps per tile, Z rows per Z warp in registers, min CTAs per SM).
+// Shape-specialised instances exist for the BASELINE configurations' 4-bus networks
+// (config 3: net3, 13 harmonics; config 2: net2 with two nonlinear buses, 10 harmonics);
+// every other network runs the runtime-dimension instance.
 static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const HarmTileArgs& ha,
                        bool persistent, cudaStream_t st) {
-    const int nw = h->harm_warps, nZ = sn.nZ;
-    if (nw == 16) {
-        if (nZ <= 60) return h->harm_minb == 2 ? launch_harm_t<16, 4, 2>(h, net, sn, ha, persistent, st)
-                                               : launch_harm_t<16, 4, 1>(h, net, sn, ha, persistent, st);
-        return launch_harm_t<16, 7, 1>(h, net, sn, ha, persistent, st);
+    const bool two = 2 * harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, 8, sn.yn_elems) + 2048 <=
+                     (size_t)h->smem_optin + 1024;
+    if (!h->no_specialise) {
+        if (net.n == 4 && net.m == 3 && net.c == 2 && net.H == 13 && net.q == 1)
+            return launch_harm_t<8, 2, Dims<4, 3, 2, 13, 1>>(h, net, sn, ha, persistent, st);
+        if (net.n == 4 && net.m == 2 && net.c == 1 && net.H == 10 && net.q == 2)
+            return launch_harm_t<8, 2, Dims<4, 2, 1, 10, 2>>(h, net, sn, ha, persistent, st);
     }
-    if (nZ <= 49) return launch_harm_t<8, 7, 2>(h, net, sn, ha, persistent, st);
-    return launch_harm_t<8, 15, 1>(h, net, sn, ha, persistent, st);
+    if (two) return launch_harm_t<8, 2, DynDims>(h, net, sn, ha, persistent, st);
+    return launch_harm_t<8, 1, DynDims>(h, net, sn, ha, persistent, st);
 }
 
 static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, const double* I_N,
@@ -984,6 +989,7 @@ int hpf_create(hpf_t** out, int device) {
     }
     if (const char* ev = getenv("HPF_HARM_WARPS")) h->harm_warps = (atoi(ev) == 16) ? 16 : 8;
     if (const char* ev = getenv("HPF_HARM_MINB")) h->harm_minb = (atoi(ev) == 2) ? 2 : 1;
+    if (const char* ev = getenv("HPF_NO_SPECIALISE")) h->no_specialise = atoi(ev) ? 1 : 0;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     e = cudaMalloc((void**)&h->d_counter, sizeof(int));

@@ -474,7 +474,6 @@ struct HarmTileArgs {
     double* dx_out;          // step_only: [N, B] the Newton update dx (x_new = x - dx)
 };
 
-#define HPF_ST_MAXNZ 105     // Z rows are held in registers: <= 15 rows per Z warp, 7 Z warps
 
 __host__ __device__ inline size_t harm_tile_const_doubles(int n, int H, int m, int yn_elems) {
     const size_t nH = (size_t)n * H, nZ = nH - m;
@@ -491,15 +490,25 @@ __host__ __device__ inline size_t harm_tile_smem_bytes(int n, int H, int m, int 
            8 * HPF_T * sizeof(int) + 64;
 }
 
-template <int NW, int MAXROWS, int MINB>
+// Shape specialisation: when the network dimensions are compile-time constants every loop
+// bound and every shared-memory offset folds into immediates (about a third of the generic
+// kernel's instructions are integer address arithmetic).  Dims<0,...> = runtime dimensions.
+template <int N_, int M_, int C_, int H_, int Q_>
+struct Dims {
+    static constexpr int n = N_, m = M_, c = C_, H = H_, q = Q_;
+};
+typedef Dims<0, 0, 0, 0, 0> DynDims;
+
+template <int NW, int MINB, class D>
 __global__ void __launch_bounds__(NW * 32, MINB)
 harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     extern __shared__ __align__(16) double smem[];
     constexpr int CW = NW - 1;                     // Z ("compute") warps
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool border = (warp == NW - 1);
-    const int n = net.n, m = net.m, c = net.c, H = net.H, q = net.q, nH = net.nH;
-    const int nZ = sn.nZ, nx = sn.nx, nth = m - 1;
+    const int n = D::n ? D::n : net.n, m = D::n ? D::m : net.m, c = D::n ? D::c : net.c;
+    const int H = D::n ? D::H : net.H, q = D::n ? D::q : net.q, nH = n * H;
+    const int nZ = nH - m, nx = (m - 1) + (m - c), nth = m - 1;
     const size_t B = (size_t)a.B;
 #define AT(X, i) X[(i) * HPF_T + lane]
     // ---- shared memory: network constants, then per-lane arrays ----
