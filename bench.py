@@ -387,12 +387,14 @@ def run_ours(a):
         # algorithmic FP64 work per Newton iteration of one scenario (DESIGN.md "Roofline accounting")
         nZ = n * H - m
         fl_mis = 8 * (H * n * n + q * H * H + (m - 1) * n)
-        fl_struct = fl_mis + 8 * nZ * nZ + 8 * nZ * (m - 1) + 10 * n * H
+        # structured step: u_Z = -V_Z - G (V_F + u_F) - w_N, polar conversion, small border system
+        fl_struct = fl_mis + 8 * nZ * m + 10 * n * H + 8 * (2 * m) ** 2
         fl_dense = fl_mis + 16 * (H * n * n + q * H * H) + 2.0 / 3.0 * N ** 3 + 2.0 * N * N
         fl_f = 24 * n * n + 2.0 / 3.0 * Nf ** 3 + 2.0 * Nf * Nf
         if strategy == "structured":
             kname = "harm_tile_kernel (harmonic Newton, structured step, 32 scenarios per CTA)"
-            flops = (it_h + B) * fl_mis + it_h * (fl_struct - fl_mis)   # n_iter+1 mismatches, n_iter steps
+            # n_iter+1 mismatches, n_iter steps (sincos: 52 per round, NOT counted as flops)
+            flops = (it_h + B) * fl_mis + it_h * (fl_struct - fl_mis)
             t_kernel = ms_harm / 1e3
             fl_iter = fl_struct
         else:
@@ -423,6 +425,9 @@ def run_ours(a):
                              "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (no FP64 figure "
                                             "in MEASURED_PEAKS.json)",
                              "flops_per_nr_iteration": fl_iter,
+                             "sincos_per_nr_iteration": n * H,
+                             "note": "latency/issue-bound kernel: flops exclude the FP64 sincos per phasor; see "
+                                     "profiles/ for issue-slot and FP64-pipe utilisation from ncu",
                              "hbm_bytes_per_scenario": by_solve,
                              "hbm_gbs_of_whole_solve": by_solve * B / (ms / a.steps) / 1e6},
                 "roofline_kernels": kernels, "hbm_peak_source": hbm_src}

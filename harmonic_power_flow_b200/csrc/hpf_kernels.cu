@@ -668,6 +668,8 @@ struct hpf_handle {
     size_t work_doubles = 0;
     double* d_io = nullptr;       // staging buffers of hpf_solve_host (grow-only)
     size_t io_doubles = 0;
+    cudaStream_t st_io[3] = {nullptr, nullptr, nullptr};   // copy-in, compute, copy-out
+    cudaEvent_t ev_io[8] = {};
     // structured strategy: 0 = not set up yet, 1 = ready, -1 = not available for this network
     int struct_state = 0;
     double2 *d_Ainv = nullptr, *d_Gz = nullptr, *d_WNL = nullptr, *d_wN = nullptr;
@@ -1010,6 +1012,8 @@ int hpf_destroy(hpf_t* h) {
     cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work); cudaFree(h->d_io); cudaFree(h->d_Ainv); cudaFree(h->d_Gz);
     cudaFree(h->d_WNL); cudaFree(h->d_wN);
     for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 3; ++i) if (h->st_io[i]) cudaStreamDestroy(h->st_io[i]);
+    for (int i = 0; i < 8; ++i) if (h->ev_io[i]) cudaEventDestroy(h->ev_io[i]);
     delete h;
     return HPF_OK;
 }
@@ -1211,39 +1215,71 @@ int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const doub
     int rc = ready(h, "hpf_solve_host", true);
     if (rc) return rc;
     if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_solve_host: B < 0");
+    if (!P || !Q || !V_m || !V_a || !n_iter_f || !n_iter_h || !err_h || !status || (h->q > 0 && !I_N))
+        return fail(h, HPF_E_INVALID, "hpf_solve_host: NULL buffer");
     CK(cudaSetDevice(h->device));
+    // Pipelined in chunks of scenarios on three streams: while chunk k is being solved,
+    // chunk k+1 is copied in and the results of chunk k-1 are copied out (PCIe is full duplex).
+    // The host arrays are batch-innermost [rows, B]; a chunk is a column block, moved with 2-D
+    // copies into compact [rows, Bc] device arrays (pinned host memory makes them asynchronous).
     const size_t n = h->n, H = h->H, q = h->q, Bs = (size_t)B;
-    const size_t nP = n * Bs, nI = 2 * q * H * Bs, nV = n * H * Bs;
-    // one grow-only device staging area: P, Q, I_N | V_m, V_a, I_inj, err_h | 3 int arrays
-    const size_t nd = 2 * nP + nI + 2 * nV + nI + Bs + (3 * Bs + 1) / 2 + 2;
+    int nchunk = (B >= 32768) ? 4 : (B >= 8192 ? 2 : 1);
+    const size_t Bc_max = ((Bs + nchunk - 1) / nchunk + 31) / 32 * 32;
+    nchunk = (int)((Bs + Bc_max - 1) / Bc_max);
+    // per chunk (compact): P, Q [n] | I_N [2qH] | V_m, V_a [nH] | I_inj [2qH] | err [1] | 3 ints
+    const size_t per_scn = 2 * n + 2 * q * H + 2 * n * H + 2 * q * H + 1 + 2;
+    const size_t nd = per_scn * Bc_max * nchunk + 16;
     if (nd > h->io_doubles) {
-        if (h->d_io) { cudaFree(h->d_io); h->d_io = nullptr; h->io_doubles = 0; }
+        if (h->d_io) { CK(cudaDeviceSynchronize()); cudaFree(h->d_io); h->d_io = nullptr; h->io_doubles = 0; }
         CK(cudaMalloc((void**)&h->d_io, nd * sizeof(double)));
         h->io_doubles = nd;
     }
-    double* d = h->d_io;
-    int* di = reinterpret_cast<int*>(d + 2 * nP + nI + 2 * nV + nI + Bs);
-    cudaError_t e;
-    double *dP = d, *dQ = dP + nP, *dI = dQ + nP, *dVm = dI + nI, *dVa = dVm + nV, *dInj = dVa + nV,
-           *dErr = dInj + nI;
-    cudaStream_t st = nullptr;
+    if (!h->st_io[0]) {
+        for (int i = 0; i < 3; ++i) CK(cudaStreamCreateWithFlags(&h->st_io[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&h->ev_io[i], cudaEventDisableTiming));
+    }
+    cudaStream_t s_in = h->st_io[0], s_cmp = h->st_io[1], s_out = h->st_io[2];
+    auto cp2d = [&](void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows,
+                    cudaMemcpyKind kind, cudaStream_t st) {
+        return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+    };
     rc = HPF_OK;
-    auto bail = [&](cudaError_t ee) { rc = fail(h, HPF_E_CUDA, cudaGetErrorString(ee)); };
-    if ((e = cudaMemcpyAsync(dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) bail(e);
-    if (!rc && (e = cudaMemcpyAsync(dQ, Q, nP * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) bail(e);
-    if (!rc && nI && (e = cudaMemcpyAsync(dI, I_N, nI * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) bail(e);
-    if (!rc)
-        rc = hpf_solve(h, B, dP, dQ, dI, thresh_f, max_iter_f, thresh_h, max_iter_h, 0, dVm, dVa,
-                       I_inj ? dInj : nullptr, di, di + Bs, dErr, di + 2 * Bs, nullptr, nullptr, st);
-    if (!rc && (e = cudaMemcpyAsync(V_m, dVm, nV * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
-    if (!rc && (e = cudaMemcpyAsync(V_a, dVa, nV * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
-    if (!rc && I_inj && nI && (e = cudaMemcpyAsync(I_inj, dInj, nI * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
-    if (!rc && (e = cudaMemcpyAsync(err_h, dErr, Bs * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
-    if (!rc && (e = cudaMemcpyAsync(n_iter_f, di, Bs * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
-    if (!rc && (e = cudaMemcpyAsync(n_iter_h, di + Bs, Bs * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
-    if (!rc && (e = cudaMemcpyAsync(status, di + 2 * Bs, Bs * sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) bail(e);
-    e = cudaStreamSynchronize(st);
-    if (!rc && e != cudaSuccess) bail(e);
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < nchunk && !rc; ++k) {
+        const size_t b0 = (size_t)k * Bc_max, Bc = (b0 + Bc_max <= Bs) ? Bc_max : Bs - b0;
+        double* d = h->d_io + (size_t)k * per_scn * Bc_max;
+        double *dP = d, *dQ = dP + n * Bc, *dI = dQ + n * Bc, *dVm = dI + 2 * q * H * Bc, *dVa = dVm + n * H * Bc,
+               *dInj = dVa + n * H * Bc, *dErr = dInj + 2 * q * H * Bc;
+        int* di = reinterpret_cast<int*>(dErr + Bc + (Bc & 1));
+        const size_t w8 = Bc * sizeof(double), w16 = Bc * 2 * sizeof(double);
+        const size_t p8 = Bs * sizeof(double), p16 = Bs * 2 * sizeof(double);
+        e = cp2d(dP, w8, P + b0, p8, w8, n, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess) e = cp2d(dQ, w8, Q + b0, p8, w8, n, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess && q)
+            e = cp2d(dI, w16, I_N + 2 * b0, p16, w16, q * H, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_io[k], s_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_cmp, h->ev_io[k], 0);
+        if (e != cudaSuccess) break;
+        rc = hpf_solve(h, (int)Bc, dP, dQ, dI, thresh_f, max_iter_f, thresh_h, max_iter_h, 0, dVm, dVa,
+                       I_inj ? dInj : nullptr, di, di + Bc, dErr, di + 2 * Bc, nullptr, nullptr, s_cmp);
+        if (rc) break;
+        e = cudaEventRecord(h->ev_io[4 + k], s_cmp);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, h->ev_io[4 + k], 0);
+        if (e == cudaSuccess) e = cp2d(V_m + b0, p8, dVm, w8, w8, n * H, cudaMemcpyDeviceToHost, s_out);
+        if (e == cudaSuccess) e = cp2d(V_a + b0, p8, dVa, w8, w8, n * H, cudaMemcpyDeviceToHost, s_out);
+        if (e == cudaSuccess && I_inj && q)
+            e = cp2d(I_inj + 2 * b0, p16, dInj, w16, w16, q * H, cudaMemcpyDeviceToHost, s_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(err_h + b0, dErr, Bc * sizeof(double), cudaMemcpyDeviceToHost, s_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(n_iter_f + b0, di, Bc * sizeof(int), cudaMemcpyDeviceToHost, s_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(n_iter_h + b0, di + Bc, Bc * sizeof(int), cudaMemcpyDeviceToHost, s_out);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(status + b0, di + 2 * Bc, Bc * sizeof(int), cudaMemcpyDeviceToHost, s_out);
+        if (e != cudaSuccess) break;
+    }
+    if (!rc && e != cudaSuccess) rc = fail(h, HPF_E_CUDA, std::string("hpf_solve_host: ") + cudaGetErrorString(e));
+    for (int i = 0; i < 3; ++i) {
+        const cudaError_t e2 = cudaStreamSynchronize(h->st_io[i]);
+        if (!rc && e2 != cudaSuccess) rc = fail(h, HPF_E_CUDA, std::string("hpf_solve_host: ") + cudaGetErrorString(e2));
+    }
     return rc;
 }
 

@@ -284,6 +284,20 @@ def test_host_buffer_entry_point_is_bit_identical(solvers):
         assert np.array_equal(a[k], b[k]), k
 
 
+def test_host_entry_point_chunked_pipeline(solvers, tmp_path):
+    """B large enough for the 4-chunk copy/solve/copy pipeline with a ragged last chunk: same
+    bits as the device-resident call (results do not depend on the position in the batch)."""
+    from harmonic_power_flow_b200 import scenarios
+    sol, net, _ = solvers("net3_c_h25")
+    B = 40001
+    P, Q, I_N = scenarios.make_batch(net, B, "tight", exact_prefix=16)
+    a = sol.solve(P, Q, I_N).to_host()
+    b = sol.solve_host(P, Q, I_N)
+    for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    assert (b["status"] == 0).all()
+
+
 def test_fused_solve_equals_stepwise_kernels(solvers):
     """The fused kernel and a host loop over kernels 2-4 share their arithmetic: identical
     iteration counts and (bitwise) identical iterates."""
