@@ -490,6 +490,22 @@ __host__ __device__ inline size_t harm_tile_smem_bytes(int n, int H, int m, int 
            8 * HPF_T * sizeof(int) + 64;
 }
 
+// Row loop of one warp: rows start, start+stride, ... < end.  With a compile-time row count
+// the loop is fully unrolled so the (independent) rows' dependency chains interleave: the
+// kernel is latency-bound, each row being a chain of dependent FP64 operations.
+template <int NR, class F>
+__device__ __forceinline__ void row_loop(int start, int end, int stride, F f) {
+    if constexpr (NR > 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int s = start + r * stride;
+            if (s < end) f(s);
+        }
+    } else {
+        for (int s = start; s < end; s += stride) f(s);
+    }
+}
+
 // Shape specialisation: when the network dimensions are compile-time constants every loop
 // bound and every shared-memory offset folds into immediates (about a third of the generic
 // kernel's instructions are integer address arithmetic).  Dims<0,...> = runtime dimensions.
@@ -509,6 +525,10 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     const int n = D::n ? D::n : net.n, m = D::n ? D::m : net.m, c = D::n ? D::c : net.c;
     const int H = D::n ? D::H : net.H, q = D::n ? D::q : net.q, nH = n * H;
     const int nZ = nH - m, nx = (m - 1) + (m - c), nth = m - 1;
+    // compile-time row counts per Z warp (0 = runtime loops)
+    constexpr int ZR = D::n ? (D::n * D::H - D::m + CW - 1) / CW : 0;
+    constexpr int HR = D::n ? (D::q * D::H + CW - 1) / CW : 0;
+    constexpr int LR = D::n ? (D::m * (D::H - 1) + CW - 1) / CW : 0;
     const size_t B = (size_t)a.B;
 #define AT(X, i) X[(i) * HPF_T + lane]
     // ---- shared memory: network constants, then per-lane arrays ----
@@ -617,12 +637,14 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                         AT(INre, u) = w.x; AT(INim, u) = w.y;
                     }
                 }
-                for (int s = m + warp; s < nH; s += CW) {
-                    const double2 e = sincos_ol(AT(Va, s));
+                row_loop<ZR>(m + warp, nH, CW, [&](int s) {
+                    double sn_, cs_;
+                    if constexpr (D::n != 0) sincos(AT(Va, s), &sn_, &cs_);       // inline: rows interleave
+                    else { const double2 e = sincos_ol(AT(Va, s)); cs_ = e.x; sn_ = e.y; }
                     const double vm = AT(Vm, s);
-                    AT(Vre, s) = vm * e.x;
-                    AT(Vim, s) = vm * e.y;
-                }
+                    AT(Vre, s) = vm * cs_;
+                    AT(Vim, s) = vm * sn_;
+                });
             }
         }
         __syncthreads();
@@ -631,7 +653,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
             double mx = 0.0;
             if (!border) {
                 // heavy rows first: nonlinear buses, (Y_h V_h)_i + I_N - sum_p Y_N[h][p] V_p,i
-                for (int u = warp; u < q * H; u += CW) {
+                row_loop<HR>(warp, q * H, CW, [&](int u) {
                     const int k = u / H, h = u - k * H, i = m + k, s = h * n + i;
                     const int dev = net.dev_of_nl[k];
                     double2 acc;
@@ -657,10 +679,10 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     const double v1 = fabs(f.x), v2 = fabs(f.y);      // s >= m >= c: both parts are rows
                     const double v = (v2 != v2 || v2 > v1) ? v2 : v1;
                     mx = (v != v || v > mx) ? v : mx;
-                }
+                });
                 // light rows: linear buses at the harmonics h >= 1 (index)
                 const int nlin = m * (H - 1);
-                for (int t = warp; t < nlin; t += CW) {
+                row_loop<LR>(warp, nlin, CW, [&](int t) {
                     const int h = 1 + t / m, i = t - (h - 1) * m;
                     const double2* Yrow = sY + ((size_t)h * n + i) * n;
                     double2 f = make_double2(0.0, 0.0);
@@ -671,7 +693,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     const double v1 = fabs(f.x), v2 = fabs(f.y);
                     const double v = (v2 != v2 || v2 > v1) ? v2 : v1;
                     mx = (v != v || v > mx) ? v : mx;
-                }
+                });
             } else {
                 // ---- border warp: power mismatch of the linear buses (HG:372-380) ----
                 for (int i = 0; i < m; ++i) {
@@ -821,7 +843,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
         }
         if (!border) {
             // u_z = -V_z - sum_i G[z][i] (V_i + u_F,i) - w_N,z ; polar conversion; update
-            for (int z = warp; z < nZ; z += CW) {
+            row_loop<ZR>(warp, nZ, CW, [&](int z) {
                 const int s = z + m;
                 const double2 vs = make_double2(AT(Vre, s), AT(Vim, s));
                 double2 acc = make_double2(vs.x + AT(Wre, z), vs.y + AT(Wim, z));
@@ -842,7 +864,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     AT(Va, s) += dth;
                     AT(Vm, s) = vm + dvm;
                 }
-            }
+            });
         } else {
             if (a.step_only) {
                 if (sc >= 0)
