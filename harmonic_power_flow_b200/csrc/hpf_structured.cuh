@@ -22,6 +22,7 @@
 // per CTA with lane = scenario; lanes are refilled from a global queue as soon as their
 // scenario finishes because iteration counts differ, 8..34+).
 #pragma once
+#include <cstdint>
 #include "hpf_device.cuh"
 
 #define HPF_T 32            // scenarios per tile (= lanes)
@@ -383,6 +384,14 @@ wn_tile_kernel(const DevNet net, const StructNet sn, const double2* __restrict__
     }
 }
 
+__device__ __forceinline__ void cp_async_f64(double* sdst, const double* gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
 // Out-of-line transcendental helpers: one copy each keeps the Newton loop inside the
 // instruction cache (the inlined versions made the kernel 150 KB of SASS).
 __device__ __noinline__ double2 sincos_ol(double x) {
@@ -626,17 +635,36 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                             AT(Va, s) = 0.0;
                         }
                     }
-                    for (int z = warp; z < nZ; z += CW) {
-                        double2 w = make_double2(0.0, 0.0);
-                        if (sc >= 0) w = __ldcs(a.wN + (size_t)z * B + sc);
-                        AT(Wre, z) = w.x; AT(Wim, z) = w.y;
-                    }
-                    for (int u = warp; u < q * H; u += CW) {
-                        double2 w = make_double2(0.0, 0.0);
-                        if (sc >= 0) w = __ldcs(a.I_N + (size_t)u * B + sc);
-                        AT(INre, u) = w.x; AT(INim, u) = w.y;
+                    // I_N and w_N of a refilled lane are not needed before phases B / C: fetch them
+                    // with asynchronous global->shared copies (LDGSTS) that complete behind the
+                    // sincos work instead of stalling the whole tile on DRAM latency every round.
+                    // group 0: I_N rows and the w_N rows the border system reads (z < q); group 1: rest
+                    if (sc >= 0) {
+                        for (int u = warp; u < q * H; u += CW) {
+                            const double* src = reinterpret_cast<const double*>(a.I_N + (size_t)u * B + sc);
+                            cp_async_f64(&AT(INre, u), src);
+                            cp_async_f64(&AT(INim, u), src + 1);
+                        }
+                        for (int z = warp; z < q; z += CW) {
+                            const double* src = reinterpret_cast<const double*>(a.wN + (size_t)z * B + sc);
+                            cp_async_f64(&AT(Wre, z), src);
+                            cp_async_f64(&AT(Wim, z), src + 1);
+                        }
+                    } else {
+                        for (int u = warp; u < q * H; u += CW) { AT(INre, u) = 0.0; AT(INim, u) = 0.0; }
+                        for (int z = warp; z < nZ; z += CW) { AT(Wre, z) = 0.0; AT(Wim, z) = 0.0; }
                     }
                 }
+                cp_async_commit();
+                if (isnew && sc >= 0) {
+                    for (int z = warp; z < nZ; z += CW) {
+                        if (z < q) continue;
+                        const double* src = reinterpret_cast<const double*>(a.wN + (size_t)z * B + sc);
+                        cp_async_f64(&AT(Wre, z), src);
+                        cp_async_f64(&AT(Wim, z), src + 1);
+                    }
+                }
+                cp_async_commit();
                 row_loop<ZR>(m + warp, nH, CW, [&](int s) {
                     double sn_, cs_;
                     if constexpr (D::n != 0) sincos(AT(Va, s), &sn_, &cs_);       // inline: rows interleave
@@ -645,6 +673,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     AT(Vre, s) = vm * cs_;
                     AT(Vim, s) = vm * sn_;
                 });
+                cp_async_wait<1>();                 // group 0 (I_N, first w_N rows) has landed
             }
         }
         __syncthreads();
@@ -796,6 +825,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 }
             }
             AT(red, warp) = mx;
+            if (!border) cp_async_wait<0>();        // remaining w_N rows (used in phase C by this thread)
         }
         __syncthreads();
         // ================= C: decisions, finished lanes, update, refill =================
