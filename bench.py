@@ -338,32 +338,46 @@ def run_ours(a):
     kernels = []
     fp64_peak = None
     if rank == 0:
-        def timed(fn, reps=5):
-            fn(); torch.cuda.synchronize()
-            tot = 0.0
-            for _ in range(reps):
-                flush.fill_(1)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-                tot += e0.elapsed_time(e1)
-            return tot / reps
+        def timed(fns, reps=12):
+            """Average device time of one launch: `reps` launches queued back to back between two
+            events (host launch overhead hidden behind the running kernels), rotating over
+            input/output sets whose total footprint exceeds the 126 MB L2."""
+            for fn in fns:
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.fill_(1)
+            e0.record()
+            for r in range(reps):
+                fns[r % len(fns)]()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
         raw = sol.solve(dP, dQ, dI, raw=True, max_iter_h=3, want_I_inj=False)   # a mid-iteration state
         Vm, Va = raw.V_m, raw.V_a
-        t_mis = timed(lambda: sol.mismatch(Vm, Va, dP, dQ, dI))
+        nset = 3                                             # 3 x 124 MB of traffic per rotation
+        sets = [(Vm.clone(), Va.clone(), dP.clone(), dQ.clone(), dI.clone(),
+                 (torch.empty((N, B), dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.float64, device=dev)))
+                for _ in range(nset)]
+        t_mis = timed([(lambda s_=s_: sol.mismatch(s_[0], s_[1], s_[2], s_[3], s_[4], out=s_[5])) for s_ in sets])
+        del sets
         by_mis = 16 * n * H + 8 * N + 16 * q * H + 16 * (m - 1) + 8
-        kernels.append({"kernel": "mismatch_tile_kernel", "bound": "hbm", "ms": t_mis,
+        kernels.append({"kernel": "mismatch_tile_kernel", "bound": "hbm (nominal); instruction issue in ncu",
+                        "ms": t_mis,
                         "achieved": by_mis * B / t_mis / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": by_mis * B / t_mis / 1e6 / hbm_peak, "bytes_per_scenario": by_mis})
+                        "frac": by_mis * B / t_mis / 1e6 / hbm_peak, "bytes_per_scenario": by_mis,
+                        "timing": "12 back-to-back launches over 3 rotating buffer sets (372 MB > L2)"})
         Bj = min(B, 16384)
-        J = sol.jacobian(Vm[:, :, :Bj].contiguous(), Va[:, :, :Bj].contiguous())
         Vmj, Vaj = Vm[:, :, :Bj].contiguous(), Va[:, :, :Bj].contiguous()
-        t_jac = timed(lambda: sol.jacobian(Vmj, Vaj, out=J))
+        Js = [sol.jacobian(Vmj, Vaj) for _ in range(2)]      # 2 x 1.35 GB outputs
+        t_jac = timed([(lambda J_=J_: sol.jacobian(Vmj, Vaj, out=J_)) for J_ in Js], reps=6)
+        J = Js[0]
+        del Js
         by_jac = 8 * N * N + 16 * n * H
         kernels.append({"kernel": "jacobian_kernel", "bound": "hbm", "ms": t_jac, "batch": Bj,
                         "achieved": by_jac * Bj / t_jac / 1e6, "peak": hbm_peak, "unit": "GB/s",
                         "frac": by_jac * Bj / t_jac / 1e6 / hbm_peak, "bytes_per_scenario": by_jac})
         f, _ = sol.mismatch(Vmj, Vaj, dP[:, :Bj].contiguous(), dQ[:, :Bj].contiguous(), dI[:, :, :Bj].contiguous())
-        t_lu = timed(lambda: sol.lu_solve(J, f), reps=3)
+        t_lu = timed([lambda: sol.lu_solve(J, f)], reps=3)
         fl_lu = 2.0 / 3.0 * N ** 3 + 2.0 * N * N
         del J
         fp64_peak = measure_fp64_peak(torch, dev)

@@ -367,10 +367,11 @@ struct MismatchArgs {
     double2* I_inj;
 };
 
-__host__ __device__ inline size_t tile_smem_bytes(int n, int H, int q) {
+__host__ __device__ inline size_t tile_smem_bytes(int n, int H, int q, int m, int yn_elems) {
     const size_t nH = (size_t)n * H;
-    // V (re, im) [nH][32]; I_N, I_inj [qH][32] c128; I1 [n][32] c128; P, Q [n][32]; red [8][32]
-    return (2 * nH + 4 * (size_t)q * H + 2 * n + 2 * n + 8) * HPF_TILE * sizeof(double) + 16;
+    // constants Y, Y_N (c128); I_N [qH][32] c128; V (re, im) [nH][32]; P, Q [m][32]; red [8][32]
+    return (2 * ((size_t)H * n * n + yn_elems) + (2 * (size_t)q * H + 2 * nH + 2 * m + 8) * HPF_TILE) *
+               sizeof(double) + 16;
 }
 
 __device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
@@ -386,23 +387,34 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // The whole input tile (V_m, V_a, P, Q, I_N of 32 scenarios) is requested with asynchronous
-// copies (LDGSTS) before anything is computed, so every byte of the tile is in flight at once
-// (the first version loaded row by row between sincos calls and was latency-bound at 25 % of
-// HBM bandwidth).
-__global__ void __launch_bounds__(HPF_THREADS)
-mismatch_tile_kernel(const DevNet net, const MismatchArgs a) {
+// copies (LDGSTS) before anything is computed, so every byte of the tile is in flight at once.
+// ncu shows the kernel is bound by INSTRUCTION ISSUE, not by HBM (52 FP64 sincos + ~400
+// complex MACs per 1.9 KB of traffic), so the instruction count is what matters: network
+// constants live in shared memory and the shape-specialised instances (class D, see
+// hpf_structured.cuh) fold all index arithmetic into immediates.
+template <class D>
+__global__ void __launch_bounds__(HPF_THREADS, 4)
+mismatch_tile_kernel(const DevNet net, const MismatchArgs a, const int yn_elems) {
     extern __shared__ __align__(16) double smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int n = net.n, H = net.H, nH = net.nH, q = net.q, c = net.c, m = net.m;
+    constexpr int NW = HPF_THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = D::n ? D::n : net.n, m = D::n ? D::m : net.m, c = D::n ? D::c : net.c;
+    const int H = D::n ? D::H : net.H, q = D::n ? D::q : net.q, nH = n * H;
+    constexpr int SR = D::n ? (D::n * D::H + NW - 1) / NW : 0;
+    constexpr int HR = D::n ? (D::q * D::H + NW - 1) / NW : 0;
+    constexpr int LR = D::n ? (D::m * D::H + NW - 1) / NW : 0;
     const size_t B = (size_t)a.B;
-    double2* I1 = reinterpret_cast<double2*>(smem);
-    double2* IN = I1 + (size_t)n * HPF_TILE;
-    double2* Iinj = IN + (size_t)q * H * HPF_TILE;
-    double* Vre = reinterpret_cast<double*>(Iinj + (size_t)q * H * HPF_TILE);   // raw V_m, then Re V
-    double* Vim = Vre + (size_t)nH * HPF_TILE;                                   // raw V_a, then Im V
+    double2* sY = reinterpret_cast<double2*>(smem);
+    double2* sYN = sY + (size_t)H * n * n;
+    double2* IN = sYN + yn_elems;
+    double* Vre = reinterpret_cast<double*>(IN + (size_t)q * H * HPF_TILE);   // raw V_m, then Re V
+    double* Vim = Vre + (size_t)nH * HPF_TILE;                                  // raw V_a, then Im V
     double* Pl = Vim + (size_t)nH * HPF_TILE;
-    double* Ql = Pl + (size_t)n * HPF_TILE;
-    double* red = Ql + (size_t)n * HPF_TILE;
+    double* Ql = Pl + (size_t)m * HPF_TILE;
+    double* red = Ql + (size_t)m * HPF_TILE;
+    for (int t = threadIdx.x; t < H * n * n; t += HPF_THREADS) sY[t] = net.Y[t];
+    for (int t = threadIdx.x; t < yn_elems; t += HPF_THREADS) sYN[t] = net.YN[t];
+#define TA(X, i) X[(i) * HPF_TILE + lane]
 
     for (size_t tile = blockIdx.x; tile * HPF_TILE < B; tile += gridDim.x) {
         const size_t b = tile * HPF_TILE + lane;
@@ -410,64 +422,96 @@ mismatch_tile_kernel(const DevNet net, const MismatchArgs a) {
         const size_t bb = ok ? b : B - 1;            // clamp: compute, do not store
         __syncthreads();
         // phase L: request the tile
-        for (int t = warp; t < nH; t += nw) {
-            cp_async8(Vre + t * HPF_TILE + lane, a.V_m + t * B + bb);
-            cp_async8(Vim + t * HPF_TILE + lane, a.V_a + t * B + bb);
+        for (int t = warp; t < nH; t += NW) {
+            cp_async8(&TA(Vre, t), a.V_m + t * B + bb);
+            cp_async8(&TA(Vim, t), a.V_a + t * B + bb);
         }
-        for (int t = 1 + warp; t < m; t += nw) {
-            cp_async8(Pl + t * HPF_TILE + lane, a.P + t * B + bb);
-            cp_async8(Ql + t * HPF_TILE + lane, a.Q + t * B + bb);
+        for (int t = 1 + warp; t < m; t += NW) {
+            cp_async8(&TA(Pl, t), a.P + t * B + bb);
+            cp_async8(&TA(Ql, t), a.Q + t * B + bb);
         }
-        for (int u = warp; u < q * H; u += nw) cp_async16(IN + u * HPF_TILE + lane, a.I_N + u * B + bb);
+        for (int u = warp; u < q * H; u += NW) cp_async16(&TA(IN, u), a.I_N + u * B + bb);
         cp_async_wait_all();
         __syncthreads();
-        // phase A: phasors in place
-        for (int t = warp; t < nH; t += nw) {
-            const double vm = Vre[t * HPF_TILE + lane];
+        // phase A: phasors in place, V = V_m e^{j theta}
+        row_loop<SR>(warp, nH, NW, [&](int t) {
+            const double vm = TA(Vre, t);
             double sn, cs;
-            sincos(Vim[t * HPF_TILE + lane], &sn, &cs);
-            Vre[t * HPF_TILE + lane] = vm * cs;
-            Vim[t * HPF_TILE + lane] = vm * sn;
-        }
+            sincos(TA(Vim, t), &sn, &cs);
+            TA(Vre, t) = vm * cs;
+            TA(Vim, t) = vm * sn;
+        });
         __syncthreads();
-        // phase B: I1 = Y1 V1 and Norton injections
-        for (int t = warp; t < n + q * H; t += nw) {
-            if (t < n) {
-                I1[t * HPF_TILE + lane] = ydotv<HPF_TILE>(net, 0, t, lane, Vre, Vim);
-            } else {
-                const int u = t - n, k = u / H, h = u - k * H;
-                const double2 inj = norton_injection<HPF_TILE>(net, k, h, lane, Vre, Vim, IN[u * HPF_TILE + lane]);
-                Iinj[u * HPF_TILE + lane] = inj;
-                if (a.I_inj && ok) a.I_inj[u * B + b] = inj;
-            }
-        }
-        __syncthreads();
-        // phase C: mismatch rows
+        // phase B: rows of the mismatch (HG:360-388)
         double mx = 0.0;
-        for (int e = warp; e < nH - 1; e += nw) {
-            const double2 f = harmonic_mismatch_entry<HPF_TILE>(net, e, lane, Vre, Vim, I1, Iinj, Pl, Ql);
+        auto emit = [&](int s, double2 f) {          // s = stacked index of the row, entry e = s - 1
+            const int e = s - 1;
             double v1 = fabs(f.x);
-            if (ok) __stcs(a.f + (size_t)h_row_re(net, e) * B + b, f.x);
+            if (ok) __stcs(a.f + (size_t)e * B + b, f.x);
             if (e >= c - 1) {
-                if (ok) __stcs(a.f + (size_t)h_row_im(net, e) * B + b, f.y);
+                if (ok) __stcs(a.f + (size_t)((nH - 1) + e - (c - 1)) * B + b, f.y);
                 const double v2 = fabs(f.y);
                 v1 = (v2 != v2 || v2 > v1) ? v2 : v1;
             }
             mx = (v1 != v1 || v1 > mx) ? v1 : mx;
-        }
-        red[warp * HPF_TILE + lane] = mx;
+        };
+        // nonlinear buses: (Y_h V_h)_i + I_N - sum_p Y_N[h][p] V_p,i   (HG:313-323,335-354)
+        row_loop<HR>(warp, q * H, NW, [&](int u) {
+            const int k = u / H, h = u - k * H, i = m + k, s = h * n + i;
+            const int dev = net.dev_of_nl[k];
+            double2 acc;
+            if (net.coupled) {
+                const double2* row = sYN + ((size_t)dev * H + h) * H;
+                acc = make_double2(0.0, 0.0);
+                for (int pp = 0; pp < H; ++pp) {
+                    const int t2 = pp * n + i;
+                    acc = cfma(acc, row[pp], make_double2(TA(Vre, t2), TA(Vim, t2)));
+                }
+            } else {
+                acc = cmul(sYN[(size_t)dev * H + h], make_double2(TA(Vre, s), TA(Vim, s)));
+            }
+            const double2 inj = csub(TA(IN, u), acc);
+            if (a.I_inj && ok) a.I_inj[u * B + b] = inj;
+            const double2* Yrow = sY + ((size_t)h * n + i) * n;
+            double2 f = make_double2(0.0, 0.0);
+            for (int j = 0; j < n; ++j) {
+                const int t2 = h * n + j;
+                f = cfma(f, Yrow[j], make_double2(TA(Vre, t2), TA(Vim, t2)));
+            }
+            emit(s, cadd(f, inj));
+        });
+        // linear buses: current balance at h >= 1 (index), power balance at the fundamental
+        row_loop<LR>(warp, m * H, NW, [&](int t) {
+            const int h = t / m, i = t - h * m, s = h * n + i;
+            if (s == 0) return;                                  // slack: no row
+            const double2* Yrow = sY + ((size_t)h * n + i) * n;
+            double2 f = make_double2(0.0, 0.0);
+            for (int j = 0; j < n; ++j) {
+                const int t2 = h * n + j;
+                f = cfma(f, Yrow[j], make_double2(TA(Vre, t2), TA(Vim, t2)));
+            }
+            if (h == 0) {                                        // dS = (P + jQ) + V conj(Y1 V)  (HG:372-380)
+                const double2 v = make_double2(TA(Vre, i), TA(Vim, i));
+                const double2 sl = cmul(v, cconj(f));
+                f = make_double2(TA(Pl, i) + sl.x, TA(Ql, i) + sl.y);
+            }
+            emit(s, f);
+        });
+        TA(red, warp) = mx;
         __syncthreads();
         if (warp == 0) {
             double r = 0.0;
             bool bad = false;
-            for (int w = 0; w < nw; ++w) {
-                const double v = red[w * HPF_TILE + lane];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const double v = TA(red, w);
                 bad |= (v != v);
                 r = fmax(r, v);
             }
             if (ok) a.err[b] = bad ? CUDART_NAN : r;
         }
     }
+#undef TA
 }
 
 // Fallback for networks whose 32-scenario tile does not fit in shared memory (e.g. net1 with
@@ -1295,15 +1339,28 @@ int hpf_mismatch(hpf_t* h, int B, const double* V_m, const double* V_a, const do
     MismatchArgs a;
     a.B = B; a.V_m = V_m; a.V_a = V_a; a.P = P; a.Q = Q; a.I_N = (const double2*)I_N;
     a.f = f; a.err = err; a.I_inj = (double2*)I_inj;
-    size_t smem = tile_smem_bytes(net.n, net.H, net.q);
+    const int yn_elems = h->n_dev * (h->coupled ? h->H * h->H : h->H);
+    size_t smem = tile_smem_bytes(net.n, net.H, net.q, net.m, yn_elems);
     int occ = 0;
     if (smem <= (size_t)h->smem_optin) {
-        rc = prep_kernel(h, mismatch_tile_kernel, smem, "hpf_mismatch", &occ);
+        const long long tiles = ((long long)B + HPF_TILE - 1) / HPF_TILE;
+        auto launch = [&](auto kernel) -> int {
+            int rc2 = prep_kernel(h, kernel, smem, "hpf_mismatch", &occ);
+            if (rc2) return rc2;
+            // one CTA per 32-scenario tile: the hardware scheduler balances the tail (a persistent
+            // grid of occ*SMs CTAs quantises 2048 tiles into 4 rounds of 592, 13 % idle)
+            long long grid = tiles;
+            (void)occ;
+            kernel<<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a, yn_elems);
+            return HPF_OK;
+        };
+        if (!h->no_specialise && net.n == 4 && net.m == 3 && net.c == 2 && net.H == 13 && net.q == 1)
+            rc = launch(mismatch_tile_kernel<Dims<4, 3, 2, 13, 1>>);
+        else if (!h->no_specialise && net.n == 4 && net.m == 2 && net.c == 1 && net.H == 10 && net.q == 2)
+            rc = launch(mismatch_tile_kernel<Dims<4, 2, 1, 10, 2>>);
+        else
+            rc = launch(mismatch_tile_kernel<DynDims>);
         if (rc) return rc;
-        long long tiles = ((long long)B + HPF_TILE - 1) / HPF_TILE;
-        long long grid = (long long)occ * h->sm_count;
-        if (grid > tiles) grid = tiles;
-        mismatch_tile_kernel<<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a);
     } else {
         smem = scn_smem_bytes(net.n, net.H, net.q, net.N, false);
         rc = prep_kernel(h, mismatch_cta_kernel, smem, "hpf_mismatch", &occ);

@@ -264,12 +264,12 @@ class BatchSolver:
         return dx
 
     # -- standalone kernels --------------------------------------------------------------
-    def mismatch(self, V_m, V_a, P, Q, I_N=None, want_I_inj=False):
+    def mismatch(self, V_m, V_a, P, Q, I_N=None, want_I_inj=False, out=None):
         n = self.net
         V_m, V_a = self._dev(V_m, torch.float64), self._dev(V_a, torch.float64)
         P, Q, I_N = self.prepare(P, Q, I_N)
         B = P.shape[1]
-        f, err = self._f64(self.N, B), self._f64(B)
+        f, err = out if out is not None else (self._f64(self.N, B), self._f64(B))
         I_inj = self._c128(n.q, n.H, B) if want_I_inj else None
         _lib.check(self._h, self.lib.hpf_mismatch(self._h, B, _ptr(V_m), _ptr(V_a), _ptr(P), _ptr(Q),
                                                   _ptr(I_N), _ptr(f), _ptr(err), _ptr(I_inj), self._stream()))
