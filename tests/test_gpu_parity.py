@@ -414,3 +414,63 @@ def test_reference_shaped_api(tmp_path):
     THD = hg.get_THD(V)
     assert np.abs(THD.to_numpy() - d["THD"]).max() < 1e-8
     hg.configure(H_MAX=51)
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_full_size_batch_properties(solvers):
+    """BASELINE config 3 at full size (65,536 scenarios): size-independent properties.
+    (a) every scenario converges; (b) the returned iterate really has ||f||_inf <= 1e-4 when the
+    mismatch is re-evaluated by the standalone kernel on the raw iterate, and it equals the
+    reported err_h; (c) splitting the batch differently (as another GPU count would) gives
+    bit-identical results; (d) I_inj equals I_N - Y_N V recomputed on the host for a sample."""
+    from harmonic_power_flow_b200 import scenarios
+    sol, net, _ = solvers("net3_c_h25")
+    B = 65536
+    P, Q, I_N = scenarios.make_batch(net, B, "tight", exact_prefix=32)
+    dP, dQ, dI = sol.prepare(P, Q, I_N)
+    raw = sol.solve(dP, dQ, dI, raw=True)
+    assert int((raw.status == 0).sum()) == B
+    assert int(raw.n_iter_f.min()) == 2 and int(raw.n_iter_f.max()) == 2
+    f, err = sol.mismatch(raw.V_m, raw.V_a, dP, dQ, dI)
+    assert float(err.max()) <= 1e-4
+    assert torch.allclose(err, raw.err_h, rtol=1e-6, atol=1e-13)
+    # (c) three unequal shards vs one batch
+    cuts = [0, 21845, 43691, B]
+    for lo, hi in zip(cuts, cuts[1:]):
+        part = sol.solve(dP[:, lo:hi].contiguous(), dQ[:, lo:hi].contiguous(), dI[:, :, lo:hi].contiguous(),
+                         raw=True)
+        assert torch.equal(part.V_m, raw.V_m[:, :, lo:hi]) and torch.equal(part.V_a, raw.V_a[:, :, lo:hi])
+        assert torch.equal(part.n_iter_h, raw.n_iter_h[lo:hi]) and torch.equal(part.I_inj, raw.I_inj[:, :, lo:hi])
+    # (d) Norton injection identity on a sample
+    V = (raw.V_m * torch.exp(1j * raw.V_a))[:, net.m:, ::4099].cpu().numpy()          # [H, q, S]
+    inj = raw.I_inj[:, :, ::4099].cpu().numpy()
+    want = I_N[:, :, ::4099] - np.einsum("qhp,pqs->qhs", net.Y_N[net.dev_of_nl_bus], V)
+    assert np.abs(inj - want).max() <= 1e-12 * np.abs(want).max()
+    # post-processed output is the same phasor, magnitudes >= 0, angles in [0, 2 pi]
+    pp = sol.solve(dP, dQ, dI)
+    Vr = raw.V_m * torch.exp(1j * raw.V_a)
+    Vp = pp.V_m * torch.exp(1j * pp.V_a)
+    assert float((Vr - Vp).abs().max()) < 1e-10          # torch.exp on un-reduced angles of tens of radians
+    assert float(pp.V_m.min()) >= 0 and float(pp.V_a.min()) >= 0 and float(pp.V_a.max()) <= 2 * np.pi
+
+
+def test_config2_batch_1024_against_oracle(solvers):
+    """BASELINE config 2: net2 with two Norton loads (SMPS + EV), odd harmonics to the 19th,
+    1,024 scenarios; a sample is checked against the CPU oracle, the whole batch for convergence."""
+    from harmonic_power_flow_b200 import scenarios
+    sol, net, _ = solvers("net2ev_c_h19")
+    B = 1024
+    P, Q, I_N = scenarios.make_batch(net, B, "tight")
+    r = sol.solve(P, Q, I_N).to_host()
+    assert (r["status"] == 0).all()
+    on = O.net_from_golden(GOLDEN, "net2ev", 19, True)
+    Y = O.build_admittance_matrices(on)
+    mism = 0
+    for b in range(0, B, 37):
+        o = O.hpf(on, P=P[:, b], Q=Q[:, b], I_N=I_N[:, :, b], Y=Y)
+        mism += int(o["n_iter_h"] != r["n_iter_h"][b])
+        if o["n_iter_h"] == r["n_iter_h"][b]:
+            V = helpers.phasor(r["V_m"][:, :, b], r["V_a"][:, :, b])
+            Vo = helpers.phasor(o["V_m"], o["V_a"])
+            assert (np.abs(V - Vo) / np.abs(Vo)).max() < 1e-6
+    assert mism <= 2            # 28 samples; the reference disagrees with itself at this rate
