@@ -677,6 +677,183 @@ lu_solve_kernel(const DevNet net, const LuArgs a) {
 }
 
 // =======================================================================================
+// Structured Newton step for networks whose 32-scenario tile does not fit in shared memory
+// (e.g. net1: 20 buses x 26 harmonics): one scenario per CTA, threads over the rows, same
+// closed-form step as harm_tile_kernel (hpf_structured.cuh); Y(h), G and W_NL stay in
+// global memory (L2), the border system is solved by the block LU (lu_solve_smem).
+__host__ __device__ inline size_t harm_cta_smem_bytes(int n, int H, int m, int c, int q, int N) {
+    const size_t nH = (size_t)n * H, nZ = nH - m, nx = (size_t)(m - 1) + (m - c);
+    return scn_smem_bytes(n, H, q, N, false) +
+           (2 * nZ + 2 * q + 2 * m + (size_t)odd_ld((int)nx) * (nx + 1) + nx + 8) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(HPF_THREADS)
+harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const ScnSmem s = carve(smem, net, false);
+    const int tid = threadIdx.x;
+    const int n = net.n, m = net.m, c = net.c, H = net.H, q = net.q, nH = net.nH, N = net.N;
+    const int nZ = sn.nZ, nx = sn.nx, nth = m - 1, ldb = odd_ld(nx);
+    const size_t B = (size_t)a.B;
+    double* rhs = s.rinv;                                     // f, N doubles
+    double* wbase = reinterpret_cast<double*>(s.flag) + 4;
+    if ((reinterpret_cast<uintptr_t>(wbase) & 15) != 0) wbase += 1;            // double2 alignment
+    double2* W = reinterpret_cast<double2*>(wbase);
+    double2* U0 = W + nZ;
+    double2* UF = U0 + q;
+    double* Mb = reinterpret_cast<double*>(UF + m);           // ldb x (nx + 1), column-major
+    double* brinv = Mb + (size_t)ldb * (nx + 1);
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s.flag[1] = a.step_only ? (int)blockIdx.x : atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int b = s.flag[1];
+        if (b >= a.B) break;
+        for (int t = tid; t < n; t += blockDim.x) {
+            s.P[t] = a.P[t * B + b];
+            s.Q[t] = a.Q[t * B + b];
+        }
+        for (int t = tid; t < q * H; t += blockDim.x) s.IN[t] = a.I_N[t * B + b];
+        for (int t = tid; t < nZ; t += blockDim.x) W[t] = a.wN[t * B + b];
+        for (int t = tid; t < nH; t += blockDim.x) {
+            if (a.step_only || t < n) {
+                s.Vm[t] = a.V_m[t * B + b];
+                s.Va[t] = a.V_a[t * B + b];
+            } else {
+                s.Vm[t] = 0.1;                                 // flat start of the harmonics (HG:183)
+                s.Va[t] = 0.0;
+            }
+        }
+        __syncthreads();
+        int status = a.step_only ? 0 : a.status[b];
+        int it = 0;
+        double err;
+        for (;;) {
+            err = cta_harmonic_mismatch(net, s, rhs);          // phasors, I1, Iinj, f
+            if (!a.step_only && !((err > a.thresh_h) && (it < a.max_h))) break;
+            // u0 of the fundamental nonlinear rows (closed form)
+            for (int k = tid; k < q; k += blockDim.x) {
+                const int sk = m + k;
+                double2 acc = make_double2(s.Vre[sk] + W[k].x, s.Vim[sk] + W[k].y);
+                for (int i = 0; i < m; ++i)
+                    acc = cfma(acc, ldg2(sn.G + (size_t)k * m + i), make_double2(s.Vre[i], s.Vim[i]));
+                U0[k] = cneg(acc);
+            }
+            __syncthreads();
+            // border system: one thread per (power row i, column), entries accumulated in registers
+            for (int t = tid; t < nth * (nx + 1); t += blockDim.x) {
+                const int i = 1 + t / (nx + 1), col = t - (i - 1) * (nx + 1);
+                const double2 vi = make_double2(s.Vre[i], s.Vim[i]);
+                const double2 ei = make_double2(s.Ere[i], s.Eim[i]);
+                const double2 i1 = s.I1[i];
+                const double2 jvi = cmulj(vi);
+                const bool is_rhs = (col == nx), is_v = (col >= nth);
+                const int j = is_rhs ? 0 : (is_v ? c + (col - nth) : col + 1);
+                double2 e, vj = make_double2(0.0, 0.0), ej = vj;
+                if (is_rhs) {
+                    // f_S of bus i sits in rhs[]: Re at row i-1, Im at row (nH-1) + (i-1) - (c-1)
+                    e = make_double2(-rhs[i - 1], (i >= c) ? -rhs[(nH - 1) + (i - 1) - (c - 1)] : 0.0);
+                } else {
+                    const double2 y = ldg2(net.Y + (size_t)i * n + j);
+                    vj = make_double2(s.Vre[j], s.Vim[j]);
+                    ej = make_double2(s.Ere[j], s.Eim[j]);
+                    if (is_v) {
+                        e = cmul(vi, cconj(cmul(y, ej)));
+                        if (i == j) e = cadd(cmul(ei, cconj(i1)), e);
+                    } else {
+                        const double2 yv = cmul(y, vj);
+                        e = cmul(jvi, cconj((i == j) ? csub(i1, yv) : cneg(yv)));
+                    }
+                }
+                for (int k = 0; k < q; ++k) {
+                    const int bk = m + k;
+                    const double2 y = ldg2(net.Y + (size_t)i * n + bk);
+                    if (y.x == 0.0 && y.y == 0.0) continue;
+                    const double2 vb = make_double2(s.Vre[bk], s.Vim[bk]);
+                    const double2 eb = make_double2(s.Ere[bk], s.Eim[bk]);
+                    const double2 ak = cmul(jvi, cconj(cneg(cmul(y, vb))));
+                    const double2 vk = cmul(vi, cconj(cmul(y, eb)));
+                    const double2 uu = is_rhs ? U0[k] : cmul(ldg2(sn.G + (size_t)k * m + j), is_v ? ej : cmulj(vj));
+                    const double2 ce = cmul(cconj(eb), uu);
+                    const double dth = ce.y / s.Vm[bk], dvm = ce.x;
+                    e.x -= ak.x * dth + vk.x * dvm;
+                    e.y -= ak.y * dth + vk.y * dvm;
+                }
+                Mb[(i - 1) + (size_t)col * ldb] = e.x;
+                if (i >= c) Mb[(nth + i - c) + (size_t)col * ldb] = e.y;
+            }
+            int info = 0;
+            if (nx > 0) info = lu_solve_smem(Mb, nx, ldb, brinv, s.flag);   // (starts with a barrier)
+            else __syncthreads();
+            if (info && status == HPF_ST_CONVERGED) status = HPF_ST_SINGULAR;
+            const double* xF = Mb + (size_t)nx * ldb;
+            for (int i = tid; i < m; i += blockDim.x) {
+                const double dth = (i >= 1) ? xF[i - 1] : 0.0;
+                const double dvm = (i >= c) ? xF[nth + i - c] : 0.0;
+                const double2 vi = make_double2(s.Vre[i], s.Vim[i]);
+                UF[i] = make_double2(-vi.y * dth + s.Ere[i] * dvm, vi.x * dth + s.Eim[i] * dvm);
+            }
+            __syncthreads();
+            // u_Z = -V_Z - G (V_F + u_F) - w_N, polar conversion, update (Vre/Vim/E are this
+            // round's phasors and are not touched here, so rows can be updated in any order)
+            for (int z = tid; z < nZ; z += blockDim.x) {
+                const int sz = z + m;
+                double2 acc = make_double2(s.Vre[sz] + W[z].x, s.Vim[sz] + W[z].y);
+                const double2* grow = sn.G + (size_t)z * m;
+                for (int i = 0; i < m; ++i)
+                    acc = cfma(acc, ldg2(grow + i), make_double2(s.Vre[i] + UF[i].x, s.Vim[i] + UF[i].y));
+                const double2 wv = cmul(make_double2(s.Ere[sz], -s.Eim[sz]), cneg(acc));
+                const double vm = s.Vm[sz];
+                const double dth = wv.y / vm, dvm = wv.x;
+                if (a.step_only) {
+                    a.dx_out[(size_t)(sz - 1) * B + b] = -dth;
+                    a.dx_out[(size_t)((nH - 1) + sz - c) * B + b] = -dvm;
+                } else {
+                    s.Va[sz] += dth;
+                    s.Vm[sz] = vm + dvm;
+                }
+            }
+            for (int i = 1 + tid; i < m; i += blockDim.x) {
+                const double dth = xF[i - 1];
+                const double dvm = (i >= c) ? xF[nth + i - c] : 0.0;
+                if (a.step_only) {
+                    a.dx_out[(size_t)(i - 1) * B + b] = -dth;
+                    if (i >= c) a.dx_out[(size_t)((nH - 1) + i - c) * B + b] = -dvm;
+                } else {
+                    s.Va[i] += dth;
+                    if (i >= c) s.Vm[i] += dvm;
+                }
+            }
+            __syncthreads();
+            if (a.step_only) break;
+            ++it;
+        }
+        if (a.step_only) break;                                // one scenario per CTA in step mode
+        if (it >= a.max_h && status == HPF_ST_CONVERGED) status = HPF_ST_MAXITER;
+        if (!(err < CUDART_INF)) status = HPF_ST_NONFINITE;
+        for (int t = tid; t < nH; t += blockDim.x) {
+            double vm = s.Vm[t], va = s.Va[t];
+            if (!(a.flags & HPF_SOLVE_RAW)) {
+                if (vm < 0.0) va += CUDART_PI;
+                va = mod_twopi(va);
+                if (vm < 0.0) vm = -vm;
+            }
+            a.V_m[t * B + b] = vm;
+            a.V_a[t * B + b] = va;
+        }
+        if (a.I_inj)
+            for (int t = tid; t < q * H; t += blockDim.x) a.I_inj[t * B + b] = s.Iinj[t];
+        if (tid == 0) {
+            a.n_iter_h[b] = it;
+            a.err_h[b] = err;
+            a.status[b] = status;
+        }
+    }
+    (void)N;
+}
+
+// =======================================================================================
 // THD (HG:563-572): one thread per (bus, scenario); sums run sequentially over the
 // harmonics like Python's sum(); coalesced across the batch.
 __global__ void thd_kernel(int n, int H, const int* __restrict__ harmonics, int B,
@@ -866,10 +1043,20 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     const DevNet net = devnet(h);
     const int nZ = net.nH - net.m;
     if (nZ < 1) return HPF_OK;
+    // variant 1: 32-scenario tile kernels; variant 2: one scenario per CTA (larger networks)
+    int variant = 1;
     if (harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, h->harm_warps,
-                             h->n_dev * (h->coupled ? h->H * h->H : h->H)) > (size_t)h->smem_optin)
-        return HPF_OK;
-    if (fund_tile_doubles_per_warp(net.n, net.Nf) * sizeof(double) > (size_t)h->smem_optin) return HPF_OK;
+                             h->n_dev * (h->coupled ? h->H * h->H : h->H)) > (size_t)h->smem_optin ||
+        fund_tile_doubles_per_warp(net.n, net.Nf) * sizeof(double) > (size_t)h->smem_optin)
+        variant = 2;
+    if (variant == 2) {
+        const int nx = (net.m - 1) + (net.m - net.c);
+        if (harm_cta_smem_bytes(net.n, net.H, net.m, net.c, net.q, net.N) > (size_t)h->smem_optin ||
+            nx > 32 * HPF_LU_MAXCHUNK || net.Nf > 32 * HPF_LU_MAXCHUNK ||
+            scn_smem_bytes(net.n, net.H, net.q, net.Nf, true) > (size_t)h->smem_optin ||
+            (size_t)net.q * net.H * HPF_T * sizeof(double2) + 16 > (size_t)h->smem_optin)
+            return HPF_OK;
+    }
     double2* AZF = nullptr;
     int* ipiv = nullptr;
     double* pr = nullptr;
@@ -896,7 +1083,7 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     if (e != cudaSuccess) return fail(h, HPF_E_CUDA, std::string("structured setup: ") + cudaGetErrorString(e));
     h->pivot_min = prh[0]; h->pivot_max = prh[1];
     // usable when the inversion met no zero pivot and the pivots span < 1e12 (well conditioned)
-    if (info == 0 && prh[0] > 0.0 && prh[1] / prh[0] < 1e12) h->struct_state = 1;
+    if (info == 0 && prh[0] > 0.0 && prh[1] / prh[0] < 1e12) h->struct_state = variant;
     return HPF_OK;
 }
 
@@ -946,6 +1133,18 @@ static int launch_harm_t(hpf_t* h, const DevNet& net, const StructNet& sn, const
 // every other network runs the runtime-dimension instance.
 static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const HarmTileArgs& ha,
                        bool persistent, cudaStream_t st) {
+    if (h->struct_state == 2) {
+        const size_t smem = harm_cta_smem_bytes(net.n, net.H, net.m, net.c, net.q, net.N);
+        int occ = 0;
+        int rc = prep_kernel(h, harm_cta_kernel, smem, "hpf_solve", &occ);
+        if (rc) return rc;
+        long long grid = ha.B;
+        if (persistent && grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
+        harm_cta_kernel<<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, sn, ha);
+        h->launches++;
+        CK(cudaGetLastError());
+        return HPF_OK;
+    }
     const bool two = 2 * harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, 8, sn.yn_elems) + 2048 <=
                      (size_t)h->smem_optin + 1024;
     if (!h->no_specialise) {
@@ -966,8 +1165,13 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
     const StructNet sn = structnet(h);
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     if (h->profiling) { CK(cudaEventRecord(h->ev[0], st)); }
-    // fundamental stage: one lane per scenario
-    {
+    // fundamental stage: one lane per scenario (variant 1) or the per-CTA kernel (variant 2)
+    if (h->struct_state == 2) {
+        int rc = solve_common(h, 1, B, P, Q, nullptr, thresh_f, max_f, 0.0, 0, 0, V_m, V_a, nullptr, n_iter_f,
+                              nullptr, nullptr, nullptr, status, nullptr, nullptr, st);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));     // solve_common used the counter
+    } else {
         const size_t per_warp = fund_tile_doubles_per_warp(net.n, net.Nf) * sizeof(double);
         int warps = 4;
         while (warps > 1 && per_warp * warps > (size_t)h->smem_optin / 2) warps >>= 1;
@@ -1200,7 +1404,7 @@ int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I
         CK(cudaSetDevice(h->device));
         rc = ensure_struct(h, (cudaStream_t)stream);
         if (rc) return rc;
-        if (h->struct_state == 1)
+        if (h->struct_state >= 1)
             return solve_structured(h, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags,
                                     V_m, V_a, I_inj, n_iter_f, n_iter_h, err_h, status, (cudaStream_t)stream);
     }
@@ -1214,7 +1418,7 @@ int hpf_struct_info(hpf_t* h, int* available, int* nZ, double* pivot_min, double
     CK(cudaSetDevice(h->device));
     rc = ensure_struct(h, nullptr);
     if (rc) return rc;
-    if (available) *available = h->struct_state == 1 ? 1 : 0;
+    if (available) *available = h->struct_state >= 1 ? h->struct_state : 0;
     if (nZ) *nZ = h->n * h->H - h->m;
     if (pivot_min) *pivot_min = h->pivot_min;
     if (pivot_max) *pivot_max = h->pivot_max;
@@ -1231,7 +1435,7 @@ int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const
     CK(cudaSetDevice(h->device));
     rc = ensure_struct(h, (cudaStream_t)stream);
     if (rc) return rc;
-    if (h->struct_state != 1)
+    if (h->struct_state < 1)
         return fail(h, HPF_E_UNSUPPORTED, "hpf_newton_step: structured strategy not available for this network");
     const DevNet net = devnet(h);
     const StructNet sn = structnet(h);

@@ -246,12 +246,12 @@ class BatchSolver:
         return float(ms[0]), float(ms[1])
 
     def struct_info(self):
-        """-> dict(available, nZ, pivot_min, pivot_max) of the structured strategy."""
+        """-> dict(available: 0 no / 1 tile kernels / 2 per-CTA kernel, nZ, pivot_min, pivot_max)."""
         av, nz = C.c_int(), C.c_int()
         pmin, pmax = C.c_double(), C.c_double()
         _lib.check(self._h, self.lib.hpf_struct_info(self._h, C.byref(av), C.byref(nz), C.byref(pmin),
                                                      C.byref(pmax)))
-        return dict(available=bool(av.value), nZ=nz.value, pivot_min=pmin.value, pivot_max=pmax.value)
+        return dict(available=int(av.value), nZ=nz.value, pivot_min=pmin.value, pivot_max=pmax.value)
 
     def newton_step(self, V_m, V_a, P, Q, I_N=None):
         """One structured Newton step: dx [N, B] with x_new = x - dx (hpf_newton_step)."""
