@@ -339,19 +339,28 @@ def run_ours(a):
     fp64_peak = None
     if rank == 0:
         def timed(fns, reps=12):
-            """Average device time of one launch: `reps` launches queued back to back between two
-            events (host launch overhead hidden behind the running kernels), rotating over
-            input/output sets whose total footprint exceeds the 126 MB L2."""
-            for fn in fns:
-                fn()
+            """Average device time of one launch: `reps` launches captured in ONE CUDA graph and
+            replayed between two events (no host launch overhead between the kernels: the Python
+            wrapper costs ~30 us per call, as much as the mismatch kernel itself), rotating over
+            input/output sets whose total footprint exceeds the 126 MB L2; best of 5 replays."""
+            side = torch.cuda.Stream()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                for fn in fns:
+                    fn()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g, stream=side):
+                    for r in range(reps):
+                        fns[r % len(fns)]()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            flush.fill_(1)
-            e0.record()
-            for r in range(reps):
-                fns[r % len(fns)]()
-            e1.record(); torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / reps
+            best = float("inf")
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                flush.fill_(1)
+                e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) / reps)
+            del g
+            return best
         raw = sol.solve(dP, dQ, dI, raw=True, max_iter_h=3, want_I_inj=False)   # a mid-iteration state
         Vm, Va = raw.V_m, raw.V_a
         nset = 3                                             # 3 x 124 MB of traffic per rotation
@@ -361,11 +370,11 @@ def run_ours(a):
         t_mis = timed([(lambda s_=s_: sol.mismatch(s_[0], s_[1], s_[2], s_[3], s_[4], out=s_[5])) for s_ in sets])
         del sets
         by_mis = 16 * n * H + 8 * N + 16 * q * H + 16 * (m - 1) + 8
-        kernels.append({"kernel": "mismatch_tile_kernel", "bound": "hbm (nominal); instruction issue in ncu",
+        kernels.append({"kernel": "mismatch_lane_kernel (one thread per scenario)", "bound": "hbm",
                         "ms": t_mis,
                         "achieved": by_mis * B / t_mis / 1e6, "peak": hbm_peak, "unit": "GB/s",
                         "frac": by_mis * B / t_mis / 1e6 / hbm_peak, "bytes_per_scenario": by_mis,
-                        "timing": "12 back-to-back launches over 3 rotating buffer sets (372 MB > L2)"})
+                        "timing": "CUDA graph of 12 launches over 3 rotating buffer sets (372 MB > L2), best of 5 replays"})
         Bj = min(B, 16384)
         Vmj, Vaj = Vm[:, :, :Bj].contiguous(), Va[:, :, :Bj].contiguous()
         Js = [sol.jacobian(Vmj, Vaj) for _ in range(2)]      # 2 x 1.35 GB outputs

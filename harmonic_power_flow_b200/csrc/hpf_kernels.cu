@@ -514,6 +514,8 @@ mismatch_tile_kernel(const DevNet net, const MismatchArgs a, const int yn_elems)
 #undef TA
 }
 
+#include "hpf_lane.cuh"
+
 // Fallback for networks whose 32-scenario tile does not fit in shared memory (e.g. net1 with
 // 26 harmonics): one scenario per CTA, same arithmetic (VS = 1), strided HBM access.
 __global__ void __launch_bounds__(HPF_THREADS)
@@ -898,6 +900,12 @@ struct hpf_handle {
     int harm_warps = 8;           // warps per 32-scenario tile of the harmonic kernel (8 or 16)
     int harm_minb = 1;
     int no_specialise = 0;        // $HPF_NO_SPECIALISE=1: always use the runtime-dimension kernels
+    int mismatch_tile = 0;        // $HPF_MISMATCH_TILE=1: standalone mismatch through the tile kernel
+    // host mirror of the network constants for kernels that take them as parameters
+    // (constant bank): fetched lazily from the device tables, see host_consts()
+    std::vector<double2> hY, hYN;
+    std::vector<int> hdev;
+    bool host_consts_valid = false;
     double pivot_min = 0.0, pivot_max = 0.0;
     int profiling = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -1208,6 +1216,41 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
     return HPF_OK;
 }
 
+// Host mirror of Y(h), Y_N and the device map (a few KB).  Y(h) is produced on the device
+// (ybus_kernel), so the FIRST call after a network change waits for the stream that built it.
+static int host_consts(hpf_t* h) {
+    if (h->host_consts_valid) return HPF_OK;
+    CK(cudaDeviceSynchronize());
+    const size_t ny = (size_t)h->H * h->n * h->n;
+    const size_t nyn = (size_t)h->n_dev * (h->coupled ? (size_t)h->H * h->H : (size_t)h->H);
+    h->hY.resize(ny);
+    h->hYN.resize(nyn);
+    h->hdev.resize((size_t)h->q);
+    CK(cudaMemcpy(h->hY.data(), h->d_Y, ny * sizeof(double2), cudaMemcpyDeviceToHost));
+    if (nyn && h->have_dev) CK(cudaMemcpy(h->hYN.data(), h->d_YN, nyn * sizeof(double2), cudaMemcpyDeviceToHost));
+    if (h->q && h->have_dev) CK(cudaMemcpy(h->hdev.data(), h->d_devof, (size_t)h->q * sizeof(int), cudaMemcpyDeviceToHost));
+    h->host_consts_valid = true;
+    return HPF_OK;
+}
+
+template <class D>
+static int launch_mismatch_lane(hpf_t* h, const MismatchArgs& a, cudaStream_t st) {
+    int rc = host_consts(h);
+    if (rc) return rc;
+    static_assert(sizeof(LaneConsts<D>) + sizeof(MismatchArgs) <= 32000, "kernel parameter space");
+    LaneConsts<D> C;
+    memset(&C, 0, sizeof(C));
+    for (int t = 0; t < D::H * D::n * D::n; ++t) C.Y[t] = h->hY[t];
+    const int per = h->coupled ? D::H * D::H : D::H;
+    for (int k = 0; k < D::q; ++k)
+        for (int t = 0; t < per; ++t) C.YNk[k * per + t] = h->hYN[(size_t)h->hdev[k] * per + t];
+    const int threads = HPF_LANE_THREADS;
+    const unsigned grid = (unsigned)(((long long)a.B + threads - 1) / threads);
+    if (h->coupled) mismatch_lane_kernel<D, true><<<grid, threads, 0, st>>>(C, a);
+    else mismatch_lane_kernel<D, false><<<grid, threads, 0, st>>>(C, a);
+    return HPF_OK;
+}
+
 extern "C" {
 
 int hpf_abi_version(void) { return HPF_ABI_VERSION; }
@@ -1240,6 +1283,7 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_HARM_WARPS")) h->harm_warps = (atoi(ev) == 16) ? 16 : 8;
     if (const char* ev = getenv("HPF_HARM_MINB")) h->harm_minb = (atoi(ev) == 2) ? 2 : 1;
     if (const char* ev = getenv("HPF_NO_SPECIALISE")) h->no_specialise = atoi(ev) ? 1 : 0;
+    if (const char* ev = getenv("HPF_MISMATCH_TILE")) h->mismatch_tile = atoi(ev) ? 1 : 0;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     e = cudaMalloc((void**)&h->d_counter, sizeof(int));
@@ -1293,6 +1337,7 @@ int hpf_set_network(hpf_t* h, int n, int m, int c, int H, const int* harmonics, 
     h->have_Y = false;
     h->have_dev = false;
     h->struct_state = 0;
+    h->host_consts_valid = false;
     return HPF_OK;
 }
 
@@ -1312,6 +1357,7 @@ int hpf_set_devices(hpf_t* h, int n_dev, int coupled, const double* Y_N, const i
     CK(upload(&h->d_devof, dev_of_nl_bus, (size_t)h->q));
     h->have_dev = true;
     h->struct_state = 0;
+    h->host_consts_valid = false;
     return HPF_OK;
 }
 
@@ -1330,6 +1376,7 @@ int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
                            cudaMemcpyDeviceToDevice, st));
     h->have_Y = true;
     h->struct_state = 0;
+    h->host_consts_valid = false;
     return HPF_OK;
 }
 
@@ -1341,6 +1388,7 @@ int hpf_set_Y(hpf_t* h, const double* Y) {
     CK(cudaMemcpy(h->d_Y, Y, (size_t)h->H * h->n * h->n * sizeof(double2), cudaMemcpyHostToDevice));
     h->have_Y = true;
     h->struct_state = 0;
+    h->host_consts_valid = false;
     return HPF_OK;
 }
 
@@ -1546,7 +1594,14 @@ int hpf_mismatch(hpf_t* h, int B, const double* V_m, const double* V_a, const do
     const int yn_elems = h->n_dev * (h->coupled ? h->H * h->H : h->H);
     size_t smem = tile_smem_bytes(net.n, net.H, net.q, net.m, yn_elems);
     int occ = 0;
-    if (smem <= (size_t)h->smem_optin) {
+    const bool lane_ok = !h->no_specialise && !h->mismatch_tile;
+    if (lane_ok && net.n == 4 && net.m == 3 && net.c == 2 && net.H == 13 && net.q == 1) {
+        rc = launch_mismatch_lane<Dims<4, 3, 2, 13, 1>>(h, a, (cudaStream_t)stream);
+        if (rc) return rc;
+    } else if (lane_ok && net.n == 4 && net.m == 2 && net.c == 1 && net.H == 10 && net.q == 2) {
+        rc = launch_mismatch_lane<Dims<4, 2, 1, 10, 2>>(h, a, (cudaStream_t)stream);
+        if (rc) return rc;
+    } else if (smem <= (size_t)h->smem_optin) {
         const long long tiles = ((long long)B + HPF_TILE - 1) / HPF_TILE;
         auto launch = [&](auto kernel) -> int {
             int rc2 = prep_kernel(h, kernel, smem, "hpf_mismatch", &occ);

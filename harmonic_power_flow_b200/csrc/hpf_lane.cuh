@@ -1,0 +1,295 @@
+// Standalone mismatch kernel (kernel 2), "lane" variant: ONE THREAD PER SCENARIO, the whole
+// row set of harmonic_mismatch() (HG:360-390) streamed harmonic by harmonic through registers.
+//
+// Why: the 32-scenario tile kernel (mismatch_tile_kernel) spreads the rows of a scenario over
+// 8 warps, so every operand of every complex MAC is a shared-memory load and the kernel ends
+// up bound by instruction issue (ncu: 11.8 k instructions per scenario, 30 % of them FP64).
+// Here a thread owns its scenario: the phasors of the nonlinear buses stay in registers for
+// the Norton contraction (HG:313-323), the phasors of one harmonic are live for the Y(h) V
+// rows of that harmonic only (HG:335-354,372-380), and every network constant is a
+// constant-bank operand of the FP64 instruction itself (kernel parameter space,
+// __grid_constant__): no shared memory, no barrier, no load instruction for Y(h) / Y_N.
+// HBM traffic is unchanged: batch-innermost arrays, a warp touches 32 consecutive scenarios,
+// every global access is one 256-byte (f64) or 512-byte (c128) segment.
+//
+// Only shape-specialised instances exist (register arrays need compile-time extents); other
+// networks use the tile kernel.
+#pragma once
+#include <type_traits>
+#include "hpf_device.cuh"
+
+// sin / cos with the network's phasor angles: Cody-Waite reduction by pi/2 in three parts and
+// the classic degree-13 / degree-14 minimax polynomials on [-pi/4, pi/4] (fdlibm's
+// coefficients), error < 1 ulp.  Coefficients are constant-bank operands (the library
+// routine materialises them as immediates, two extra issue slots per coefficient).  Beyond
+// |x| >= 105615 the three-part reduction loses accuracy: the library routine is called.
+__constant__ double HPF_SC[20] = {
+    6.36619772367581382433e-01,   // 0  2/pi
+    6755399441055744.0,           // 1  1.5 * 2^52 (round-to-nearest-integer by addition)
+    1.57079632679489655800e+00,   // 2  pi/2 hi
+    6.12323399573676603587e-17,   // 3  pi/2 mid
+    -1.49738490485916983169e-33,  // 4  pi/2 lo (pi/2 - hi - mid)
+    -1.66666666666666324348e-01,  // 5  S1
+    8.33333333332248946124e-03,   // 6  S2
+    -1.98412698298579493134e-04,  // 7  S3
+    2.75573137070700676789e-06,   // 8  S4
+    -2.50507602534068634195e-08,  // 9  S5
+    1.58969099521155010221e-10,   // 10 S6
+    4.16666666666666019037e-02,   // 11 C1
+    -1.38888888888741095749e-03,  // 12 C2
+    2.48015872894767294178e-05,   // 13 C3
+    -2.75573143513906633035e-07,  // 14 C4
+    2.08757232129817482790e-09,   // 15 C5
+    -1.13596475577881948265e-11,  // 16 C6
+    105615.0,                     // 17 fast-path bound
+    0.0, 0.0};
+
+__device__ __noinline__ double2 sincos_slow(double x) {
+    double s, c;
+    sincos(x, &s, &c);
+    return make_double2(s, c);
+}
+
+// Branch-free fast path (valid for |x| < 105615; garbage-in-garbage-out beyond, NaN for NaN).
+__device__ __forceinline__ void sincos_core(const double x, double& sn, double& cs) {
+    const double t = fma(x, HPF_SC[0], HPF_SC[1]);
+    const int k = __double2loint(t);
+    const double qd = t - HPF_SC[1];
+    double r = fma(-qd, HPF_SC[2], x);
+    r = fma(-qd, HPF_SC[3], r);
+    r = fma(-qd, HPF_SC[4], r);
+    const double z = r * r;
+    double ps = fma(z, HPF_SC[10], HPF_SC[9]);
+    double pc = fma(z, HPF_SC[16], HPF_SC[15]);
+    ps = fma(z, ps, HPF_SC[8]);
+    pc = fma(z, pc, HPF_SC[14]);
+    ps = fma(z, ps, HPF_SC[7]);
+    pc = fma(z, pc, HPF_SC[13]);
+    ps = fma(z, ps, HPF_SC[6]);
+    pc = fma(z, pc, HPF_SC[12]);
+    ps = fma(z, ps, HPF_SC[5]);
+    pc = fma(z, pc, HPF_SC[11]);
+    const double s0 = fma(z * r, ps, r);                  // r + r^3 (S1 + z S2 + ...)
+    const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));  // 1 - z/2 + z^2 (C1 + z C2 + ...)
+    const bool swap = (k & 1) != 0;
+    const double a = swap ? c0 : s0;                      // sin(x) up to sign
+    const double b = swap ? s0 : c0;                      // cos(x) up to sign
+    // signs by integer XOR on the high word (keeps the FP64 pipe free)
+    sn = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
+    cs = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
+}
+
+// N independent sin/cos pairs: all fast paths first (independent dependency chains that the
+// scheduler interleaves), one rare fix-up branch for large arguments afterwards.
+template <int N>
+__device__ __forceinline__ void sincos_group(const double* x, double* sn, double* cs) {
+    bool big = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        sincos_core(x[i], sn[i], cs[i]);
+        big |= (fabs(x[i]) >= HPF_SC[17]);                // also +-Inf; NaN propagates through the core
+    }
+    if (big) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (fabs(x[i]) >= HPF_SC[17]) {
+                const double2 r2 = sincos_slow(x[i]);
+                sn[i] = r2.x;
+                cs[i] = r2.y;
+            }
+    }
+}
+
+// NaN-propagating running maximum of |v| on the INTEGER pipe: for sign-cleared IEEE doubles the
+// bit patterns order like the magnitudes, and every NaN pattern is above +Inf, so an integer
+// max keeps a NaN once it has seen one (numpy's norm(inf) / max do the same, HG:389).
+__device__ __forceinline__ void absmax_bits(long long& mxb, const double v) {
+    // (inline PTX: written as an AND on the 64-bit pattern the compiler turns the mask into an
+    // FP64 |v| = DADD, which is not bit-preserving for NaN and occupies the FP64 pipe)
+    long long bits;
+    asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tand.b32 hi, hi, 0x7fffffff;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}" : "=l"(bits) : "d"(v));
+    mxb = bits > mxb ? bits : mxb;
+}
+
+// Network constants of a shape-specialised instance, passed BY VALUE as a kernel parameter
+// (constant bank 0): Y(h) [H][n][n] and the Norton admittances pre-gathered per nonlinear
+// bus, YNk [q][H][H] (coupled) or [q][H] in the first q*H entries (uncoupled).
+template <class D>
+struct LaneConsts {
+    double2 Y[D::H * D::n * D::n];
+    double2 YNk[D::q * D::H * D::H];
+};
+
+#define HPF_LANE_THREADS 64
+#define HPF_LANE_STAGES 4
+
+__device__ __forceinline__ void lane_cp_async8(double* sdst, const double* gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void lane_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void lane_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+template <class D, bool COUPLED>
+__global__ void __launch_bounds__(HPF_LANE_THREADS, 7)
+mismatch_lane_kernel(const __grid_constant__ LaneConsts<D> C, const MismatchArgs a) {
+    constexpr int n = D::n, m = D::m, c = D::c, H = D::H, q = D::q, nH = n * H;
+    // phasors of the nonlinear buses, one column per thread: read back with a RUNTIME harmonic
+    // index inside the rolled harmonic loop (the register copy needs compile-time indices)
+    __shared__ double2 sVnl[q * H][HPF_LANE_THREADS];
+    __shared__ double ring[HPF_LANE_STAGES][2 * m + 2 * q][HPF_LANE_THREADS];
+    const size_t B = (size_t)a.B;
+    const size_t b0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b0 >= B) return;                                 // no barrier in this kernel: spare lanes just leave
+    const size_t b = b0;
+    const size_t nB = (size_t)n * B;
+
+    // Input ring: the raw state (V_m, V_a of the linear buses, I_N of the nonlinear ones) of the
+    // next HPF_LANE_STAGES harmonics is kept in flight with asynchronous global->shared copies
+    // (LDGSTS, one column per thread, no register cost).  With one prefetched harmonic in
+    // registers a single resident wave (65,536 scenarios = 14 warps per SM) cannot cover the
+    // HBM latency: all warps are in the same phase at the same time.
+    const double* pvm = a.V_m + b;                       // row (h + STAGES) n of V_m / V_a (next to request)
+    const double* pva = a.V_a + b;
+    const double2* pin = a.I_N + b;
+    double2* pij = a.I_inj ? a.I_inj + b : nullptr;
+    auto request = [&](const int stage) {
+        double* slot = &ring[stage][0][threadIdx.x];
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+            lane_cp_async8(slot + (2 * j) * HPF_LANE_THREADS, pvm + (size_t)j * B);
+            lane_cp_async8(slot + (2 * j + 1) * HPF_LANE_THREADS, pva + (size_t)j * B);
+        }
+#pragma unroll
+        for (int k = 0; k < q; ++k) {
+            const double* src = reinterpret_cast<const double*>(pin + (size_t)(k * H) * B);
+            lane_cp_async8(slot + (2 * m + 2 * k) * HPF_LANE_THREADS, src);
+            lane_cp_async8(slot + (2 * m + 2 * k + 1) * HPF_LANE_THREADS, src + 1);
+        }
+        pvm += nB;
+        pva += nB;
+        pin += B;
+    };
+#pragma unroll
+    for (int st = 0; st < HPF_LANE_STAGES; ++st) {
+        if (st < H) request(st);
+        lane_cp_async_commit();
+    }
+    double Pl[m], Ql[m];
+#pragma unroll
+    for (int i = 1; i < m; ++i) {
+        Pl[i] = __ldcs(a.P + (size_t)i * B + b);
+        Ql[i] = __ldcs(a.Q + (size_t)i * B + b);
+    }
+
+    // ---- pass 1: phasors of the nonlinear buses at every harmonic (registers + smem) ----
+    double2 Vnl[q][H];
+#pragma unroll
+    for (int k = 0; k < q; ++k) {
+        double rm[H], ra[H], sn[H], cs[H];
+        const double* pm = a.V_m + (size_t)(m + k) * B + b;
+        const double* pa = a.V_a + (size_t)(m + k) * B + b;
+#pragma unroll
+        for (int p = 0; p < H; ++p) {
+            rm[p] = __ldcs(pm);
+            ra[p] = __ldcs(pa);
+            pm += nB;
+            pa += nB;
+        }
+        constexpr int G4 = 4;
+#pragma unroll
+        for (int p0 = 0; p0 < H; p0 += G4) {
+            if (p0 + G4 <= H) sincos_group<G4>(ra + p0, sn + p0, cs + p0);
+            else sincos_group<(H % G4) ? (H % G4) : G4>(ra + p0, sn + p0, cs + p0);
+        }
+#pragma unroll
+        for (int p = 0; p < H; ++p) {
+            Vnl[k][p] = make_double2(rm[p] * cs[p], rm[p] * sn[p]);
+            sVnl[k * H + p][threadIdx.x] = Vnl[k][p];
+        }
+    }
+
+    long long mxb = 0;
+    double* pf = a.f + b;                                // row e of f (real parts), advanced row by row
+    double* pfi = pf + (size_t)((nH - 1) - (c - 1)) * B; // row of the imaginary part of entry e (HG:388)
+
+    // ---- pass 2: harmonic by harmonic (the h >= 1 blocks are ONE rolled loop: fully unrolled
+    //      the kernel is 120 KB of straight-line code and starves on instruction fetch); the
+    //      raw state of harmonic h+1 is in flight while harmonic h is computed ----
+    auto harmonic = [&](auto first_tag, const int h) {
+        constexpr bool FIRST = decltype(first_tag)::value;
+        double cm[m], ca[m];
+        double2 cin[q];
+        lane_cp_async_wait<HPF_LANE_STAGES - 1>();        // the group of harmonic h has landed
+        {
+            const int stage = h % HPF_LANE_STAGES;
+            const double* slot = &ring[stage][0][threadIdx.x];
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                cm[j] = slot[(2 * j) * HPF_LANE_THREADS];
+                ca[j] = slot[(2 * j + 1) * HPF_LANE_THREADS];
+            }
+#pragma unroll
+            for (int k = 0; k < q; ++k)
+                cin[k] = make_double2(slot[(2 * m + 2 * k) * HPF_LANE_THREADS],
+                                      slot[(2 * m + 2 * k + 1) * HPF_LANE_THREADS]);
+            if (h + HPF_LANE_STAGES < H) request(stage);  // refill the slot just consumed
+            lane_cp_async_commit();                       // (possibly empty: keeps the group count uniform)
+        }
+        double2 V[n];
+        {
+            double sn[m], cs[m];
+            sincos_group<m>(ca, sn, cs);
+#pragma unroll
+            for (int j = 0; j < m; ++j) V[j] = make_double2(cm[j] * cs[j], cm[j] * sn[j]);
+        }
+#pragma unroll
+        for (int k = 0; k < q; ++k) V[m + k] = FIRST ? Vnl[k][0] : sVnl[k * H + h][threadIdx.x];
+        const double2* Yh = C.Y + h * (n * n);
+        // rows of this harmonic, bus order
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            if (FIRST && i == 0) continue;                               // slack: no row
+            double2 f = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < n; ++j) f = cfma(f, Yh[i * n + j], V[j]);
+            if (i < m) {
+                if (FIRST) {                                             // dS = (P + jQ) + V conj(Y1 V)  (HG:372-380)
+                    const double2 sl = cmul(V[i], cconj(f));
+                    f = make_double2(Pl[i] + sl.x, Ql[i] + sl.y);
+                }
+            } else {
+                // nonlinear bus: (Y_h V_h)_i + I_N - sum_p Y_N[h][p] V_p,i   (HG:313-323,335-354)
+                const int k = i - m;
+                double2 acc;
+                if (COUPLED) {
+                    const double2* row = C.YNk + (k * H + h) * H;
+                    acc = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int p = 0; p < H; ++p) acc = cfma(acc, row[p], Vnl[k][p]);
+                } else {
+                    acc = cmul(C.YNk[k * H + h], V[i]);
+                }
+                const double2 inj = csub(cin[k], acc);
+                if (pij) __stcs(pij + (size_t)(k * H) * B, inj);
+                f = cadd(f, inj);
+            }
+            // emit row e = h n + i - 1 (rows are produced in order)
+            __stcs(pf, f.x);
+            absmax_bits(mxb, f.x);
+            if (!FIRST || i - 1 >= c - 1) {
+                __stcs(pfi, f.y);
+                absmax_bits(mxb, f.y);
+            }
+            pf += B;
+            pfi += B;
+        }
+        if (pij) pij += B;
+    };
+    harmonic(std::true_type{}, 0);
+#pragma unroll 1
+    for (int h = 1; h < H; ++h) harmonic(std::false_type{}, h);
+    a.err[b] = __longlong_as_double(mxb);
+}
