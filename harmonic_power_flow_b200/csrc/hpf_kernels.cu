@@ -19,6 +19,7 @@
 #include "../../include/hpf_b200.h"
 #include "hpf_device.cuh"
 #include "hpf_structured.cuh"
+#include "hpf_lu_blocked.cuh"
 
 #define HPF_THREADS 256
 #define HPF_TILE 32          // scenarios per CTA in the tile kernels
@@ -229,16 +230,25 @@ struct SolveArgs {
     double* workspace;     // GMEM variant: gridDim.x * ld * (N + 1) doubles
 };
 
-#define HPF_THREADS_GMEM 1024
+#define HPF_THREADS_GMEM 512
+// GMEM kernels: the matrix lives in a per-CTA global workspace with leading dimension
+// lub_ld(N); the blocked LU's staging buffers follow the scenario state in shared memory.
+__host__ __device__ inline size_t scn_smem_doubles_aligned(int n, int H, int q, int N) {
+    return (scn_smem_bytes(n, H, q, N, false) + 15) / 16 * 2;
+}
+__host__ __device__ inline size_t gmem_kernel_smem_bytes(int n, int H, int q, int N) {
+    return (scn_smem_doubles_aligned(n, H, q, N) + LUB_SMEM_DOUBLES) * sizeof(double) + 16;
+}
 template <bool GMEM>
 __global__ void __launch_bounds__(GMEM ? HPF_THREADS_GMEM : HPF_THREADS)
 solve_kernel(const DevNet net, const SolveArgs a) {
     extern __shared__ __align__(16) double smem[];
     ScnSmem s = carve(smem, net, !GMEM);
-    if (GMEM) s.A = a.workspace + (size_t)blockIdx.x * odd_ld(net.N) * (net.N + 1);
     const int tid = threadIdx.x;
     const int n = net.n, c = net.c, nH = net.nH, N = net.N, Nf = net.Nf, H = net.H, q = net.q;
-    const int ld = odd_ld(N);
+    const int ld = GMEM ? lub_ld(N) : odd_ld(N);
+    if (GMEM) s.A = a.workspace + (size_t)blockIdx.x * ld * (N + 1);
+    double* lub = smem + scn_smem_doubles_aligned(n, H, q, N);      // GMEM only
     const size_t B = (size_t)a.B;
 
     for (;;) {
@@ -271,7 +281,7 @@ solve_kernel(const DevNet net, const SolveArgs a) {
             cta_zero(s.A, (size_t)ld * Nf);
             __syncthreads();
             cta_fund_jacobian(net, s, s.A, 1, ld);
-            const int info = GMEM ? lu_solve_any(s.A, Nf, ld, s.rinv, s.flag, s.red)
+            const int info = GMEM ? lu_solve_blocked(s.A, Nf, ld, lub, s.flag)
                                   : lu_solve_smem(s.A, Nf, ld, s.rinv, s.flag);
             if (info) status = HPF_ST_SINGULAR;
             for (int t = tid; t < Nf; t += blockDim.x) {       // HG:226-235
@@ -311,7 +321,7 @@ solve_kernel(const DevNet net, const SolveArgs a) {
             cta_zero(s.A, (size_t)ld * N);
             __syncthreads();
             cta_harmonic_jacobian(net, s, s.A, 1, ld);
-            const int info = GMEM ? lu_solve_any(s.A, N, ld, s.rinv, s.flag, s.red)
+            const int info = GMEM ? lu_solve_blocked(s.A, N, ld, lub, s.flag)
                                   : lu_solve_smem(s.A, N, ld, s.rinv, s.flag);
             if (info && status == HPF_ST_CONVERGED) status = HPF_ST_SINGULAR;
             for (int t = tid; t < N; t += blockDim.x) {        // HG:476-485
@@ -659,8 +669,9 @@ __global__ void __launch_bounds__(GMEM ? HPF_THREADS_GMEM : HPF_THREADS)
 lu_solve_kernel(const DevNet net, const LuArgs a) {
     extern __shared__ __align__(16) double smem[];
     ScnSmem s = carve(smem, net, !GMEM);
-    if (GMEM) s.A = a.workspace + (size_t)blockIdx.x * odd_ld(net.N) * (net.N + 1);
-    const int N = net.N, ld = odd_ld(N);
+    const int N = net.N, ld = GMEM ? lub_ld(N) : odd_ld(N);
+    if (GMEM) s.A = a.workspace + (size_t)blockIdx.x * ld * (N + 1);
+    double* lub = smem + scn_smem_doubles_aligned(net.n, net.H, net.q, N);   // GMEM only
     const size_t B = (size_t)a.B;
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         __syncthreads();
@@ -671,7 +682,7 @@ lu_solve_kernel(const DevNet net, const LuArgs a) {
         }
         double* rhs = s.A + (size_t)N * ld;
         for (int t = threadIdx.x; t < N; t += blockDim.x) rhs[t] = a.f[t * B + b];
-        const int info = GMEM ? lu_solve_any(s.A, N, ld, s.rinv, s.flag, s.red)
+        const int info = GMEM ? lu_solve_blocked(s.A, N, ld, lub, s.flag)
                               : lu_solve_smem(s.A, N, ld, s.rinv, s.flag);
         for (int t = threadIdx.x; t < N; t += blockDim.x) a.dx[t * B + b] = rhs[t];
         if (threadIdx.x == 0) a.info[b] = info;
@@ -1003,7 +1014,8 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     DevNet net = devnet(h);
     if (mode == 1) net.N = net.Nf;      // fundamental only: size the matrix for Nf
     const bool gm = !fits_smem_lu(h, net);
-    const size_t smem = scn_smem_bytes(net.n, net.H, net.q, net.N, !gm);
+    const size_t smem = gm ? gmem_kernel_smem_bytes(net.n, net.H, net.q, net.N)
+                           : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
     int occ = 0;
     rc = gm ? prep_kernel(h, solve_kernel<true>, smem, who, &occ, HPF_THREADS_GMEM)
             : prep_kernel(h, solve_kernel<false>, smem, who, &occ);
@@ -1020,7 +1032,7 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     if (grid > B) grid = B;
     a.workspace = nullptr;
     if (gm) {
-        rc = ensure_workspace(h, (size_t)grid * odd_ld(net.N) * (net.N + 1));
+        rc = ensure_workspace(h, (size_t)grid * lub_ld(net.N) * (net.N + 1));
         if (rc) return rc;
         a.workspace = h->d_work;
     }
@@ -1675,7 +1687,8 @@ int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, 
     LuArgs a;
     a.B = B; a.J = J; a.f = f; a.dx = dx; a.info = info; a.stride = hpf_jacobian_stride(h);
     const bool gm = !fits_smem_lu(h, net);
-    const size_t smem = scn_smem_bytes(net.n, net.H, net.q, net.N, !gm);
+    const size_t smem = gm ? gmem_kernel_smem_bytes(net.n, net.H, net.q, net.N)
+                           : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
     int occ = 0;
     rc = gm ? prep_kernel(h, lu_solve_kernel<true>, smem, "hpf_lu_solve", &occ, HPF_THREADS_GMEM)
             : prep_kernel(h, lu_solve_kernel<false>, smem, "hpf_lu_solve", &occ);
@@ -1684,7 +1697,7 @@ int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, 
     if (grid > B) grid = B;
     a.workspace = nullptr;
     if (gm) {
-        rc = ensure_workspace(h, (size_t)grid * odd_ld(net.N) * (net.N + 1));
+        rc = ensure_workspace(h, (size_t)grid * lub_ld(net.N) * (net.N + 1));
         if (rc) return rc;
         a.workspace = h->d_work;
         lu_solve_kernel<true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, (cudaStream_t)stream>>>(net, a);

@@ -1,0 +1,264 @@
+// Blocked dense LU with partial pivoting + solve for systems that do not fit shared memory
+// (N > 192): the linear algebra of HG:229 / HG:476-479 for the large networks (net1 dense
+// path, the border system and the fundamental stage of the 200- / 1000-bus configurations).
+//
+// One CTA factorises one augmented matrix [A | b] that lives in GLOBAL memory (L2 resident or
+// streamed), column-major, leading dimension ld (a multiple of 2 so that two consecutive rows
+// of a column are one aligned 16-byte word).  Right-looking, panel width 32:
+//   1. panel: unblocked elimination with partial pivoting inside the 32 columns (one thread
+//      per row, the pivot search of column j+1 is fused into the update of column j);
+//   2. the 32 row interchanges and the triangular solve with L11 for every column to the
+//      right (one thread per column, 32 values in registers, L11 broadcast from smem);
+//   3. trailing update A22 -= L21 U12 on the FP64 TENSOR CORES (mma.sync m8n8k4 DMMA): L21 and
+//      U12 slices are staged in shared memory (conflict-free padded strides), every warp owns
+//      32 x 32 sub-tiles = 4 x 4 DMMA tiles, accumulators in registers, the trailing matrix is
+//      read-modified-written once per panel with 16-byte accesses.  The product is formed
+//      TRANSPOSED (D[c][r] = sum_k U12[k][c] L21[r][k]) so that the row-major C fragment of the
+//      instruction maps onto two consecutive rows of a column of the column-major matrix.
+//      Why tensor cores here: a register-tiled FMA update needs 8 shared-memory operand loads
+//      per 16 FMAs (4 x 4 tile), the DMMA path 8 fragment loads per 16 x 256 MACs, and the
+//      DMMA pipe has twice the FMA pipe's FP64 rate on this part.
+//   4. blocked back substitution (32 x 32 diagonal blocks solved by one warp).
+// L is not kept (the right-hand side is carried as column N), so columns left of the panel
+// are never touched again.  Returns 0 or k+1 for a zero / non-finite pivot at step k, like
+// lu_solve_smem.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#define LUB_NB 32
+#define LUB_TR 256                 // matrix rows per staged slice
+#define LUB_TC 128                 // matrix columns per staged slice
+#define LUB_SL (LUB_TR + 4)        // smem stride of L21^T  [k][r]   (stride mod 16 == 4)
+#define LUB_SU (LUB_NB + 4)        // smem stride of U12^T  [c][k]   (stride mod 16 == 4)
+#define LUB_SMEM_DOUBLES (LUB_NB * (LUB_NB + 1) + LUB_NB * LUB_SL + LUB_TC * LUB_SU + 2 * LUB_NB + 80)
+
+__host__ __device__ inline int lub_ld(int N) { return (N + 7) & ~7; }
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// block-wide argmax of (value, index) with idamax tie-breaking (first maximal |a|)
+__device__ __forceinline__ void lub_argmax(double& best, int& bi, double* redv, int* redi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        best = (lane < nw) ? redv[lane] : -1.0;
+        bi = (lane < nw) ? redi[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { redv[32] = best; redi[32] = bi; }
+    }
+    __syncthreads();
+    best = redv[32];
+    bi = redi[32];
+}
+
+// A: N x (N+1) column-major in global memory, ld even; sm: >= LUB_SMEM_DOUBLES doubles of
+// SHARED memory; sflag: one int of shared memory.
+__device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N, const int ld,
+                                             double* sm, int* sflag) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
+    double* L11 = sm;                                   // [NB][NB+1]  L11[r][c]
+    double* Ls = L11 + LUB_NB * (LUB_NB + 1);           // [NB][SL]    Ls[k][r] = L21[r][k]
+    double* Us = Ls + LUB_NB * LUB_SL;                  // [TC][SU]    Us[c][k] = -U12[k][c]
+    double* redv = Us + LUB_TC * LUB_SU;                // 33
+    int* redi = reinterpret_cast<int*>(redv + 34);      // 33 ints
+    int* piv = redi + 34;                               // NB ints
+    if (tid == 0) *sflag = 0;
+    __syncthreads();
+
+    for (int k0 = 0; k0 < N; k0 += LUB_NB) {
+        const int nb = min(LUB_NB, N - k0);
+        // ---------------- 1. panel ----------------
+        {
+            // pivot of the first column
+            double best = -1.0;
+            int bi = k0;
+            for (int i = k0 + tid; i < N; i += nthr) {
+                const double v = fabs(A[(size_t)k0 * ld + i]);
+                if (v > best) { best = v; bi = i; }
+            }
+            lub_argmax(best, bi, redv, redi);
+            for (int j = 0; j < nb; ++j) {
+                const int kc = k0 + j;
+                const int p = bi;
+                if (!(best > 0.0) || !(best < CUDART_INF)) {
+                    if (tid == 0 && *sflag == 0) *sflag = kc + 1;
+                }
+                if (tid == 0) piv[j] = p;
+                if (p != kc && tid < nb) {                      // swap inside the panel
+                    double* c0 = A + (size_t)(k0 + tid) * ld;
+                    const double t = c0[kc];
+                    c0[kc] = c0[p];
+                    c0[p] = t;
+                }
+                __syncthreads();
+                const double r = 1.0 / A[(size_t)kc * ld + kc];
+                // scale column kc, rank-1 update of the panel columns to its right; the new
+                // column kc+1 feeds the next pivot search
+                best = -1.0;
+                bi = kc + 1;
+                for (int i = kc + 1 + tid; i < N; i += nthr) {
+                    const double l = A[(size_t)kc * ld + i] * r;
+                    A[(size_t)kc * ld + i] = l;
+                    for (int jj = j + 1; jj < nb; ++jj) {
+                        double* cj = A + (size_t)(k0 + jj) * ld;
+                        const double v = cj[i] - l * cj[kc];
+                        cj[i] = v;
+                        if (jj == j + 1) {
+                            const double av = fabs(v);
+                            if (av > best) { best = av; bi = i; }
+                        }
+                    }
+                }
+                if (j + 1 < nb) lub_argmax(best, bi, redv, redi);   // (contains the barriers)
+                else __syncthreads();
+            }
+        }
+        const int cr = k0 + nb;                                  // first row / column of the trailing part
+        if (cr > N) break;
+        // L11 -> smem
+        for (int t = tid; t < nb * nb; t += nthr) {
+            const int c = t / nb, r = t - c * nb;
+            L11[r * (LUB_NB + 1) + c] = A[(size_t)(k0 + c) * ld + k0 + r];
+        }
+        __syncthreads();
+        // ---------------- 2. interchanges + U12 = L11^{-1} A12 (incl. the rhs column N) ----------------
+        for (int c = cr + tid; c <= N; c += nthr) {
+            double* col = A + (size_t)c * ld;
+            for (int t = 0; t < nb; ++t) {
+                const int p = piv[t];
+                if (p != k0 + t) {
+                    const double x = col[k0 + t];
+                    col[k0 + t] = col[p];
+                    col[p] = x;
+                }
+            }
+            double v[LUB_NB];
+#pragma unroll
+            for (int t = 0; t < LUB_NB; ++t) v[t] = (t < nb) ? col[k0 + t] : 0.0;
+#pragma unroll
+            for (int t = 1; t < LUB_NB; ++t) {
+                double acc = v[t];
+#pragma unroll
+                for (int s2 = 0; s2 < t; ++s2) acc = fma(-L11[t * (LUB_NB + 1) + s2], v[s2], acc);
+                v[t] = (t < nb) ? acc : 0.0;
+            }
+#pragma unroll
+            for (int t = 1; t < LUB_NB; ++t)
+                if (t < nb) col[k0 + t] = v[t];
+        }
+        __syncthreads();
+        if (cr >= N) break;                                      // nothing below the panel
+        // ---------------- 3. trailing update on the tensor cores ----------------
+        for (int r0 = cr; r0 < N; r0 += LUB_TR) {
+            // L21 slice: Ls[k][r] = A[r0 + r][k0 + k]
+            for (int t = tid; t < LUB_NB * LUB_TR; t += nthr) {
+                const int k = t / LUB_TR, r = t - k * LUB_TR;
+                Ls[k * LUB_SL + r] = (k < nb && r0 + r < N) ? A[(size_t)(k0 + k) * ld + r0 + r] : 0.0;
+            }
+            for (int c0 = cr; c0 <= N; c0 += LUB_TC) {
+                __syncthreads();                                 // previous Us consumers done (and Ls visible)
+                for (int t = tid; t < LUB_TC * LUB_NB; t += nthr) {
+                    const int c = t / LUB_NB, k = t - c * LUB_NB;
+                    Us[c * LUB_SU + k] = (k < nb && c0 + c <= N) ? -A[(size_t)(c0 + c) * ld + k0 + k] : 0.0;
+                }
+                __syncthreads();
+                constexpr int SUBR = LUB_TR / 32, SUBC = LUB_TC / 32;
+                for (int st = warp; st < SUBR * SUBC; st += nw) {
+                    const int sc = st / SUBR, sr = st - sc * SUBR;
+                    const int cb = c0 + sc * 32, rb = r0 + sr * 32;
+                    if (cb > N || rb >= N) continue;
+                    const int fr = lane >> 2, fk = lane & 3;     // fragment row / k index
+                    double acc[4][4][2];
+                    // C fragment: D[c = cb + 8 ic + fr][r = rb + 8 ir + 2 fk + {0,1}]
+#pragma unroll
+                    for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                        for (int ir = 0; ir < 4; ++ir) {
+                            const int c = cb + 8 * ic + fr, r = rb + 8 * ir + 2 * fk;
+                            if (c <= N && r + 1 < N) {
+                                const double2 v2 = *reinterpret_cast<const double2*>(A + (size_t)c * ld + r);
+                                acc[ic][ir][0] = v2.x; acc[ic][ir][1] = v2.y;
+                            } else {
+                                acc[ic][ir][0] = (c <= N && r < N) ? A[(size_t)c * ld + r] : 0.0;
+                                acc[ic][ir][1] = 0.0;
+                            }
+                        }
+                    const double* us = Us + (sc * 32 + fr) * LUB_SU + fk;
+                    const double* ls = Ls + fk * LUB_SL + sr * 32 + fr;
+#pragma unroll
+                    for (int kk = 0; kk < LUB_NB; kk += 4) {
+                        double af[4], bf[4];
+#pragma unroll
+                        for (int ic = 0; ic < 4; ++ic) af[ic] = us[(8 * ic) * LUB_SU + kk];
+#pragma unroll
+                        for (int ir = 0; ir < 4; ++ir) bf[ir] = ls[kk * LUB_SL + 8 * ir];
+#pragma unroll
+                        for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                            for (int ir = 0; ir < 4; ++ir)
+                                dmma884(acc[ic][ir][0], acc[ic][ir][1], af[ic], bf[ir]);
+                    }
+#pragma unroll
+                    for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                        for (int ir = 0; ir < 4; ++ir) {
+                            const int c = cb + 8 * ic + fr, r = rb + 8 * ir + 2 * fk;
+                            if (c <= N && r + 1 < N) {
+                                *reinterpret_cast<double2*>(A + (size_t)c * ld + r) =
+                                    make_double2(acc[ic][ir][0], acc[ic][ir][1]);
+                            } else if (c <= N && r < N) {
+                                A[(size_t)c * ld + r] = acc[ic][ir][0];
+                            }
+                        }
+                }
+            }
+            __syncthreads();                                     // before Ls is overwritten
+        }
+    }
+    __syncthreads();
+    // ---------------- 4. blocked back substitution U x = y (y = column N) ----------------
+    double* y = A + (size_t)N * ld;
+    double* xs = Ls;                                             // NB solved values
+    for (int kb = ((N - 1) / LUB_NB) * LUB_NB; kb >= 0; kb -= LUB_NB) {
+        const int nb = min(LUB_NB, N - kb);
+        for (int t = tid; t < nb * nb; t += nthr) {
+            const int c = t / nb, r = t - c * nb;
+            L11[r * (LUB_NB + 1) + c] = A[(size_t)(kb + c) * ld + kb + r];   // diagonal block of U
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double v = (lane < nb) ? y[kb + lane] : 0.0;
+            for (int j = nb - 1; j >= 0; --j) {
+                const double d = L11[j * (LUB_NB + 1) + j];
+                const double xj = __shfl_sync(0xffffffffu, v, j) / d;
+                if (lane == j) v = xj;
+                else if (lane < j) v = fma(-L11[lane * (LUB_NB + 1) + j], xj, v);
+            }
+            if (lane < nb) { y[kb + lane] = v; xs[lane] = v; }
+        }
+        __syncthreads();
+        for (int i = tid; i < kb; i += nthr) {
+            double acc = y[i];
+            for (int j = 0; j < nb; ++j) acc = fma(-A[(size_t)(kb + j) * ld + i], xs[j], acc);
+            y[i] = acc;
+        }
+        __syncthreads();
+    }
+    return *sflag;
+}

@@ -58,3 +58,25 @@ def phasor(Vm, Va):
 def state_vectors(V_m, V_a, c):
     """x = [theta[1:], V_m[c:]] (HG:393-398) from (H, n) arrays."""
     return np.append(V_a.ravel()[1:], V_m.ravel()[c:])
+
+
+def oracle_net(net):
+    """PackedNet (product loaders) -> oracle Net: same per-unit numbers, Y_N expanded per bus."""
+    import hpf_oracle as O
+    Y_N = None if net.Y_N is None else net.Y_N[net.dev_of_nl_bus]
+    return O.Net(n=net.n, m=net.m, c=net.c, harmonics=np.asarray(net.harmonics), line_from=net.from_id,
+                 line_to=net.to_id, R=net.R, X=net.X, G=net.G, B=net.B, X_sh=net.X_sh, P=net.P, Q=net.Q,
+                 I_N=net.I_N, Y_N=Y_N, coupled=bool(net.coupled))
+
+
+def synthetic_packed(kind, tmpdir, h_max=25, coupled=True, **kw):
+    """Synthetic network (config 4 / 5 generators) through the product's own CSV loaders."""
+    from harmonic_power_flow_b200 import synthetic
+    tmpdir = str(tmpdir)
+    write_ne_csvs(tmpdir)
+    gen = synthetic.radial_feeder if kind == "radial" else synthetic.meshed
+    pb, pl = gen(tmpdir, tmpdir, **kw)
+    st = netio.Settings(H_MAX=h_max, ne_dir=tmpdir)
+    buses, lines, m, n, c = netio.init_network(pb, pl, st)
+    NE = netio.import_Norton_Equivalents(buses, coupled, st)
+    return netio.pack_network(buses, lines, m, n, c, st.HARMONICS, NE, coupled), st

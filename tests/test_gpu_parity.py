@@ -164,9 +164,12 @@ def test_lu_solve_newton_step(solvers, case):
     assert np.abs((x0 - dx) - d["x1"]).max() <= 1e-8 * np.abs(d["x1"]).max()
 
 
-def test_lu_solve_random_batch_and_singular(solvers):
-    sol, net, d = solvers("net3_c_h5")
-    N, B = sol.N, 67
+@pytest.mark.parametrize("case,B", [("net3_c_h5", 67), ("net2_c_h51", 9), ("net1_c_h25", 7), ("net1_c_h51", 7)])
+def test_lu_solve_random_batch_and_singular(solvers, case, B):
+    """Shared-memory LU (N <= 192) and the blocked global-memory LU with the tensor-core
+    trailing update (N = 206, 518, 1038: several panels, ragged last panel / slices)."""
+    sol, net, d = solvers(case)
+    N = sol.N
     rng = np.random.default_rng(3)
     A = rng.standard_normal((B, N, N))
     A[5, :, 3] = 0.0                                         # exactly singular -> zero pivot
