@@ -694,35 +694,54 @@ lu_solve_kernel(const DevNet net, const LuArgs a) {
 // (e.g. net1: 20 buses x 26 harmonics): one scenario per CTA, threads over the rows, same
 // closed-form step as harm_tile_kernel (hpf_structured.cuh); Y(h), G and W_NL stay in
 // global memory (L2), the border system is solved by the block LU (lu_solve_smem).
-__host__ __device__ inline size_t harm_cta_smem_bytes(int n, int H, int m, int c, int q, int N) {
+// For the 200- / 1000-bus configurations not even one scenario fits: the state then lives in a
+// per-CTA global-memory slab (gstate; L2 resident or streamed) and the border system
+// (2m-1-c up to 1199 unknowns) goes through the blocked tensor-core LU; shared memory keeps
+// only the reduction scratch and the LU staging buffers.
+__host__ __device__ inline size_t harm_cta_state_doubles(int n, int H, int m, int c, int q, int N, bool gmem) {
     const size_t nH = (size_t)n * H, nZ = nH - m, nx = (size_t)(m - 1) + (m - c);
-    return scn_smem_bytes(n, H, q, N, false) +
-           (2 * nZ + 2 * q + 2 * m + (size_t)odd_ld((int)nx) * (nx + 1) + nx + 8) * sizeof(double);
+    const size_t ldb = gmem ? (size_t)lub_ld((int)nx) : (size_t)odd_ld((int)nx);
+    return (scn_smem_bytes(n, H, q, N, false) + 15) / 16 * 2 + 2 * nZ + 2 * q + 2 * m + ldb * (nx + 1) + nx + 16;
+}
+__host__ __device__ inline size_t harm_cta_smem_bytes(int n, int H, int m, int c, int q, int N) {
+    return harm_cta_state_doubles(n, H, m, c, q, N, false) * sizeof(double);
+}
+__host__ __device__ inline size_t harm_cta_gmem_smem_bytes() {
+    return (LUB_SMEM_DOUBLES + 80) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(HPF_THREADS)
 harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     extern __shared__ __align__(16) double smem[];
-    const ScnSmem s = carve(smem, net, false);
+    const bool gst = a.gstate != nullptr;
+    double* base = gst ? a.gstate + (size_t)blockIdx.x * a.gstate_stride : smem;
+    ScnSmem s = carve(base, net, false);
+    double* lub = smem + 80;                                  // gstate only: LU staging
+    if (gst) {                                                // barriers / reductions need real smem
+        s.red = smem;
+        s.flag = reinterpret_cast<int*>(smem + 66);
+    }
     const int tid = threadIdx.x;
     const int n = net.n, m = net.m, c = net.c, H = net.H, q = net.q, nH = net.nH, N = net.N;
-    const int nZ = sn.nZ, nx = sn.nx, nth = m - 1, ldb = odd_ld(nx);
+    const int nZ = sn.nZ, nx = sn.nx, nth = m - 1, ldb = gst ? lub_ld(nx) : odd_ld(nx);
     const size_t B = (size_t)a.B;
     double* rhs = s.rinv;                                     // f, N doubles
-    double* wbase = reinterpret_cast<double*>(s.flag) + 4;
-    if ((reinterpret_cast<uintptr_t>(wbase) & 15) != 0) wbase += 1;            // double2 alignment
+    double* wbase = base + (scn_smem_bytes(n, H, q, N, false) + 15) / 16 * 2;
     double2* W = reinterpret_cast<double2*>(wbase);
     double2* U0 = W + nZ;
     double2* UF = U0 + q;
     double* Mb = reinterpret_cast<double*>(UF + m);           // ldb x (nx + 1), column-major
+    if ((reinterpret_cast<uintptr_t>(Mb) & 63) != 0) Mb += (64 - (reinterpret_cast<uintptr_t>(Mb) & 63)) / 8;
     double* brinv = Mb + (size_t)ldb * (nx + 1);
 
+    int step_b = (int)blockIdx.x;                             // step mode: static striding
     for (;;) {
         __syncthreads();
-        if (tid == 0) s.flag[1] = a.step_only ? (int)blockIdx.x : atomicAdd(a.work_counter, 1);
+        if (tid == 0) s.flag[1] = a.step_only ? step_b : atomicAdd(a.work_counter, 1);
         __syncthreads();
         const int b = s.flag[1];
         if (b >= a.B) break;
+        step_b += (int)gridDim.x;
         for (int t = tid; t < n; t += blockDim.x) {
             s.P[t] = a.P[t * B + b];
             s.Q[t] = a.Q[t * B + b];
@@ -750,7 +769,7 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 const int sk = m + k;
                 double2 acc = make_double2(s.Vre[sk] + W[k].x, s.Vim[sk] + W[k].y);
                 for (int i = 0; i < m; ++i)
-                    acc = cfma(acc, ldg2(sn.G + (size_t)k * m + i), make_double2(s.Vre[i], s.Vim[i]));
+                    acc = cfma(acc, ldg2(sn.GT + (size_t)i * nZ + k), make_double2(s.Vre[i], s.Vim[i]));
                 U0[k] = cneg(acc);
             }
             __syncthreads();
@@ -779,10 +798,9 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                         e = cmul(jvi, cconj((i == j) ? csub(i1, yv) : cneg(yv)));
                     }
                 }
-                for (int k = 0; k < q; ++k) {
-                    const int bk = m + k;
+                for (int en = sn.nbr_ptr[i]; en < sn.nbr_ptr[i + 1]; ++en) {   // nonlinear neighbours of bus i
+                    const int k = sn.nbr_idx[en], bk = m + k;
                     const double2 y = ldg2(net.Y + (size_t)i * n + bk);
-                    if (y.x == 0.0 && y.y == 0.0) continue;
                     const double2 vb = make_double2(s.Vre[bk], s.Vim[bk]);
                     const double2 eb = make_double2(s.Ere[bk], s.Eim[bk]);
                     const double2 ak = cmul(jvi, cconj(cneg(cmul(y, vb))));
@@ -797,8 +815,12 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 if (i >= c) Mb[(nth + i - c) + (size_t)col * ldb] = e.y;
             }
             int info = 0;
-            if (nx > 0) info = lu_solve_smem(Mb, nx, ldb, brinv, s.flag);   // (starts with a barrier)
-            else __syncthreads();
+            if (nx > 0) {                                                   // (both start with a barrier)
+                if (gst) { __syncthreads(); info = lu_solve_blocked(Mb, nx, ldb, lub, s.flag); }
+                else info = lu_solve_smem(Mb, nx, ldb, brinv, s.flag);
+            } else {
+                __syncthreads();
+            }
             if (info && status == HPF_ST_CONVERGED) status = HPF_ST_SINGULAR;
             const double* xF = Mb + (size_t)nx * ldb;
             for (int i = tid; i < m; i += blockDim.x) {
@@ -813,9 +835,9 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
             for (int z = tid; z < nZ; z += blockDim.x) {
                 const int sz = z + m;
                 double2 acc = make_double2(s.Vre[sz] + W[z].x, s.Vim[sz] + W[z].y);
-                const double2* grow = sn.G + (size_t)z * m;
+                const double2* gcol = sn.GT + z;
                 for (int i = 0; i < m; ++i)
-                    acc = cfma(acc, ldg2(grow + i), make_double2(s.Vre[i] + UF[i].x, s.Vim[i] + UF[i].y));
+                    acc = cfma(acc, ldg2(gcol + (size_t)i * nZ), make_double2(s.Vre[i] + UF[i].x, s.Vim[i] + UF[i].y));
                 const double2 wv = cmul(make_double2(s.Ere[sz], -s.Eim[sz]), cneg(acc));
                 const double vm = s.Vm[sz];
                 const double dth = wv.y / vm, dvm = wv.x;
@@ -842,7 +864,7 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
             if (a.step_only) break;
             ++it;
         }
-        if (a.step_only) break;                                // one scenario per CTA in step mode
+        if (a.step_only) continue;
         if (it >= a.max_h && status == HPF_ST_CONVERGED) status = HPF_ST_MAXITER;
         if (!(err < CUDART_INF)) status = HPF_ST_NONFINITE;
         for (int t = tid; t < nH; t += blockDim.x) {
@@ -864,6 +886,14 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
         }
     }
     (void)N;
+}
+
+// flat start of the harmonic rows (HG:183): |V| = 0.1, angle 0
+__global__ void flat_start_fill_kernel(double* __restrict__ Vm, double* __restrict__ Va, size_t cnt) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (size_t)gridDim.x * blockDim.x) {
+        Vm[t] = 0.1;
+        Va[t] = 0.0;
+    }
 }
 
 // =======================================================================================
@@ -906,12 +936,16 @@ struct hpf_handle {
     cudaEvent_t ev_io[8] = {};
     // structured strategy: 0 = not set up yet, 1 = ready, -1 = not available for this network
     int struct_state = 0;
-    double2 *d_Ainv = nullptr, *d_Gz = nullptr, *d_WNL = nullptr, *d_wN = nullptr;
+    double2 *d_Ainv = nullptr, *d_Gz = nullptr, *d_GzT = nullptr, *d_WNL = nullptr, *d_wN = nullptr;
+    int *d_nbr_ptr = nullptr, *d_nbr_idx = nullptr;
+    double* d_gstate = nullptr;   // variant 3: per-CTA scenario state slabs
+    size_t gstate_doubles = 0;
     size_t wN_elems = 0;
     int harm_warps = 8;           // warps per 32-scenario tile of the harmonic kernel (8 or 16)
     int harm_minb = 1;
     int no_specialise = 0;        // $HPF_NO_SPECIALISE=1: always use the runtime-dimension kernels
     int mismatch_tile = 0;        // $HPF_MISMATCH_TILE=1: standalone mismatch through the tile kernel
+    int force_variant = 0;        // $HPF_STRUCT_VARIANT=2|3: force a per-CTA variant of the harmonic stage
     // host mirror of the network constants for kernels that take them as parameters
     // (constant bank): fetched lazily from the device tables, see host_consts()
     std::vector<double2> hY, hYN;
@@ -1013,7 +1047,15 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     cudaStream_t st = (cudaStream_t)stream;
     DevNet net = devnet(h);
     if (mode == 1) net.N = net.Nf;      // fundamental only: size the matrix for Nf
-    const bool gm = !fits_smem_lu(h, net);
+    bool gm = !fits_smem_lu(h, net);
+    const int H_full = net.H;
+    if (mode == 1 && gm) {
+        // large network: the fundamental stage only needs the h = 1 block of the state, so the
+        // kernel sees a one-harmonic view (its per-scenario arrays are sized by nH) and the
+        // flat start of the harmonic rows (HG:183) is written by a fill kernel
+        net.H = 1; net.nH = net.n;
+        gm = !fits_smem_lu(h, net);
+    }
     const size_t smem = gm ? gmem_kernel_smem_bytes(net.n, net.H, net.q, net.N)
                            : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
     int occ = 0;
@@ -1039,6 +1081,12 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     if (h->profiling) { CK(cudaEventRecord(h->ev[1], st)); }
     if (gm) solve_kernel<true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, a);
     else solve_kernel<false><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, a);
+    if (net.H != H_full) {
+        const size_t cnt = (size_t)(H_full - 1) * net.n * B;
+        flat_start_fill_kernel<<<(unsigned)((cnt + 255) / 256 < 65535 * 8 ? (cnt + 255) / 256 : 65535 * 8), 256, 0, st>>>(
+            V_m + (size_t)net.n * B, V_a + (size_t)net.n * B, cnt);
+        h->launches++;
+    }
     if (h->profiling) { CK(cudaEventRecord(h->ev[2], st)); h->ev_valid = 2; }
     h->launches++;
     CK(cudaGetLastError());
@@ -1052,18 +1100,27 @@ static StructNet structnet(const hpf_t* h) {
     s.nx = (h->m - 1) + (h->m - h->c);
     s.Ainv = h->d_Ainv;
     s.G = h->d_Gz;
+    s.GT = h->d_GzT;
+    s.nbr_ptr = h->d_nbr_ptr;
+    s.nbr_idx = h->d_nbr_idx;
     s.WNL = h->d_WNL;
     s.yn_elems = h->n_dev * (h->coupled ? h->H * h->H : h->H);
     return s;
 }
 
+static int host_consts(hpf_t* h);
+
+// Structured set-up, once per network.  Variants of the harmonic stage:
+//   1  32-scenario tile kernels (state of 32 scenarios in shared memory: the 4-bus networks)
+//   2  one scenario per CTA, state in shared memory (net1: 20 buses x 26 harmonics)
+//   3  one scenario per CTA, state in a global-memory slab, blocked tensor-core LU for the
+//      border system (200- / 1000-bus configurations)
 static int ensure_struct(hpf_t* h, cudaStream_t st) {
     if (h->struct_state != 0) return HPF_OK;
     h->struct_state = -1;
     const DevNet net = devnet(h);
     const int nZ = net.nH - net.m;
     if (nZ < 1) return HPF_OK;
-    // variant 1: 32-scenario tile kernels; variant 2: one scenario per CTA (larger networks)
     int variant = 1;
     if (harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, h->harm_warps,
                              h->n_dev * (h->coupled ? h->H * h->H : h->H)) > (size_t)h->smem_optin ||
@@ -1073,33 +1130,85 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
         const int nx = (net.m - 1) + (net.m - net.c);
         if (harm_cta_smem_bytes(net.n, net.H, net.m, net.c, net.q, net.N) > (size_t)h->smem_optin ||
             nx > 32 * HPF_LU_MAXCHUNK || net.Nf > 32 * HPF_LU_MAXCHUNK ||
-            scn_smem_bytes(net.n, net.H, net.q, net.Nf, true) > (size_t)h->smem_optin ||
-            (size_t)net.q * net.H * HPF_T * sizeof(double2) + 16 > (size_t)h->smem_optin)
-            return HPF_OK;
+            scn_smem_bytes(net.n, net.H, net.q, net.Nf, true) > (size_t)h->smem_optin)
+            variant = 3;
+    }
+    if (h->force_variant >= 2 && h->force_variant > variant) variant = h->force_variant;   // (tests)
+    if (variant == 3) {                                 // fundamental stage: one-harmonic view, see solve_common
+        DevNet nf = net;
+        nf.N = nf.Nf; nf.H = 1; nf.nH = nf.n;
+        if (!fits_smem_lu(h, nf) && gmem_kernel_smem_bytes(nf.n, 1, nf.q, nf.N) > (size_t)h->smem_optin)
+            return HPF_OK;                              // (n beyond ~2000 buses)
     }
     double2* AZF = nullptr;
+    double2* tmp = nullptr;
     int* ipiv = nullptr;
     double* pr = nullptr;
-    cudaFree(h->d_Ainv); cudaFree(h->d_Gz); cudaFree(h->d_WNL);
-    h->d_Ainv = nullptr; h->d_Gz = nullptr; h->d_WNL = nullptr;
+    cudaFree(h->d_Ainv); cudaFree(h->d_Gz); cudaFree(h->d_GzT); cudaFree(h->d_WNL);
+    cudaFree(h->d_nbr_ptr); cudaFree(h->d_nbr_idx);
+    h->d_Ainv = nullptr; h->d_Gz = nullptr; h->d_GzT = nullptr; h->d_WNL = nullptr;
+    h->d_nbr_ptr = nullptr; h->d_nbr_idx = nullptr;
     const int qH = net.q * net.H;
-    CK(cudaMalloc((void**)&h->d_WNL, (size_t)(nZ * qH + 1) * sizeof(double2)));
+    // nonlinear neighbours of the linear buses (structure of Y1), from the host mirror of Y
+    {
+        int rc = host_consts(h);
+        if (rc) return rc;
+        std::vector<int> ptr((size_t)net.m + 1, 0), idx;
+        for (int i = 0; i < net.m; ++i) {
+            for (int k = 0; k < net.q; ++k) {
+                const double2 y = h->hY[(size_t)i * net.n + net.m + k];
+                if (y.x != 0.0 || y.y != 0.0) idx.push_back(k);
+            }
+            ptr[(size_t)i + 1] = (int)idx.size();
+        }
+        CK(upload(&h->d_nbr_ptr, ptr.data(), ptr.size()));
+        CK(upload(&h->d_nbr_idx, idx.data(), idx.size()));
+    }
+    CK(cudaMalloc((void**)&h->d_WNL, ((size_t)nZ * qH + 1) * sizeof(double2)));
     CK(cudaMalloc((void**)&h->d_Ainv, (size_t)nZ * nZ * sizeof(double2)));
     CK(cudaMalloc((void**)&h->d_Gz, (size_t)nZ * net.m * sizeof(double2)));
+    CK(cudaMalloc((void**)&h->d_GzT, (size_t)nZ * net.m * sizeof(double2)));
     CK(cudaMalloc((void**)&AZF, (size_t)nZ * net.m * sizeof(double2)));
     CK(cudaMalloc((void**)&ipiv, (size_t)(nZ + 2) * sizeof(int)));
     CK(cudaMalloc((void**)&pr, 2 * sizeof(double)));
-    struct_assemble_kernel<<<64, 256, 0, st>>>(net, h->d_Ainv, AZF);
-    cinv_gj_kernel<<<1, 1024, 0, st>>>(nZ, h->d_Ainv, ipiv, ipiv + nZ, pr);
-    struct_G_kernel<<<(nZ * net.m + 127) / 128, 128, 0, st>>>(nZ, net.m, h->d_Ainv, AZF, h->d_Gz);
-    if (qH > 0) struct_WNL_kernel<<<(nZ * qH + 127) / 128, 128, 0, st>>>(net, nZ, h->d_Ainv, h->d_WNL);
-    h->launches += 4;
+    struct_assemble_kernel<<<h->sm_count * 8, 256, 0, st>>>(net, h->d_Ainv, AZF);
+    h->launches++;
+    if (nZ <= 768) {
+        cinv_gj_kernel<<<1, 1024, 0, st>>>(nZ, h->d_Ainv, ipiv, ipiv + nZ, pr);
+        h->launches++;
+    } else {
+        CK(cudaMalloc((void**)&tmp, ((size_t)2 * nZ + 1) * sizeof(double2)));
+        double2 *rowk = tmp, *colk = tmp + nZ, *pinv = tmp + 2 * (size_t)nZ;
+        const int g1 = (nZ + 255) / 256;
+        int gy = (h->sm_count * 8 + g1 - 1) / g1;
+        if (gy > nZ) gy = nZ;
+        for (int k = 0; k < nZ; ++k) {
+            gjm_pivot_kernel<<<1, 1024, 0, st>>>(nZ, k, h->d_Ainv, ipiv, ipiv + nZ, pr, pinv);
+            gjm_row_kernel<<<g1, 256, 0, st>>>(nZ, k, h->d_Ainv, ipiv, pinv, rowk);
+            gjm_col_kernel<<<g1, 256, 0, st>>>(nZ, k, h->d_Ainv, colk);
+            gjm_elim_kernel<<<dim3(g1, gy), 256, 0, st>>>(nZ, k, h->d_Ainv, rowk, colk);
+        }
+        gjm_unpermute_kernel<<<g1, 256, 0, st>>>(nZ, h->d_Ainv, ipiv);
+        h->launches += 4LL * nZ + 1;
+    }
+    {
+        const size_t tot = (size_t)nZ * net.m;
+        struct_G_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(nZ, net.m, net.q < nZ ? net.q : nZ,
+                                                                       h->d_Ainv, AZF, h->d_Gz, h->d_GzT);
+        h->launches++;
+    }
+    if (qH > 0) {
+        const size_t tot = (size_t)nZ * qH;
+        struct_WNL_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(net, nZ, h->d_Ainv, h->d_WNL);
+        h->launches++;
+    }
     int info = -1;
     double prh[2] = {0.0, 0.0};
     cudaError_t e = cudaMemcpyAsync(&info, ipiv + nZ, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(prh, pr, sizeof(prh), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(AZF); cudaFree(ipiv); cudaFree(pr);
+    cudaFree(AZF); cudaFree(ipiv); cudaFree(pr); cudaFree(tmp);
+    if (variant == 3) { cudaFree(h->d_Ainv); h->d_Ainv = nullptr; }    // (GBs for the 1000-bus network)
     if (e != cudaSuccess) return fail(h, HPF_E_CUDA, std::string("structured setup: ") + cudaGetErrorString(e));
     h->pivot_min = prh[0]; h->pivot_max = prh[1];
     // usable when the inversion met no zero pivot and the pivots span < 1e12 (well conditioned)
@@ -1119,14 +1228,19 @@ static int launch_wn(hpf_t* h, const DevNet& net, const StructNet& sn, int B, co
     if (qH == 0) { CK(cudaMemsetAsync(h->d_wN, 0, need * sizeof(double2), st)); return HPF_OK; }
     WnArgs wa;
     wa.B = B; wa.I_N = (const double2*)I_N; wa.wN = h->d_wN;
-    const size_t smem = (size_t)qH * HPF_T * sizeof(double2) + 16;
+    const size_t smem = (size_t)(qH < HPF_WN_UCH ? qH : HPF_WN_UCH) * HPF_T * sizeof(double2) + 16;
     int occ = 0;
     int rc = prep_kernel(h, wn_tile_kernel, smem, "hpf_solve", &occ, 256);
     if (rc) return rc;
     const long long tiles = ((long long)B + HPF_T - 1) / HPF_T;
     long long grid = (long long)occ * h->sm_count;
     if (grid > tiles) grid = tiles;
-    wn_tile_kernel<<<(unsigned)grid, 256, smem, st>>>(net, sn, sn.WNL, wa);
+    // few tiles (large networks, small batches): spread the row groups over grid.y as well
+    const long long groups = (sn.nZ + 8 * HPF_WN_RPW - 1) / (8 * HPF_WN_RPW);
+    long long gy = ((long long)occ * h->sm_count + grid - 1) / grid;
+    if (gy > groups) gy = groups;
+    if (gy < 1) gy = 1;
+    wn_tile_kernel<<<dim3((unsigned)grid, (unsigned)gy), 256, smem, st>>>(net, sn, sn.WNL, wa);
     h->launches++;
     CK(cudaGetLastError());
     return HPF_OK;
@@ -1153,14 +1267,28 @@ static int launch_harm_t(hpf_t* h, const DevNet& net, const StructNet& sn, const
 // every other network runs the runtime-dimension instance.
 static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const HarmTileArgs& ha,
                        bool persistent, cudaStream_t st) {
-    if (h->struct_state == 2) {
-        const size_t smem = harm_cta_smem_bytes(net.n, net.H, net.m, net.c, net.q, net.N);
+    if (h->struct_state >= 2) {
+        const bool gst = h->struct_state == 3;
+        const size_t smem = gst ? harm_cta_gmem_smem_bytes()
+                                : harm_cta_smem_bytes(net.n, net.H, net.m, net.c, net.q, net.N);
         int occ = 0;
         int rc = prep_kernel(h, harm_cta_kernel, smem, "hpf_solve", &occ);
         if (rc) return rc;
         long long grid = ha.B;
-        if (persistent && grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
-        harm_cta_kernel<<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, sn, ha);
+        if ((persistent || gst) && grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
+        HarmTileArgs ha2 = ha;
+        ha2.gstate = nullptr; ha2.gstate_stride = 0;
+        if (gst) {
+            const size_t stride = (harm_cta_state_doubles(net.n, net.H, net.m, net.c, net.q, net.N, true) + 15) / 8 * 8;
+            const size_t need = stride * (size_t)grid;
+            if (need > h->gstate_doubles) {
+                if (h->d_gstate) { CK(cudaDeviceSynchronize()); cudaFree(h->d_gstate); h->d_gstate = nullptr; h->gstate_doubles = 0; }
+                CK(cudaMalloc((void**)&h->d_gstate, need * sizeof(double)));
+                h->gstate_doubles = need;
+            }
+            ha2.gstate = h->d_gstate; ha2.gstate_stride = stride;
+        }
+        harm_cta_kernel<<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, sn, ha2);
         h->launches++;
         CK(cudaGetLastError());
         return HPF_OK;
@@ -1186,7 +1314,7 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     if (h->profiling) { CK(cudaEventRecord(h->ev[0], st)); }
     // fundamental stage: one lane per scenario (variant 1) or the per-CTA kernel (variant 2)
-    if (h->struct_state == 2) {
+    if (h->struct_state >= 2) {
         int rc = solve_common(h, 1, B, P, Q, nullptr, thresh_f, max_f, 0.0, 0, 0, V_m, V_a, nullptr, n_iter_f,
                               nullptr, nullptr, nullptr, status, nullptr, nullptr, st);
         if (rc) return rc;
@@ -1220,7 +1348,7 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
         ha.wN = h->d_wN;
         ha.thresh_h = thresh_h; ha.max_h = max_h; ha.V_m = V_m; ha.V_a = V_a; ha.I_inj = (double2*)I_inj;
         ha.n_iter_h = n_iter_h; ha.status = status; ha.err_h = err_h; ha.work_counter = h->d_counter;
-        ha.dx_out = nullptr;
+        ha.dx_out = nullptr; ha.gstate = nullptr; ha.gstate_stride = 0;
         rc = launch_harm(h, net, sn, ha, true, st);
         if (rc) return rc;
     }
@@ -1296,6 +1424,7 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_HARM_MINB")) h->harm_minb = (atoi(ev) == 2) ? 2 : 1;
     if (const char* ev = getenv("HPF_NO_SPECIALISE")) h->no_specialise = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_MISMATCH_TILE")) h->mismatch_tile = atoi(ev) ? 1 : 0;
+    if (const char* ev = getenv("HPF_STRUCT_VARIANT")) h->force_variant = atoi(ev);
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     e = cudaMalloc((void**)&h->d_counter, sizeof(int));
@@ -1314,7 +1443,8 @@ int hpf_destroy(hpf_t* h) {
     cudaFree(h->d_harm); cudaFree(h->d_from); cudaFree(h->d_to); cudaFree(h->d_devof);
     cudaFree(h->d_R); cudaFree(h->d_X); cudaFree(h->d_G); cudaFree(h->d_B); cudaFree(h->d_Xsh);
     cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work); cudaFree(h->d_io); cudaFree(h->d_Ainv); cudaFree(h->d_Gz);
-    cudaFree(h->d_WNL); cudaFree(h->d_wN);
+    cudaFree(h->d_WNL); cudaFree(h->d_wN); cudaFree(h->d_GzT); cudaFree(h->d_nbr_ptr); cudaFree(h->d_nbr_idx);
+    cudaFree(h->d_gstate);
     for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 3; ++i) if (h->st_io[i]) cudaStreamDestroy(h->st_io[i]);
     for (int i = 0; i < 8; ++i) if (h->ev_io[i]) cudaEventDestroy(h->ev_io[i]);
@@ -1506,7 +1636,7 @@ int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const
     ha.wN = h->d_wN;
     ha.thresh_h = 0.0; ha.max_h = 1; ha.V_m = const_cast<double*>(V_m); ha.V_a = const_cast<double*>(V_a);
     ha.I_inj = nullptr; ha.n_iter_h = nullptr; ha.status = nullptr; ha.err_h = nullptr;
-    ha.work_counter = nullptr; ha.dx_out = dx;
+    ha.work_counter = nullptr; ha.dx_out = dx; ha.gstate = nullptr; ha.gstate_stride = 0;
     return launch_harm(h, net, sn, ha, false, (cudaStream_t)stream);
 }
 

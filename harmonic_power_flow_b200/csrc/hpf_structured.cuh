@@ -31,8 +31,13 @@ struct StructNet {
     int nZ, nx;
     const double2* Ainv;   // [nZ][nZ] row-major
     const double2* G;      // [nZ][m]
+    const double2* GT;     // [m][nZ]   transposed copy (coalesced over rows in the per-CTA kernel)
     const double2* WNL;    // [nZ][qH]  columns of Ainv that multiply the Norton currents
     int yn_elems;          // complex entries of the Y_N table
+    // nonlinear neighbours of the linear buses at the fundamental (CSR over i = 0..m-1):
+    // k = nbr_idx[e] for nbr_ptr[i] <= e < nbr_ptr[i+1]  <=>  Y1[i][m+k] != 0
+    const int* nbr_ptr;
+    const int* nbr_idx;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -165,15 +170,112 @@ cinv_gj_kernel(int n, double2* __restrict__ A, int* __restrict__ ipiv, int* __re
     if (tid == 0) { pivrange[0] = pmin; pivrange[1] = pmax; }
 }
 
+// setup 2b: the same Gauss-Jordan inversion spread over the whole GPU for large operators
+// (nZ in the thousands: 200- / 1000-bus networks), four small launches per pivot step:
+//   gjm_pivot   (1 CTA)      pivot row p of column k, 1 / pivot, bookkeeping
+//   gjm_row     (columns)    interchange rows k <-> p, scale the pivot row, keep a copy of it
+//   gjm_col     (rows)       copy of column k (the multipliers), taken after the interchange
+//   gjm_elim    (elements)   a_ij -= a_ik a_kj (j != k),  a_ik = -a_ik a_kk
+// and gjm_unpermute (rows) to undo the interchanges on the columns at the end.
+__global__ void __launch_bounds__(1024)
+gjm_pivot_kernel(int n, int k, const double2* __restrict__ A, int* __restrict__ ipiv, int* __restrict__ info,
+                 double* __restrict__ pivrange, double2* __restrict__ pinv_out) {
+    __shared__ double redv[33];
+    __shared__ int redi[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + tid; i < n; i += blockDim.x) {
+        const double2 a = A[(size_t)i * n + k];
+        const double v = hypot(a.x, a.y);
+        if (v > best) { best = v; bi = i; }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        best = (lane < nw) ? redv[lane] : -1.0;
+        bi = (lane < nw) ? redi[lane] : 0x7fffffff;
+        for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            ipiv[k] = bi;
+            if (k == 0) { info[0] = 0; pivrange[0] = CUDART_INF; pivrange[1] = 0.0; }
+            if (!(best > 0.0) || !(best < CUDART_INF)) { if (info[0] == 0) info[0] = k + 1; }
+            pivrange[0] = fmin(pivrange[0], best);
+            pivrange[1] = fmax(pivrange[1], best);
+            pinv_out[0] = crecip(A[(size_t)bi * n + k]);
+        }
+    }
+}
+
+__global__ void gjm_row_kernel(int n, int k, double2* __restrict__ A, const int* __restrict__ ipiv,
+                               const double2* __restrict__ pinv_in, double2* __restrict__ rowk) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int p = ipiv[k];
+    const double2 pinv = pinv_in[0];
+    const double2 tk = A[(size_t)k * n + j], tp = A[(size_t)p * n + j];
+    const double2 a = (j == k) ? make_double2(1.0, 0.0) : tp;
+    const double2 v = cmul(a, pinv);
+    A[(size_t)k * n + j] = v;
+    if (p != k) A[(size_t)p * n + j] = tk;
+    rowk[j] = v;
+}
+
+__global__ void gjm_col_kernel(int n, int k, const double2* __restrict__ A, double2* __restrict__ colk) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    colk[i] = (i == k) ? make_double2(0.0, 0.0) : A[(size_t)i * n + k];
+}
+
+__global__ void gjm_elim_kernel(int n, int k, double2* __restrict__ A, const double2* __restrict__ rowk,
+                                const double2* __restrict__ colk) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double2 r = rowk[j];
+    for (int i = blockIdx.y; i < n; i += gridDim.y) {
+        if (i == k) continue;
+        const double2 f = colk[i];
+        double2* a = A + (size_t)i * n + j;
+        *a = (j == k) ? cneg(cmul(f, r)) : csub(*a, cmul(f, r));
+    }
+}
+
+__global__ void gjm_unpermute_kernel(int n, double2* __restrict__ A, const int* __restrict__ ipiv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double2* row = A + (size_t)i * n;
+    for (int k = n - 1; k >= 0; --k) {
+        const int p = ipiv[k];
+        if (p != k) {
+            const double2 t = row[k];
+            row[k] = row[p];
+            row[p] = t;
+        }
+    }
+}
+
 // setup 3: G = Ainv * A_ZF
-__global__ void struct_G_kernel(int nZ, int m, const double2* __restrict__ Ainv,
-                                const double2* __restrict__ AZF, double2* __restrict__ G) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nZ * m) return;
-    const int r = t / m, j = t - r * m;
+// (A_ZF is zero outside its first q rows - only the fundamental rows of the nonlinear buses
+// see the fundamental voltages of the linear buses - so the sum stops at kmax = q.)
+__global__ void struct_G_kernel(int nZ, int m, int kmax, const double2* __restrict__ Ainv,
+                                const double2* __restrict__ AZF, double2* __restrict__ G,
+                                double2* __restrict__ GT) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nZ * m) return;
+    const int r = (int)(t / m), j = (int)(t - (size_t)r * m);
     double2 acc = make_double2(0.0, 0.0);
-    for (int k = 0; k < nZ; ++k) acc = cadd(acc, cmul(Ainv[(size_t)r * nZ + k], AZF[(size_t)k * m + j]));
+    for (int k = 0; k < kmax; ++k) acc = cadd(acc, cmul(Ainv[(size_t)r * nZ + k], AZF[(size_t)k * m + j]));
     G[t] = acc;
+    GT[(size_t)j * nZ + r] = acc;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -345,9 +447,9 @@ fund_tile_kernel(const DevNet net, const FundTileArgs a) {
 __global__ void struct_WNL_kernel(const DevNet net, int nZ, const double2* __restrict__ Ainv,
                                   double2* __restrict__ WNL) {
     const int qH = net.q * net.H;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nZ * qH) return;
-    const int z = t / qH, u = t - z * qH, k = u / net.H, h = u - k * net.H;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nZ * qH) return;
+    const int z = (int)(t / qH), u = (int)(t - (size_t)z * qH), k = u / net.H, h = u - k * net.H;
     const int zc = h * net.n + net.m + k - net.m;
     WNL[t] = Ainv[(size_t)z * nZ + zc];
 }
@@ -361,25 +463,48 @@ struct WnArgs {
     double2* wN;          // [nZ, B]
 };
 
+#define HPF_WN_UCH 64      // Norton currents staged per chunk
+#define HPF_WN_RPW 4       // rows accumulated per warp at a time
+
 __global__ void __launch_bounds__(256)
 wn_tile_kernel(const DevNet net, const StructNet sn, const double2* __restrict__ WNL, const WnArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
     const int qH = net.q * net.H, nZ = sn.nZ;
     const size_t B = (size_t)a.B;
-    double2* IN = reinterpret_cast<double2*>(smem);          // [qH][32]
+    double2* IN = reinterpret_cast<double2*>(smem);          // [min(qH, UCH)][32]
+    const int uch = qH < HPF_WN_UCH ? qH : HPF_WN_UCH;
     for (size_t tile = blockIdx.x; tile * HPF_T < B; tile += gridDim.x) {
         const size_t b = tile * HPF_T + lane;
         const bool ok = b < B;
         const size_t bb = ok ? b : B - 1;
-        __syncthreads();
-        for (int u = warp; u < qH; u += NW) IN[u * HPF_T + lane] = a.I_N[(size_t)u * B + bb];
-        __syncthreads();
-        for (int z = warp; z < nZ; z += NW) {
-            const double2* row = WNL + (size_t)z * qH;
-            double2 acc = make_double2(0.0, 0.0);
-            for (int u = 0; u < qH; ++u) acc = cadd(acc, cmul(ldg2(row + u), IN[u * HPF_T + lane]));
-            if (ok) a.wN[(size_t)z * B + b] = acc;
+        // row groups of NW * RPW rows; the chunk loop is inside so that the accumulators stay in
+        // registers (the staged currents are re-read from L2 once per row group)
+        for (int z0 = blockIdx.y * NW * HPF_WN_RPW; z0 < nZ; z0 += gridDim.y * NW * HPF_WN_RPW) {
+            double2 acc[HPF_WN_RPW];
+#pragma unroll
+            for (int r = 0; r < HPF_WN_RPW; ++r) acc[r] = make_double2(0.0, 0.0);
+            for (int u0 = 0; u0 < qH; u0 += uch) {
+                const int nu = min(uch, qH - u0);
+                __syncthreads();
+                for (int u = warp; u < nu; u += NW) IN[u * HPF_T + lane] = a.I_N[(size_t)(u0 + u) * B + bb];
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < HPF_WN_RPW; ++r) {
+                    const int z = z0 + r * NW + warp;
+                    if (z < nZ) {
+                        const double2* row = WNL + (size_t)z * qH + u0;
+                        double2 s2 = acc[r];
+                        for (int u = 0; u < nu; ++u) s2 = cadd(s2, cmul(ldg2(row + u), IN[u * HPF_T + lane]));
+                        acc[r] = s2;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < HPF_WN_RPW; ++r) {
+                const int z = z0 + r * NW + warp;
+                if (z < nZ && ok) a.wN[(size_t)z * B + b] = acc[r];
+            }
         }
     }
 }
@@ -481,6 +606,8 @@ struct HarmTileArgs {
     double* err_h;
     int* work_counter;
     double* dx_out;          // step_only: [N, B] the Newton update dx (x_new = x - dx)
+    double* gstate;          // per-CTA kernel, large networks: scenario state in global memory
+    size_t gstate_stride;    //   doubles per CTA (0: state in shared memory)
 };
 
 
