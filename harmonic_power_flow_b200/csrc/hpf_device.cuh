@@ -17,6 +17,12 @@ struct DevNet {
     const double2* Y;       // [H][n][n]   bus admittance per harmonic (kernel 1 output)
     const double2* YN;      // [n_dev][H][H] (coupled) or [n_dev][H]
     const int* dev_of_nl;   // [q]
+    // optional sparsity pattern of Y(h) (union over the harmonics), ELL format: the columns of
+    // row i are ell_col[i * ell_w + e], ascending, padded with -1; nullptr = use the dense rows.
+    // Built for the larger networks only; skipping exact zeros of a sequential sum leaves
+    // every finite result bit-identical.
+    const int* ell_col;
+    int ell_w;
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -65,6 +71,17 @@ __device__ __forceinline__ double2 ydotv(const DevNet& net, int h, int i, int of
     const int n = net.n;
     const double2* Yrow = net.Y + ((size_t)h * n + i) * n;
     double2 acc = make_double2(0.0, 0.0);
+    if (net.ell_col) {
+        const int* cols = net.ell_col + (size_t)i * net.ell_w;
+        for (int e = 0; e < net.ell_w; ++e) {
+            const int j = __ldg(cols + e);
+            if (j < 0) break;
+            const double2 y = ldg2(Yrow + j);
+            const double2 v = make_double2(Vre[(h * n + j) * VS + off], Vim[(h * n + j) * VS + off]);
+            acc = cfma(acc, y, v);
+        }
+        return acc;
+    }
     for (int j = 0; j < n; ++j) {
         const double2 y = ldg2(Yrow + j);
         const double2 v = make_double2(Vre[(h * n + j) * VS + off], Vim[(h * n + j) * VS + off]);

@@ -206,6 +206,13 @@ __device__ __forceinline__ void cta_fund_jacobian(const DevNet& net, const ScnSm
                                                   size_t rs, size_t cs) {
     const int n = net.n;
     auto put = [=](int row, int col, double v) { A[row * rs + col * cs] = v; };
+    if (net.ell_col) {                                   // (every non-zero of Y1 and the diagonal is listed)
+        for (int t = threadIdx.x; t < n * net.ell_w; t += blockDim.x) {
+            const int i = t / net.ell_w, j = net.ell_col[t];
+            if (j >= 0) fund_jacobian_item(net, i, j, s.Vre, s.Vim, s.Ere, s.Eim, s.I1, put);
+        }
+        return;
+    }
     for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
         const int i = t / n, j = t - i * n;
         fund_jacobian_item(net, i, j, s.Vre, s.Vim, s.Ere, s.Eim, s.I1, put);
@@ -228,6 +235,7 @@ struct SolveArgs {
     double *err_h, *err_f, *hist_f, *hist_h;
     int* work_counter;
     double* workspace;     // GMEM variant: gridDim.x * ld * (N + 1) doubles
+    int lub_doubles;       // GMEM variant: shared-memory work area of the blocked LU (doubles)
 };
 
 #define HPF_THREADS_GMEM 512
@@ -236,8 +244,13 @@ struct SolveArgs {
 __host__ __device__ inline size_t scn_smem_doubles_aligned(int n, int H, int q, int N) {
     return (scn_smem_bytes(n, H, q, N, false) + 15) / 16 * 2;
 }
-__host__ __device__ inline size_t gmem_kernel_smem_bytes(int n, int H, int q, int N) {
+__host__ __device__ inline size_t gmem_kernel_smem_bytes(int n, int H, int q, int N) {     // minimum
     return (scn_smem_doubles_aligned(n, H, q, N) + LUB_SMEM_DOUBLES) * sizeof(double) + 16;
+}
+// blocked-LU work area (doubles) for an N-row system next to the scenario state, within `optin`
+static inline size_t gmem_kernel_lub_doubles(int n, int H, int q, int N, size_t optin) {
+    const size_t state = scn_smem_doubles_aligned(n, H, q, N) * sizeof(double) + 16;
+    return lub_smem_doubles_for(N, optin > state ? optin - state : 0);
 }
 template <bool GMEM>
 __global__ void __launch_bounds__(GMEM ? HPF_THREADS_GMEM : HPF_THREADS)
@@ -281,7 +294,7 @@ solve_kernel(const DevNet net, const SolveArgs a) {
             cta_zero(s.A, (size_t)ld * Nf);
             __syncthreads();
             cta_fund_jacobian(net, s, s.A, 1, ld);
-            const int info = GMEM ? lu_solve_blocked(s.A, Nf, ld, lub, s.flag)
+            const int info = GMEM ? lu_solve_blocked(s.A, Nf, ld, lub, a.lub_doubles, s.flag)
                                   : lu_solve_smem(s.A, Nf, ld, s.rinv, s.flag);
             if (info) status = HPF_ST_SINGULAR;
             for (int t = tid; t < Nf; t += blockDim.x) {       // HG:226-235
@@ -321,7 +334,7 @@ solve_kernel(const DevNet net, const SolveArgs a) {
             cta_zero(s.A, (size_t)ld * N);
             __syncthreads();
             cta_harmonic_jacobian(net, s, s.A, 1, ld);
-            const int info = GMEM ? lu_solve_blocked(s.A, N, ld, lub, s.flag)
+            const int info = GMEM ? lu_solve_blocked(s.A, N, ld, lub, a.lub_doubles, s.flag)
                                   : lu_solve_smem(s.A, N, ld, s.rinv, s.flag);
             if (info && status == HPF_ST_CONVERGED) status = HPF_ST_SINGULAR;
             for (int t = tid; t < N; t += blockDim.x) {        // HG:476-485
@@ -662,6 +675,7 @@ struct LuArgs {
     int* info;
     long long stride;
     double* workspace;
+    int lub_doubles;
 };
 
 template <bool GMEM>
@@ -682,7 +696,7 @@ lu_solve_kernel(const DevNet net, const LuArgs a) {
         }
         double* rhs = s.A + (size_t)N * ld;
         for (int t = threadIdx.x; t < N; t += blockDim.x) rhs[t] = a.f[t * B + b];
-        const int info = GMEM ? lu_solve_blocked(s.A, N, ld, lub, s.flag)
+        const int info = GMEM ? lu_solve_blocked(s.A, N, ld, lub, a.lub_doubles, s.flag)
                               : lu_solve_smem(s.A, N, ld, s.rinv, s.flag);
         for (int t = threadIdx.x; t < N; t += blockDim.x) a.dx[t * B + b] = rhs[t];
         if (threadIdx.x == 0) a.info[b] = info;
@@ -706,11 +720,12 @@ __host__ __device__ inline size_t harm_cta_state_doubles(int n, int H, int m, in
 __host__ __device__ inline size_t harm_cta_smem_bytes(int n, int H, int m, int c, int q, int N) {
     return harm_cta_state_doubles(n, H, m, c, q, N, false) * sizeof(double);
 }
-__host__ __device__ inline size_t harm_cta_gmem_smem_bytes() {
-    return (LUB_SMEM_DOUBLES + 80) * sizeof(double);
+static inline size_t harm_cta_gmem_lub_doubles(int nx, size_t optin) {
+    return lub_smem_doubles_for(nx, optin - 80 * sizeof(double));
 }
 
-__global__ void __launch_bounds__(HPF_THREADS)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
 harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     extern __shared__ __align__(16) double smem[];
     const bool gst = a.gstate != nullptr;
@@ -816,18 +831,21 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
             }
             int info = 0;
             if (nx > 0) {                                                   // (both start with a barrier)
-                if (gst) { __syncthreads(); info = lu_solve_blocked(Mb, nx, ldb, lub, s.flag); }
+                if (gst) { __syncthreads(); info = lu_solve_blocked(Mb, nx, ldb, lub, a.lub_doubles, s.flag); }
                 else info = lu_solve_smem(Mb, nx, ldb, brinv, s.flag);
             } else {
                 __syncthreads();
             }
             if (info && status == HPF_ST_CONVERGED) status = HPF_ST_SINGULAR;
             const double* xF = Mb + (size_t)nx * ldb;
+            // V_F + u_F (the LU staging area is free again: keep it in shared memory)
+            double2* UFs = gst ? reinterpret_cast<double2*>(lub) : UF;
             for (int i = tid; i < m; i += blockDim.x) {
                 const double dth = (i >= 1) ? xF[i - 1] : 0.0;
                 const double dvm = (i >= c) ? xF[nth + i - c] : 0.0;
                 const double2 vi = make_double2(s.Vre[i], s.Vim[i]);
-                UF[i] = make_double2(-vi.y * dth + s.Ere[i] * dvm, vi.x * dth + s.Eim[i] * dvm);
+                const double2 uf = make_double2(-vi.y * dth + s.Ere[i] * dvm, vi.x * dth + s.Eim[i] * dvm);
+                UFs[i] = make_double2(vi.x + uf.x, vi.y + uf.y);
             }
             __syncthreads();
             // u_Z = -V_Z - G (V_F + u_F) - w_N, polar conversion, update (Vre/Vim/E are this
@@ -836,8 +854,7 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 const int sz = z + m;
                 double2 acc = make_double2(s.Vre[sz] + W[z].x, s.Vim[sz] + W[z].y);
                 const double2* gcol = sn.GT + z;
-                for (int i = 0; i < m; ++i)
-                    acc = cfma(acc, ldg2(gcol + (size_t)i * nZ), make_double2(s.Vre[i] + UF[i].x, s.Vim[i] + UF[i].y));
+                for (int i = 0; i < m; ++i) acc = cfma(acc, ldg2(gcol + (size_t)i * nZ), UFs[i]);
                 const double2 wv = cmul(make_double2(s.Ere[sz], -s.Eim[sz]), cneg(acc));
                 const double vm = s.Vm[sz];
                 const double dth = wv.y / vm, dvm = wv.x;
@@ -938,6 +955,8 @@ struct hpf_handle {
     int struct_state = 0;
     double2 *d_Ainv = nullptr, *d_Gz = nullptr, *d_GzT = nullptr, *d_WNL = nullptr, *d_wN = nullptr;
     int *d_nbr_ptr = nullptr, *d_nbr_idx = nullptr;
+    int* d_ell_col = nullptr;     // sparsity pattern of Y(h) for the larger networks (see DevNet)
+    int ell_w = 0;
     double* d_gstate = nullptr;   // variant 3: per-CTA scenario state slabs
     size_t gstate_doubles = 0;
     size_t wN_elems = 0;
@@ -980,6 +999,7 @@ static DevNet devnet(const hpf_t* h) {
     d.Nf = 2 * h->n - 1 - h->c;
     d.coupled = h->coupled;
     d.Y = h->d_Y; d.YN = h->d_YN; d.dev_of_nl = h->d_devof;
+    d.ell_col = h->d_ell_col; d.ell_w = h->ell_w;
     return d;
 }
 
@@ -1056,7 +1076,8 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
         net.H = 1; net.nH = net.n;
         gm = !fits_smem_lu(h, net);
     }
-    const size_t smem = gm ? gmem_kernel_smem_bytes(net.n, net.H, net.q, net.N)
+    const size_t lubd = gm ? gmem_kernel_lub_doubles(net.n, net.H, net.q, net.N, (size_t)h->smem_optin) : 0;
+    const size_t smem = gm ? (scn_smem_doubles_aligned(net.n, net.H, net.q, net.N) + lubd) * sizeof(double) + 16
                            : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
     int occ = 0;
     rc = gm ? prep_kernel(h, solve_kernel<true>, smem, who, &occ, HPF_THREADS_GMEM)
@@ -1069,6 +1090,7 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     a.V_m = V_m; a.V_a = V_a; a.I_inj = (double2*)I_inj;
     a.n_iter_f = n_iter_f; a.n_iter_h = n_iter_h; a.status = status; a.err_h = err_h; a.err_f = err_f;
     a.work_counter = h->d_counter;
+    a.lub_doubles = (int)lubd;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     long long grid = (long long)occ * h->sm_count;
     if (grid > B) grid = B;
@@ -1163,6 +1185,31 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
         }
         CK(upload(&h->d_nbr_ptr, ptr.data(), ptr.size()));
         CK(upload(&h->d_nbr_idx, idx.data(), idx.size()));
+        // sparsity pattern of Y(h), union over the harmonics (diagonal always listed)
+        cudaFree(h->d_ell_col); h->d_ell_col = nullptr; h->ell_w = 0;
+        if (net.n >= 16) {
+            const int n = net.n;
+            std::vector<std::vector<int>> cols((size_t)n);
+            int w = 0;
+            for (int i = 0; i < n; ++i) {
+                for (int j = 0; j < n; ++j) {
+                    bool nz = (i == j);
+                    for (int hh = 0; hh < net.H && !nz; ++hh) {
+                        const double2 y = h->hY[((size_t)hh * n + i) * n + j];
+                        nz = (y.x != 0.0 || y.y != 0.0);
+                    }
+                    if (nz) cols[(size_t)i].push_back(j);
+                }
+                if ((int)cols[(size_t)i].size() > w) w = (int)cols[(size_t)i].size();
+            }
+            if (w * 2 <= n) {                            // sparse enough to pay off
+                std::vector<int> ell((size_t)n * w, -1);
+                for (int i = 0; i < n; ++i)
+                    for (size_t e = 0; e < cols[(size_t)i].size(); ++e) ell[(size_t)i * w + e] = cols[(size_t)i][e];
+                CK(upload(&h->d_ell_col, ell.data(), ell.size()));
+                h->ell_w = w;
+            }
+        }
     }
     CK(cudaMalloc((void**)&h->d_WNL, ((size_t)nZ * qH + 1) * sizeof(double2)));
     CK(cudaMalloc((void**)&h->d_Ainv, (size_t)nZ * nZ * sizeof(double2)));
@@ -1269,15 +1316,18 @@ static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const H
                        bool persistent, cudaStream_t st) {
     if (h->struct_state >= 2) {
         const bool gst = h->struct_state == 3;
-        const size_t smem = gst ? harm_cta_gmem_smem_bytes()
+        const size_t lubd = gst ? harm_cta_gmem_lub_doubles(sn.nx, (size_t)h->smem_optin) : 0;
+        const size_t smem = gst ? (lubd + 80) * sizeof(double)
                                 : harm_cta_smem_bytes(net.n, net.H, net.m, net.c, net.q, net.N);
         int occ = 0;
-        int rc = prep_kernel(h, harm_cta_kernel, smem, "hpf_solve", &occ);
+        // global-state variant: every phase waits on L2 / HBM, so it runs with twice the warps
+        int rc = gst ? prep_kernel(h, harm_cta_kernel<HPF_THREADS_GMEM>, smem, "hpf_solve", &occ, HPF_THREADS_GMEM)
+                     : prep_kernel(h, harm_cta_kernel<HPF_THREADS>, smem, "hpf_solve", &occ);
         if (rc) return rc;
         long long grid = ha.B;
         if ((persistent || gst) && grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
         HarmTileArgs ha2 = ha;
-        ha2.gstate = nullptr; ha2.gstate_stride = 0;
+        ha2.gstate = nullptr; ha2.gstate_stride = 0; ha2.lub_doubles = (int)lubd;
         if (gst) {
             const size_t stride = (harm_cta_state_doubles(net.n, net.H, net.m, net.c, net.q, net.N, true) + 15) / 8 * 8;
             const size_t need = stride * (size_t)grid;
@@ -1288,7 +1338,8 @@ static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const H
             }
             ha2.gstate = h->d_gstate; ha2.gstate_stride = stride;
         }
-        harm_cta_kernel<<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, sn, ha2);
+        if (gst) harm_cta_kernel<HPF_THREADS_GMEM><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, sn, ha2);
+        else harm_cta_kernel<HPF_THREADS><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, sn, ha2);
         h->launches++;
         CK(cudaGetLastError());
         return HPF_OK;
@@ -1348,7 +1399,7 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
         ha.wN = h->d_wN;
         ha.thresh_h = thresh_h; ha.max_h = max_h; ha.V_m = V_m; ha.V_a = V_a; ha.I_inj = (double2*)I_inj;
         ha.n_iter_h = n_iter_h; ha.status = status; ha.err_h = err_h; ha.work_counter = h->d_counter;
-        ha.dx_out = nullptr; ha.gstate = nullptr; ha.gstate_stride = 0;
+        ha.dx_out = nullptr; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0;
         rc = launch_harm(h, net, sn, ha, true, st);
         if (rc) return rc;
     }
@@ -1444,7 +1495,7 @@ int hpf_destroy(hpf_t* h) {
     cudaFree(h->d_R); cudaFree(h->d_X); cudaFree(h->d_G); cudaFree(h->d_B); cudaFree(h->d_Xsh);
     cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work); cudaFree(h->d_io); cudaFree(h->d_Ainv); cudaFree(h->d_Gz);
     cudaFree(h->d_WNL); cudaFree(h->d_wN); cudaFree(h->d_GzT); cudaFree(h->d_nbr_ptr); cudaFree(h->d_nbr_idx);
-    cudaFree(h->d_gstate);
+    cudaFree(h->d_gstate); cudaFree(h->d_ell_col);
     for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 3; ++i) if (h->st_io[i]) cudaStreamDestroy(h->st_io[i]);
     for (int i = 0; i < 8; ++i) if (h->ev_io[i]) cudaEventDestroy(h->ev_io[i]);
@@ -1480,6 +1531,7 @@ int hpf_set_network(hpf_t* h, int n, int m, int c, int H, const int* harmonics, 
     h->have_dev = false;
     h->struct_state = 0;
     h->host_consts_valid = false;
+    cudaFree(h->d_ell_col); h->d_ell_col = nullptr; h->ell_w = 0;
     return HPF_OK;
 }
 
@@ -1519,6 +1571,7 @@ int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
     h->have_Y = true;
     h->struct_state = 0;
     h->host_consts_valid = false;
+    cudaFree(h->d_ell_col); h->d_ell_col = nullptr; h->ell_w = 0;
     return HPF_OK;
 }
 
@@ -1531,6 +1584,7 @@ int hpf_set_Y(hpf_t* h, const double* Y) {
     h->have_Y = true;
     h->struct_state = 0;
     h->host_consts_valid = false;
+    cudaFree(h->d_ell_col); h->d_ell_col = nullptr; h->ell_w = 0;
     return HPF_OK;
 }
 
@@ -1636,7 +1690,7 @@ int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const
     ha.wN = h->d_wN;
     ha.thresh_h = 0.0; ha.max_h = 1; ha.V_m = const_cast<double*>(V_m); ha.V_a = const_cast<double*>(V_a);
     ha.I_inj = nullptr; ha.n_iter_h = nullptr; ha.status = nullptr; ha.err_h = nullptr;
-    ha.work_counter = nullptr; ha.dx_out = dx; ha.gstate = nullptr; ha.gstate_stride = 0;
+    ha.work_counter = nullptr; ha.dx_out = dx; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0;
     return launch_harm(h, net, sn, ha, false, (cudaStream_t)stream);
 }
 
@@ -1817,8 +1871,10 @@ int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, 
     LuArgs a;
     a.B = B; a.J = J; a.f = f; a.dx = dx; a.info = info; a.stride = hpf_jacobian_stride(h);
     const bool gm = !fits_smem_lu(h, net);
-    const size_t smem = gm ? gmem_kernel_smem_bytes(net.n, net.H, net.q, net.N)
+    const size_t lubd = gm ? gmem_kernel_lub_doubles(net.n, net.H, net.q, net.N, (size_t)h->smem_optin) : 0;
+    const size_t smem = gm ? (scn_smem_doubles_aligned(net.n, net.H, net.q, net.N) + lubd) * sizeof(double) + 16
                            : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
+    a.lub_doubles = (int)lubd;
     int occ = 0;
     rc = gm ? prep_kernel(h, lu_solve_kernel<true>, smem, "hpf_lu_solve", &occ, HPF_THREADS_GMEM)
             : prep_kernel(h, lu_solve_kernel<false>, smem, "hpf_lu_solve", &occ);

@@ -5,8 +5,11 @@
 // One CTA factorises one augmented matrix [A | b] that lives in GLOBAL memory (L2 resident or
 // streamed), column-major, leading dimension ld (a multiple of 2 so that two consecutive rows
 // of a column are one aligned 16-byte word).  Right-looking, panel width 32:
-//   1. panel: unblocked elimination with partial pivoting inside the 32 columns (one thread
-//      per row, the pivot search of column j+1 is fused into the update of column j);
+//   1. panel: staged in SHARED memory (panel width 32, 16 or 8, the widest whose remaining rows
+//      fit the staging buffer), unblocked elimination with partial pivoting inside it (one
+//      thread per row, the pivot search of column j+1 is fused into the update of column j);
+//      worked directly on global memory every one of the N column steps would pay ~30
+//      dependent L2 round trips;
 //   2. the 32 row interchanges and the triangular solve with L11 for every column to the
 //      right (one thread per column, 32 values in registers, L11 broadcast from smem);
 //   3. trailing update A22 -= L21 U12 on the FP64 TENSOR CORES (mma.sync m8n8k4 DMMA): L21 and
@@ -27,11 +30,21 @@
 #include <math_constants.h>
 
 #define LUB_NB 32
-#define LUB_TR 256                 // matrix rows per staged slice
+#define LUB_TR 128                 // matrix rows per staged slice
 #define LUB_TC 128                 // matrix columns per staged slice
 #define LUB_SL (LUB_TR + 4)        // smem stride of L21^T  [k][r]   (stride mod 16 == 4)
 #define LUB_SU (LUB_NB + 4)        // smem stride of U12^T  [c][k]   (stride mod 16 == 4)
-#define LUB_SMEM_DOUBLES (LUB_NB * (LUB_NB + 1) + LUB_NB * LUB_SL + LUB_TC * LUB_SU + 2 * LUB_NB + 80)
+#define LUB_FIXED_DOUBLES (LUB_NB * (LUB_NB + 1) + 2 * LUB_NB + 80)        // L11 + reduction scratch + pivots
+#define LUB_STAGE_DOUBLES (LUB_NB * LUB_SL + LUB_TC * LUB_SU)             // L21 / U12 slices (minimum)
+#define LUB_SMEM_DOUBLES (LUB_FIXED_DOUBLES + LUB_STAGE_DOUBLES)          // minimum work area
+// work area that lets an N-row system run with the widest possible panels, capped at `cap` bytes
+__host__ __device__ inline size_t lub_smem_doubles_for(int N, size_t cap_bytes) {
+    size_t want = (size_t)LUB_FIXED_DOUBLES + (size_t)(N + 1) * LUB_NB;
+    const size_t mn = LUB_SMEM_DOUBLES, mx = cap_bytes / sizeof(double);
+    if (want < mn) want = mn;
+    if (want > mx) want = mx > mn ? mx : mn;
+    return want;
+}
 
 __host__ __device__ inline int lub_ld(int N) { return (N + 7) & ~7; }
 
@@ -67,57 +80,74 @@ __device__ __forceinline__ void lub_argmax(double& best, int& bi, double* redv, 
     bi = redi[32];
 }
 
-// A: N x (N+1) column-major in global memory, ld even; sm: >= LUB_SMEM_DOUBLES doubles of
-// SHARED memory; sflag: one int of shared memory.
+// A: N x (N+1) column-major in global memory, ld even; sm: sm_doubles >= LUB_SMEM_DOUBLES doubles
+// of SHARED memory (more = wider panels for large N); sflag: one int of shared memory.
 __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N, const int ld,
-                                             double* sm, int* sflag) {
+                                             double* sm, const int sm_doubles, int* sflag) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
     double* L11 = sm;                                   // [NB][NB+1]  L11[r][c]
-    double* Ls = L11 + LUB_NB * (LUB_NB + 1);           // [NB][SL]    Ls[k][r] = L21[r][k]
-    double* Us = Ls + LUB_NB * LUB_SL;                  // [TC][SU]    Us[c][k] = -U12[k][c]
-    double* redv = Us + LUB_TC * LUB_SU;                // 33
+    double* redv = L11 + LUB_NB * (LUB_NB + 1);         // 33
     int* redi = reinterpret_cast<int*>(redv + 34);      // 33 ints
     int* piv = redi + 34;                               // NB ints
+    double* stage = sm + LUB_FIXED_DOUBLES;             // panel staging | L21 / U12 slices
+    const int stage_doubles = sm_doubles - LUB_FIXED_DOUBLES;
+    double* Ls = stage;                                 // [NB][SL]    Ls[k][r] = L21[r][k]
+    double* Us = Ls + LUB_NB * LUB_SL;                  // [TC][SU]    Us[c][k] = -U12[k][c]
+    double* Pn = stage;                                 // [nb][rows]  panel, column-major
     if (tid == 0) *sflag = 0;
     __syncthreads();
 
-    for (int k0 = 0; k0 < N; k0 += LUB_NB) {
-        const int nb = min(LUB_NB, N - k0);
+    for (int k0 = 0; k0 < N;) {
+        const int rows = N - k0;
+        int nbw = LUB_NB;                               // widest panel whose rows fit the stage
+        while (nbw > 8 && (size_t)rows * nbw > (size_t)stage_doubles) nbw >>= 1;
+        const bool staged = (size_t)rows * nbw <= (size_t)stage_doubles;
+        const int nb = min(nbw, N - k0);
         // ---------------- 1. panel ----------------
         {
+            // panel element (row i, panel column j) at PB[j * ps + i - k0]
+            double* PB = staged ? Pn : A + (size_t)k0 * ld + k0;
+            const size_t ps = staged ? (size_t)rows : (size_t)ld;
+            if (staged) {
+                for (int t = tid; t < rows * nb; t += nthr) {
+                    const int j = t / rows, i = t - j * rows;
+                    Pn[t] = A[(size_t)(k0 + j) * ld + k0 + i];
+                }
+                __syncthreads();
+            }
             // pivot of the first column
             double best = -1.0;
-            int bi = k0;
-            for (int i = k0 + tid; i < N; i += nthr) {
-                const double v = fabs(A[(size_t)k0 * ld + i]);
+            int bi = 0;
+            for (int i = tid; i < rows; i += nthr) {
+                const double v = fabs(PB[i]);
                 if (v > best) { best = v; bi = i; }
             }
             lub_argmax(best, bi, redv, redi);
             for (int j = 0; j < nb; ++j) {
-                const int kc = k0 + j;
-                const int p = bi;
+                const int p = bi;                               // panel-relative row of the pivot
                 if (!(best > 0.0) || !(best < CUDART_INF)) {
-                    if (tid == 0 && *sflag == 0) *sflag = kc + 1;
+                    if (tid == 0 && *sflag == 0) *sflag = k0 + j + 1;
                 }
-                if (tid == 0) piv[j] = p;
-                if (p != kc && tid < nb) {                      // swap inside the panel
-                    double* c0 = A + (size_t)(k0 + tid) * ld;
-                    const double t = c0[kc];
-                    c0[kc] = c0[p];
+                if (tid == 0) piv[j] = k0 + p;
+                if (p != j && tid < nb) {                       // swap inside the panel
+                    double* c0 = PB + (size_t)tid * ps;
+                    const double t = c0[j];
+                    c0[j] = c0[p];
                     c0[p] = t;
                 }
                 __syncthreads();
-                const double r = 1.0 / A[(size_t)kc * ld + kc];
-                // scale column kc, rank-1 update of the panel columns to its right; the new
-                // column kc+1 feeds the next pivot search
+                double* cj0 = PB + (size_t)j * ps;
+                const double r = 1.0 / cj0[j];
+                // scale column j, rank-1 update of the panel columns to its right; the new
+                // column j+1 feeds the next pivot search
                 best = -1.0;
-                bi = kc + 1;
-                for (int i = kc + 1 + tid; i < N; i += nthr) {
-                    const double l = A[(size_t)kc * ld + i] * r;
-                    A[(size_t)kc * ld + i] = l;
+                bi = j + 1;
+                for (int i = j + 1 + tid; i < rows; i += nthr) {
+                    const double l = cj0[i] * r;
+                    cj0[i] = l;
                     for (int jj = j + 1; jj < nb; ++jj) {
-                        double* cj = A + (size_t)(k0 + jj) * ld;
-                        const double v = cj[i] - l * cj[kc];
+                        double* cj = PB + (size_t)jj * ps;
+                        const double v = cj[i] - l * cj[j];
                         cj[i] = v;
                         if (jj == j + 1) {
                             const double av = fabs(v);
@@ -128,9 +158,15 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
                 if (j + 1 < nb) lub_argmax(best, bi, redv, redi);   // (contains the barriers)
                 else __syncthreads();
             }
+            if (staged) {
+                for (int t = tid; t < rows * nb; t += nthr) {
+                    const int j = t / rows, i = t - j * rows;
+                    A[(size_t)(k0 + j) * ld + k0 + i] = Pn[t];
+                }
+                __syncthreads();
+            }
         }
         const int cr = k0 + nb;                                  // first row / column of the trailing part
-        if (cr > N) break;
         // L11 -> smem
         for (int t = tid; t < nb * nb; t += nthr) {
             const int c = t / nb, r = t - c * nb;
@@ -201,8 +237,9 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
                         }
                     const double* us = Us + (sc * 32 + fr) * LUB_SU + fk;
                     const double* ls = Ls + fk * LUB_SL + sr * 32 + fr;
-#pragma unroll
-                    for (int kk = 0; kk < LUB_NB; kk += 4) {
+                    const int nbk = (nb + 3) & ~3;               // (rows k >= nb of the slices are zero)
+#pragma unroll 2
+                    for (int kk = 0; kk < nbk; kk += 4) {
                         double af[4], bf[4];
 #pragma unroll
                         for (int ic = 0; ic < 4; ++ic) af[ic] = us[(8 * ic) * LUB_SU + kk];
@@ -230,6 +267,7 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
             }
             __syncthreads();                                     // before Ls is overwritten
         }
+        k0 = cr;
     }
     __syncthreads();
     // ---------------- 4. blocked back substitution U x = y (y = column N) ----------------

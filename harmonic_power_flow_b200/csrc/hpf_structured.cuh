@@ -608,6 +608,7 @@ struct HarmTileArgs {
     double* dx_out;          // step_only: [N, B] the Newton update dx (x_new = x - dx)
     double* gstate;          // per-CTA kernel, large networks: scenario state in global memory
     size_t gstate_stride;    //   doubles per CTA (0: state in shared memory)
+    int lub_doubles;         //   shared-memory work area of the blocked LU (doubles)
 };
 
 
