@@ -71,6 +71,89 @@ def load_net():
     return net
 
 
+def load_other(kind):
+    """Networks of the other BASELINE configurations through the product's own CSV loaders:
+    'net2ev' (configs[1]: net2 with an SMPS and an EV Norton-equivalent load, odd harmonics to the
+    19th), 'radial200' (configs[3]) and 'meshed1000' (configs[4]) from the seeded generators."""
+    import tempfile
+    import numpy as np
+    import pandas as pd
+    from harmonic_power_flow_b200 import netio, synthetic
+    g = os.path.join(ROOT, "tests", "golden")
+    tmp = tempfile.mkdtemp(prefix="hpf_bench_")
+    dev = np.load(os.path.join(g, "ne_devices.npz"))
+    for d in ("smps", "ev"):
+        netio.write_ne_csv(os.path.join(tmp, d + "_NE.csv"), dev[d + "__freqs"], dev[d + "__Y_N_c"],
+                           dev[d + "__I_N_c"], dev[d + "__Y_N_uc"], dev[d + "__I_N_uc"])
+    if kind == "net2ev":
+        tab = json.load(open(os.path.join(g, "networks.json")))["net2ev"]
+        pb, pl = os.path.join(tmp, "net2ev_buses.csv"), os.path.join(tmp, "net2ev_lines.csv")
+        pd.DataFrame(tab["buses"]).to_csv(pb, sep=";", index=False)
+        pd.DataFrame(tab["lines"]).to_csv(pl, sep=";", index=False)
+        h_max = 19
+    elif kind == "radial200":
+        pb, pl = synthetic.radial_feeder(tmp, tmp, n=200, load_scale=0.005)
+        h_max = 25
+    else:
+        pb, pl = synthetic.meshed(tmp, tmp, n=1000, load_scale=0.002)
+        h_max = 25
+    st = netio.Settings(H_MAX=h_max, ne_dir=tmp)
+    buses, lines, m, n, c = netio.init_network(pb, pl, st)
+    NE = netio.import_Norton_Equivalents(buses, True, st)
+    return netio.pack_network(buses, lines, m, n, c, st.HARMONICS, NE, True)
+
+
+OTHER_CONFIGS = [
+    ("configs[1]: net2 + SMPS/EV Norton loads, odd harmonics <= 19 (N=78)", "net2ev", 1024, 3),
+    ("configs[3]: synthetic 200-bus radial feeder, 40% nonlinear buses, odd harmonics <= 25 (N=5198)",
+     "radial200", 8192, 2),
+    ("configs[4]: synthetic 1000-bus meshed network, 40% nonlinear buses, full coupled Norton, odd "
+     "harmonics <= 25 (N=25998)", "meshed1000", 1024, 1),
+]
+
+
+def run_other_configs(torch, dist, BatchSolver, scenarios, local, rank, world):
+    """Device-resident solves/s of the other BASELINE configurations (weak scaling like the
+    headline: every rank solves its own block of scenarios of the same network).  The operator
+    set-up (once per network) is timed separately."""
+    out = []
+    for label, kind, B, steps in OTHER_CONFIGS:
+        net = load_other(kind)
+        sol = BatchSolver(net, local)
+        t0 = time.perf_counter()
+        info = sol.struct_info()
+        torch.cuda.synchronize()
+        t_setup = time.perf_counter() - t0
+        P, Q, I_N = scenarios.make_batch(net, B, SPREAD, seed0=rank * B, exact_prefix=8)
+        dP, dQ, dI = sol.prepare(P, Q, I_N)
+        r = sol.solve(dP, dQ, dI)                                   # warm-up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = sol.solve(dP, dQ, dI, out=r)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        vals = torch.tensor([ms, float((r.status == 0).sum().item()), r.n_iter_h.double().sum().item()],
+                            dtype=torch.float64, device=r.status.device)
+        if world > 1:
+            mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        else:
+            mx, sm = vals, vals
+        out.append({"config": label, "batch_per_gpu": B, "N": int(sol.N), "strategy_variant": int(info["available"]),
+                    "value": sm[1].item() / (mx[0].item() / 1e3), "unit": UNIT, "ms_per_step": mx[0].item(),
+                    "converged_fraction": sm[1].item() / (B * world),
+                    "mean_harmonic_iterations": sm[2].item() / (B * world),
+                    "operator_setup_s": t_setup})
+        sol.close()
+        del sol, r, dP, dQ, dI
+        torch.cuda.empty_cache()
+    return out
+
+
 def config_dict(n_gpus):
     return {"workload": "BASELINE configs[2]: net3 coupled (smps_NE), fundamental + odd harmonics <= 25 "
                         "(N=101), randomised load/spectrum scenarios (P,Q x U(0.9,1.1), I_N x U(0.95,1.05) "
@@ -394,6 +477,11 @@ def run_ours(a):
                         "achieved": fl_lu * Bj / t_lu / 1e9, "peak": fp64_peak, "unit": "TFLOP/s",
                         "frac": fl_lu * Bj / t_lu / 1e9 / fp64_peak, "flops_per_scenario": fl_lu})
 
+    # ---- the other BASELINE configurations (all ranks, weak scaling) ----
+    other = None
+    if not a.no_other:
+        other = run_other_configs(torch, dist, BatchSolver, scenarios, local, rank, world)
+
     # ---- reduce over ranks ----
     vals = torch.tensor([ms, t_e2e, float(conv), float(conv_e2e), it_h, it_f, t_wall], dtype=torch.float64, device=dev)
     if world > 1:
@@ -454,6 +542,8 @@ def run_ours(a):
                              "hbm_bytes_per_scenario": by_solve,
                              "hbm_gbs_of_whole_solve": by_solve * B / (ms / a.steps) / 1e6},
                 "roofline_kernels": kernels, "hbm_peak_source": hbm_src}
+        if other is not None:
+            line["other_configs"] = other
         if dense_info is not None:
             fld = dense_info["it_h"] * fl_dense + dense_info["it_f"] * fl_f
             achd = fld / (dense_info["kernel_ms"] / 1e3) / 1e12
@@ -490,6 +580,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="scenarios per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-LU comparison leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the other BASELINE configurations")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
