@@ -15,7 +15,7 @@ HPF_OK, HPF_E_INVALID, HPF_E_CUDA, HPF_E_UNSUPPORTED, HPF_E_NOMEM = 0, -1, -2, -
 ST_CONVERGED, ST_MAXITER, ST_SINGULAR, ST_NONFINITE = 0, 1, 2, 3
 SOLVE_RAW = 1
 SOLVE_DENSE = 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
 _ip, _dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -44,6 +44,7 @@ SIGNATURES = {
     "hpf_jacobian": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "hpf_jacobian_stride": (_ll, [_vp]),
     "hpf_lu_solve": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hpf_ne_extract": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hpf_dim_N": (_i, [_vp]),
     "hpf_dim_Nf": (_i, [_vp]),
     "hpf_launch_count": (_ll, [_vp]),

@@ -20,6 +20,7 @@
 #include "hpf_device.cuh"
 #include "hpf_structured.cuh"
 #include "hpf_lu_blocked.cuh"
+#include "hpf_ne_extract.cuh"
 
 #define HPF_THREADS 256
 #define HPF_TILE 32          // scenarios per CTA in the tile kernels
@@ -1694,6 +1695,32 @@ int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const
     return launch_harm(h, net, sn, ha, false, (cudaStream_t)stream);
 }
 
+int hpf_ne_extract(hpf_t* h, int D, int N, const double* Vf, const double* Vh, const double* I_f,
+                   const double* I_h, double* Y_N_c, double* I_N_c, double* Y_N_uc, double* I_N_uc,
+                   int* info, void* stream) {
+    if (!h) return HPF_E_INVALID;
+    if (D <= 0) return D == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_ne_extract: D < 0");
+    if (N < 2) return fail(h, HPF_E_INVALID, "hpf_ne_extract: at least 2 frequencies needed");
+    if (!Vf || !Vh || !I_f || !I_h || !Y_N_c || !I_N_c || !Y_N_uc || !I_N_uc || !info)
+        return fail(h, HPF_E_INVALID, "hpf_ne_extract: NULL buffer");
+    CK(cudaSetDevice(h->device));
+    const size_t smem = ne_extract_smem_bytes(N);
+    int occ = 0;
+    int rc = prep_kernel(h, ne_extract_kernel, smem, "hpf_ne_extract", &occ, 256);
+    if (rc) return rc;
+    NeExtractArgs a;
+    a.D = D; a.N = N;
+    a.Vf = (const double2*)Vf; a.Vh = (const double2*)Vh; a.I_f = (const double2*)I_f; a.I_h = (const double2*)I_h;
+    a.Y_N_c = (double2*)Y_N_c; a.I_N_c = (double2*)I_N_c; a.Y_N_uc = (double2*)Y_N_uc; a.I_N_uc = (double2*)I_N_uc;
+    a.info = info;
+    long long grid = (long long)occ * h->sm_count;
+    if (grid > D) grid = D;
+    ne_extract_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
 int hpf_fund_solve(hpf_t* h, int B, const double* P, const double* Q, double thresh_f, int max_iter_f,
                    double* V_m, double* V_a, int* n_iter_f, double* err_f, double* err_hist_f,
                    void* stream) {
@@ -1716,6 +1743,7 @@ int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const doub
     // copies into compact [rows, Bc] device arrays (pinned host memory makes them asynchronous).
     const size_t n = h->n, H = h->H, q = h->q, Bs = (size_t)B;
     int nchunk = (B >= 32768) ? 4 : (B >= 8192 ? 2 : 1);
+    if (const char* ev = getenv("HPF_HOST_CHUNKS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) nchunk = v; }
     const size_t Bc_max = ((Bs + nchunk - 1) / nchunk + 31) / 32 * 32;
     nchunk = (int)((Bs + Bc_max - 1) / Bc_max);
     // per chunk (compact): P, Q [n] | I_N [2qH] | V_m, V_a [nH] | I_inj [2qH] | err [1] | 3 ints

@@ -297,3 +297,36 @@ class BatchSolver:
         _lib.check(self._h, self.lib.hpf_lu_solve(self._h, B, _ptr(J), _ptr(f), _ptr(dx), _ptr(info),
                                                   self._stream()))
         return dx, info
+
+
+def ne_extract(Vf, Vh, I_f, I_h, device=0):
+    """Norton-equivalent extraction for a batch of devices (hpf_ne_extract): Vf [D,2], Vh [D,2,K],
+    I_f [D,2,N], I_h [D,2,K,N] complex -> dict of device tensors Y_N_c [D,N,N], I_N_c, Y_N_uc,
+    I_N_uc [D,N] (complex128) and info [D] (int32)."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("harmonic_power_flow_b200 needs a CUDA device (B200); no CPU fallback")
+    dev = torch.device("cuda", int(device))
+    c = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.complex128)).to(dev).contiguous() \
+        if not isinstance(a, torch.Tensor) else a.to(dev, torch.complex128).contiguous()
+    Vf, Vh, I_f, I_h = c(Vf), c(Vh), c(I_f), c(I_h)
+    D, K = Vh.shape[0], Vh.shape[2]
+    N = K + 1
+    if Vf.shape != (D, 2) or Vh.shape != (D, 2, K) or I_f.shape != (D, 2, N) or I_h.shape != (D, 2, K, N):
+        raise ValueError("ne_extract: inconsistent shapes")
+    out = {"Y_N_c": torch.empty((D, N, N), dtype=torch.complex128, device=dev),
+           "I_N_c": torch.empty((D, N), dtype=torch.complex128, device=dev),
+           "Y_N_uc": torch.empty((D, N), dtype=torch.complex128, device=dev),
+           "I_N_uc": torch.empty((D, N), dtype=torch.complex128, device=dev),
+           "info": torch.empty(D, dtype=torch.int32, device=dev)}
+    h = C.c_void_p()
+    _lib.check(None, lib.hpf_create(C.byref(h), dev.index))
+    try:
+        _lib.check(h, lib.hpf_ne_extract(h, D, N, _ptr(Vf), _ptr(Vh), _ptr(I_f), _ptr(I_h), _ptr(out["Y_N_c"]),
+                                         _ptr(out["I_N_c"]), _ptr(out["Y_N_uc"]), _ptr(out["I_N_uc"]),
+                                         _ptr(out["info"]),
+                                         C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        torch.cuda.current_stream(dev).synchronize()
+    finally:
+        lib.hpf_destroy(h)
+    return out

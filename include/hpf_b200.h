@@ -55,7 +55,7 @@ typedef struct hpf_handle hpf_t;
 #define HPF_ST_NONFINITE    3   /* NaN/Inf in the mismatch or the state            */
 
 /* ABI version of this header: bumped on any signature change. */
-#define HPF_ABI_VERSION 4
+#define HPF_ABI_VERSION 5
 int hpf_abi_version(void);
 
 /* Lifetime.  `device` is the CUDA ordinal the handle is bound to. */
@@ -199,6 +199,24 @@ int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a,
  *   in : V_m [H, n, B];  out: thd [2, n, B]  (plane 0 = THD_F, plane 1 = THD_R)
  */
 int hpf_thd(hpf_t* h, int B, const double* V_m, double* thd, void* stream);
+
+/*
+ * Before the path - Norton-equivalent extraction from simulated measurements, the arithmetic of
+ * the reference's "Circuit Simulation/NE_from_sim.py" (NE): uncoupled two-point equivalents
+ * (NE:86-118) and the coupled equivalent (NE:141-173: one (N+1) x (N+1) complex system with N
+ * right-hand sides per device), for D devices / operating points at once.  Needs no network
+ * (hpf_create only).  All pointers device memory, complex128 interleaved, K = N - 1 supply
+ * harmonics, frequency index 0 = fundamental:
+ *   in : Vf [D, 2]        fundamental supply phasor of the two fundamental-only measurements
+ *        Vh [D, 2, K]     harmonic supply phasor, magnitude set 1 / 2, per supply frequency
+ *        I_f [D, 2, N]    injected-current spectra of the fundamental-only measurements
+ *        I_h [D, 2, K, N] spectra with the harmonic source at frequency k+1, magnitude set 1 / 2
+ *   out: Y_N_c [D, N, N] (row = harmonic of the current, column = harmonic of the voltage),
+ *        I_N_c [D, N], Y_N_uc [D, N], I_N_uc [D, N]; info int32 [D] (0, or k+1: zero pivot)
+ */
+int hpf_ne_extract(hpf_t* h, int D, int N, const double* Vf, const double* Vh, const double* I_f,
+                   const double* I_h, double* Y_N_c, double* I_N_c, double* Y_N_uc, double* I_N_uc,
+                   int* info, void* stream);
 
 /*
  * Per-kernel device timing of hpf_solve (for roofline accounting): when enabled, CUDA events

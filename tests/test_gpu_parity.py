@@ -610,3 +610,63 @@ def test_config4_radial_200_bus_against_oracle(tmp_path):
     part = sol.solve(P[:, 100:190].copy(), Q[:, 100:190].copy(), I_N[:, :, 100:190].copy()).to_host()
     assert np.array_equal(part["V_m"], res["V_m"][:, :, 100:190]) and np.array_equal(part["n_iter_h"], res["n_iter_h"][100:190])
     sol.close()
+
+
+# ---------------------------------------------------------------- Norton-equivalent extraction (next-1)
+@pytest.mark.parametrize("name", ["smps", "circuit_sim"])
+def test_ne_extract_matches_reference_script(name):
+    """hpf_ne_extract against the reference's own NE_from_sim.py outputs (golden fixtures)."""
+    from harmonic_power_flow_b200 import ne_from_sim
+    import os
+    d = np.load(os.path.join(GOLDEN, "ne_extract_%s.npz" % name))
+    sim = ne_from_sim.Simulation(d["freq"], d["Vf"], d["Vh"], d["I_f"], d["I_h"])
+    ne = ne_from_sim.get_NE_from_sim(sim)
+    for k in ("Y_N_c", "I_N_c", "Y_N_uc", "I_N_uc"):
+        assert np.abs(ne[k] - d[k]).max() <= 1e-12 * np.abs(d[k]).max(), k
+
+
+def test_ne_extract_batch_round_trip_and_csv(tmp_path):
+    """64 perturbed SMPS devices with 26 frequencies: measurements synthesised from a known coupled
+    Norton equivalent (forward model HG:313-323), extracted on the GPU in one launch; the
+    extraction must return the equivalents it started from, agree with the oracle, flag a
+    singular measurement set, and survive the CSV round trip into the solve path's loader."""
+    import ne_oracle as NO
+    from harmonic_power_flow_b200 import ne_from_sim, netio
+    import os
+    dev = np.load(os.path.join(GOLDEN, "ne_devices.npz"))
+    N, D = 26, 64
+    rng = np.random.default_rng(7)
+    freq = dev["smps__freqs"][:N]
+    sims, truth = [], []
+    for s in range(D):
+        Y = dev["smps__Y_N_c"][:N, :N] * (1 + 0.1 * rng.standard_normal((N, N))) * np.exp(0.1j * rng.standard_normal((N, N)))
+        I = dev["smps__I_N_c"][:N] * (1 + 0.1 * rng.standard_normal(N))
+        Vf = 230.0 * np.sqrt(2) * np.array([1.0, np.exp(1j * 0.05)])
+        Vh = np.array([np.full(N - 1, 2.3), np.full(N - 1, 4.6)]) * np.exp(1j * rng.uniform(-0.2, 0.2))
+        if s == 9:
+            Vh[0][0] = 0.0                      # no harmonic excitation at freq[1]: a zero column -> singular
+        I_f, I_h = NO.synth_measurements(Y, I, Vf, Vh)
+        sims.append(ne_from_sim.Simulation(freq, Vf, Vh, I_f, I_h)); truth.append((Y, I))
+    from harmonic_power_flow_b200.solver import ne_extract
+    out = {k: v.cpu().numpy() for k, v in ne_extract(np.stack([s.Vf for s in sims]), np.stack([s.Vh for s in sims]),
+                                                      np.stack([s.I_f for s in sims]), np.stack([s.I_h for s in sims])).items()}
+    assert out["info"][9] != 0 and (np.delete(out["info"], 9) == 0).all()
+    with pytest.raises(np.linalg.LinAlgError):
+        ne_from_sim.get_NE_from_sim(sims)
+    for s in range(D):
+        if s == 9:
+            continue
+        Y, I = truth[s]
+        assert np.abs(out["Y_N_c"][s] - Y).max() <= 1e-9 * np.abs(Y).max()
+        assert np.abs(out["I_N_c"][s] - I).max() <= 1e-9 * np.abs(I).max()
+        Yo, Io = NO.coupled(sims[s].Vf, sims[s].Vh, sims[s].I_f, sims[s].I_h)
+        Yuo, Iuo = NO.uncoupled(sims[s].Vf, sims[s].Vh, sims[s].I_f, sims[s].I_h)
+        assert np.abs(out["Y_N_c"][s] - Yo).max() <= 1e-10 * np.abs(Yo).max()
+        assert np.abs(out["Y_N_uc"][s] - Yuo).max() <= 1e-12 * np.abs(Yuo).max()
+        assert np.abs(out["I_N_uc"][s] - Iuo).max() <= 1e-12 * np.abs(Iuo).max()
+    ne0 = {k: out[k][0] for k in ("Y_N_c", "I_N_c", "Y_N_uc", "I_N_uc")}
+    path = os.path.join(str(tmp_path), "dev0_NE.csv")
+    ne_from_sim.export_NE(path, freq, ne0)
+    tab = netio.read_ne_csv(path)
+    assert np.array_equal(tab.loc["I_N_c"].to_numpy().ravel(), ne0["I_N_c"])
+    assert np.array_equal(tab.loc[("Y_N_c", list(freq)), list(freq)].to_numpy(), ne0["Y_N_c"])

@@ -110,3 +110,22 @@ def test_oracle_scenario_sets(name):
     assert mism <= floor_mism + 1
     assert (rel > 1e-9).sum() <= (floor > 1e-9).sum() + 2
     assert np.median(rel) < 1e-11
+
+
+# ---------------------------------------------------------------- Norton-equivalent extraction (next-1)
+@pytest.mark.parametrize("name", ["smps", "circuit_sim"])
+def test_ne_oracle_matches_reference_script(name):
+    """oracle/ne_oracle.py against the outputs of the reference's own NE_from_sim.py on the
+    simulation files that ship with the reference (fixtures from oracle/make_golden_ne.py)."""
+    import ne_oracle as NO
+    d = np.load(os.path.join(GOLDEN, "ne_extract_%s.npz" % name))
+    assert "passed consistency test" in str(d["ref_stdout"])
+    Yuc, Iuc = NO.uncoupled(d["Vf"], d["Vh"], d["I_f"], d["I_h"])
+    Yc, Ic = NO.coupled(d["Vf"], d["Vh"], d["I_f"], d["I_h"])
+    for got, want in ((Yuc, d["Y_N_uc"]), (Iuc, d["I_N_uc"]), (Yc, d["Y_N_c"]), (Ic, d["I_N_c"])):
+        assert np.abs(got - want).max() <= 1e-14 * np.abs(want).max()
+    # the extracted model reproduces every measurement it was built from (NE:176-186)
+    N = len(d["freq"])
+    for k in range(N - 1):
+        v = np.zeros(N, dtype=complex); v[0] = d["Vf"][0]; v[k + 1] = d["Vh"][0][k]
+        assert np.abs(NO.forward(Yc, Ic, v) - d["I_h"][0][k]).max() <= 1e-9 * np.abs(d["I_h"][0][k]).max()
