@@ -104,7 +104,80 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
         const bool staged = (size_t)rows * nbw <= (size_t)stage_doubles;
         const int nb = min(nbw, N - k0);
         // ---------------- 1. panel ----------------
-        {
+        if (nb == LUB_NB && rows <= nthr) {
+            // REGISTER panel: thread t owns one row of the panel (32 values in registers) for all
+            // 32 column steps.  Row interchanges move no data: every thread tracks the panel
+            // position `pos` of its row (swap k <-> p: the two owners exchange positions).  Per
+            // column step: block argmax (one barrier, every warp reduces the partials redundantly),
+            // the pivot row is published through shared memory (second barrier), the active rows
+            // update with 31 register FMAs.  (On shared / global memory every step pays ~30
+            // dependent round trips per row.)
+            double* prow = stage;                                // [32] current pivot row
+            double v[LUB_NB];
+            int pos = (tid < rows) ? tid : -1;
+            if (pos >= 0) {
+#pragma unroll
+                for (int j = 0; j < LUB_NB; ++j) v[j] = A[(size_t)(k0 + j) * ld + k0 + tid];
+            } else {
+#pragma unroll
+                for (int j = 0; j < LUB_NB; ++j) v[j] = 0.0;
+            }
+            const int aw = (rows + 31) >> 5;                     // warps that own rows
+#pragma unroll
+            for (int j = 0; j < LUB_NB; ++j) {
+                double best = -1.0;
+                int bi = 0x7fffffff;
+                if (warp < aw) {                                 // (the other warps only keep the barriers)
+                    best = (pos >= j) ? fabs(v[j]) : -1.0;
+                    bi = (pos >= j) ? pos : 0x7fffffff;
+                    if (best != best) best = CUDART_INF;         // a NaN candidate must surface as a bad pivot
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                    }
+                    if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
+                }
+                __syncthreads();
+                if (warp < aw) {
+                    // every row-owning warp reduces the partials redundantly (no second barrier)
+                    best = (lane < aw) ? redv[lane] : -1.0;
+                    bi = (lane < aw) ? redi[lane] : 0x7fffffff;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                    }
+                    best = __shfl_sync(0xffffffffu, best, 0);
+                    bi = __shfl_sync(0xffffffffu, bi, 0);
+                }
+                const int p = bi;
+                if (!(best > 0.0) || !(best < CUDART_INF)) {
+                    if (tid == 0 && *sflag == 0) *sflag = k0 + j + 1;
+                }
+                if (tid == 0) piv[j] = k0 + p;
+                if (pos == p) pos = j;
+                else if (pos == j) pos = p;
+                if (pos == j) {
+#pragma unroll
+                    for (int jj = j; jj < LUB_NB; ++jj) prow[jj] = v[jj];
+                }
+                __syncthreads();
+                if (pos > j) {
+                    const double l = v[j] * (1.0 / prow[j]);
+                    v[j] = l;
+#pragma unroll
+                    for (int jj = j + 1; jj < LUB_NB; ++jj) v[jj] = fma(-l, prow[jj], v[jj]);
+                }
+            }
+            if (pos >= 0) {
+#pragma unroll
+                for (int j = 0; j < LUB_NB; ++j) A[(size_t)(k0 + j) * ld + k0 + pos] = v[j];
+            }
+            __syncthreads();
+        } else {
             // panel element (row i, panel column j) at PB[j * ps + i - k0]
             double* PB = staged ? Pn : A + (size_t)k0 * ld + k0;
             const size_t ps = staged ? (size_t)rows : (size_t)ld;
