@@ -341,79 +341,3 @@ __device__ __forceinline__ int lu_solve_smem(double* A, const int N, const int l
     __syncthreads();
     return *sflag;
 }
-
-// ---------------------------------------------------------------------------------------
-// Generic fallback for systems that do not fit the shared-memory kernel (N > 192 or
-// ld*(N+1) doubles > shared memory): same algorithm (partial pivoting, augmented rhs), the
-// matrix lives in a per-CTA global-memory workspace (L2 resident), any N, any block size.
-// `red` is a shared-memory scratch of >= 2*32 + 2 doubles.
-__device__ __forceinline__ int lu_solve_any(double* A, const int N, const int ld, double* rinv,
-                                            int* sflag, double* red) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = (blockDim.x + 31) >> 5;
-    int* redi = reinterpret_cast<int*>(red + 33);
-    if (tid == 0) *sflag = 0;
-    for (int k = 0; k < N; ++k) {
-        __syncthreads();
-        double* colk = A + (size_t)k * ld;
-        double best = -1.0;
-        int bi = k;
-        for (int i = k + tid; i < N; i += blockDim.x) {
-            const double v = fabs(colk[i]);
-            if (v > best) { best = v; bi = i; }
-        }
-        for (int o = 16; o; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if (lane == 0) { red[warp] = best; redi[warp] = bi; }
-        __syncthreads();
-        if (warp == 0) {
-            best = (lane < nw) ? red[lane] : -1.0;
-            bi = (lane < nw) ? redi[lane] : 0x7fffffff;
-            for (int o = 16; o; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
-            if (lane == 0) {
-                red[32] = best;
-                redi[32] = bi;
-                if ((!(best > 0.0) || !(best < CUDART_INF)) && *sflag == 0) *sflag = k + 1;
-            }
-        }
-        __syncthreads();
-        const int p = redi[32];
-        // swap rows k <-> p in columns k..N
-        if (p != k)
-            for (int j = k + tid; j <= N; j += blockDim.x) {
-                double* cj = A + (size_t)j * ld;
-                const double t = cj[k];
-                cj[k] = cj[p];
-                cj[p] = t;
-            }
-        __syncthreads();
-        const double r = 1.0 / colk[k];
-        __syncthreads();
-        if (tid == 0) rinv[k] = r;
-        for (int i = k + 1 + tid; i < N; i += blockDim.x) colk[i] *= r;
-        __syncthreads();
-        const int rows = N - k - 1, cols = N - k;        // columns k+1..N
-        for (int t = tid; t < rows * cols; t += blockDim.x) {
-            const int jj = t / rows, ii = t - jj * rows;
-            double* cj = A + (size_t)(k + 1 + jj) * ld;
-            cj[k + 1 + ii] -= colk[k + 1 + ii] * cj[k];
-        }
-    }
-    __syncthreads();
-    double* b = A + (size_t)N * ld;
-    for (int j = N - 1; j >= 0; --j) {
-        const double xj = b[j] * rinv[j];
-        __syncthreads();
-        if (tid == 0) b[j] = xj;
-        const double* cj = A + (size_t)j * ld;
-        for (int i = tid; i < j; i += blockDim.x) b[i] -= cj[i] * xj;
-        __syncthreads();
-    }
-    return *sflag;
-}
