@@ -154,6 +154,23 @@ def run_other_configs(torch, dist, BatchSolver, scenarios, local, rank, world):
     return out
 
 
+def ncu_traffic(kernel_substr):
+    """DRAM bytes (read + write) of one launch of a kernel from the committed ncu --set full summary
+    (profiles/r1_ncu_kernels.csv), or None.  ncu numbers are per launch at the BASELINE batch."""
+    import csv
+    try:
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_kernels.csv"))))
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        for r in rows[2:]:
+            if kernel_substr in r[0]:
+                return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+    except Exception:
+        pass
+    return None
+
+
 def config_dict(n_gpus):
     return {"workload": "BASELINE configs[2]: net3 coupled (smps_NE), fundamental + odd harmonics <= 25 "
                         "(N=101), randomised load/spectrum scenarios (P,Q x U(0.9,1.1), I_N x U(0.95,1.05) "
@@ -464,6 +481,7 @@ def run_ours(a):
                         "ms": t_mis,
                         "achieved": by_mis * B / t_mis / 1e6, "peak": hbm_peak, "unit": "GB/s",
                         "frac": by_mis * B / t_mis / 1e6 / hbm_peak, "bytes_per_scenario": by_mis,
+                        "traffic": ncu_traffic("mismatch_lane_kernel"),
                         "timing": "CUDA graph of 12 launches over 3 rotating buffer sets (372 MB > L2), best of 5 replays"})
         Bj = min(B, 16384)
         Vmj, Vaj = Vm[:, :, :Bj].contiguous(), Va[:, :, :Bj].contiguous()
@@ -474,7 +492,8 @@ def run_ours(a):
         by_jac = 8 * N * N + 16 * n * H
         kernels.append({"kernel": "jacobian_kernel", "bound": "hbm", "ms": t_jac, "batch": Bj,
                         "achieved": by_jac * Bj / t_jac / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": by_jac * Bj / t_jac / 1e6 / hbm_peak, "bytes_per_scenario": by_jac})
+                        "frac": by_jac * Bj / t_jac / 1e6 / hbm_peak, "bytes_per_scenario": by_jac,
+                        "traffic": ncu_traffic("jacobian_kernel")})
         f, _ = sol.mismatch(Vmj, Vaj, dP[:, :Bj].contiguous(), dQ[:, :Bj].contiguous(), dI[:, :, :Bj].contiguous())
         t_lu = timed([lambda: sol.lu_solve(J, f)], reps=3)
         fl_lu = 2.0 / 3.0 * N ** 3 + 2.0 * N * N
@@ -540,7 +559,9 @@ def run_ours(a):
                                  "results (rank-major) overlapped with the D2H of the rank's own results")},
                 "roofline": {"kernel": kname, "bound": "fp64", "achieved": ach, "peak": fp64_peak,
                              "unit": "TFLOP/s", "frac": (ach / fp64_peak) if fp64_peak else None,
-                             "traffic": None,
+                             "traffic": ncu_traffic("harm_tile_kernel") if strategy == "structured" else None,
+                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu "
+                                               "--set full (profiles/r1_ncu_kernels.csv)",
                              "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (no FP64 figure "
                                             "in MEASURED_PEAKS.json)",
                              "flops_per_nr_iteration": fl_iter,
