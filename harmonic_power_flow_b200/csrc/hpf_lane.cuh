@@ -18,88 +18,6 @@
 #include <type_traits>
 #include "hpf_device.cuh"
 
-// sin / cos with the network's phasor angles: Cody-Waite reduction by pi/2 in three parts and
-// the classic degree-13 / degree-14 minimax polynomials on [-pi/4, pi/4] (fdlibm's
-// coefficients), error < 1 ulp.  Coefficients are constant-bank operands (the library
-// routine materialises them as immediates, two extra issue slots per coefficient).  Beyond
-// |x| >= 105615 the three-part reduction loses accuracy: the library routine is called.
-__constant__ double HPF_SC[20] = {
-    6.36619772367581382433e-01,   // 0  2/pi
-    6755399441055744.0,           // 1  1.5 * 2^52 (round-to-nearest-integer by addition)
-    1.57079632679489655800e+00,   // 2  pi/2 hi
-    6.12323399573676603587e-17,   // 3  pi/2 mid
-    -1.49738490485916983169e-33,  // 4  pi/2 lo (pi/2 - hi - mid)
-    -1.66666666666666324348e-01,  // 5  S1
-    8.33333333332248946124e-03,   // 6  S2
-    -1.98412698298579493134e-04,  // 7  S3
-    2.75573137070700676789e-06,   // 8  S4
-    -2.50507602534068634195e-08,  // 9  S5
-    1.58969099521155010221e-10,   // 10 S6
-    4.16666666666666019037e-02,   // 11 C1
-    -1.38888888888741095749e-03,  // 12 C2
-    2.48015872894767294178e-05,   // 13 C3
-    -2.75573143513906633035e-07,  // 14 C4
-    2.08757232129817482790e-09,   // 15 C5
-    -1.13596475577881948265e-11,  // 16 C6
-    105615.0,                     // 17 fast-path bound
-    0.0, 0.0};
-
-__device__ __noinline__ double2 sincos_slow(double x) {
-    double s, c;
-    sincos(x, &s, &c);
-    return make_double2(s, c);
-}
-
-// Branch-free fast path (valid for |x| < 105615; garbage-in-garbage-out beyond, NaN for NaN).
-__device__ __forceinline__ void sincos_core(const double x, double& sn, double& cs) {
-    const double t = fma(x, HPF_SC[0], HPF_SC[1]);
-    const int k = __double2loint(t);
-    const double qd = t - HPF_SC[1];
-    double r = fma(-qd, HPF_SC[2], x);
-    r = fma(-qd, HPF_SC[3], r);
-    r = fma(-qd, HPF_SC[4], r);
-    const double z = r * r;
-    double ps = fma(z, HPF_SC[10], HPF_SC[9]);
-    double pc = fma(z, HPF_SC[16], HPF_SC[15]);
-    ps = fma(z, ps, HPF_SC[8]);
-    pc = fma(z, pc, HPF_SC[14]);
-    ps = fma(z, ps, HPF_SC[7]);
-    pc = fma(z, pc, HPF_SC[13]);
-    ps = fma(z, ps, HPF_SC[6]);
-    pc = fma(z, pc, HPF_SC[12]);
-    ps = fma(z, ps, HPF_SC[5]);
-    pc = fma(z, pc, HPF_SC[11]);
-    const double s0 = fma(z * r, ps, r);                  // r + r^3 (S1 + z S2 + ...)
-    const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));  // 1 - z/2 + z^2 (C1 + z C2 + ...)
-    const bool swap = (k & 1) != 0;
-    const double a = swap ? c0 : s0;                      // sin(x) up to sign
-    const double b = swap ? s0 : c0;                      // cos(x) up to sign
-    // signs by integer XOR on the high word (keeps the FP64 pipe free)
-    sn = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
-    cs = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
-}
-
-// N independent sin/cos pairs: all fast paths first (independent dependency chains that the
-// scheduler interleaves), one rare fix-up branch for large arguments afterwards.
-template <int N>
-__device__ __forceinline__ void sincos_group(const double* x, double* sn, double* cs) {
-    bool big = false;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        sincos_core(x[i], sn[i], cs[i]);
-        big |= (fabs(x[i]) >= HPF_SC[17]);                // also +-Inf; NaN propagates through the core
-    }
-    if (big) {
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            if (fabs(x[i]) >= HPF_SC[17]) {
-                const double2 r2 = sincos_slow(x[i]);
-                sn[i] = r2.x;
-                cs[i] = r2.y;
-            }
-    }
-}
-
 // NaN-propagating running maximum of |v| on the INTEGER pipe: for sign-cleared IEEE doubles the
 // bit patterns order like the magnitudes, and every NaN pattern is above +Inf, so an integer
 // max keeps a NaN once it has seen one (numpy's norm(inf) / max do the same, HG:389).

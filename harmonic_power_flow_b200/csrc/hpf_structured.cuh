@@ -793,14 +793,34 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     }
                 }
                 cp_async_commit();
-                row_loop<ZR>(m + warp, nH, CW, [&](int s) {
-                    double sn_, cs_;
-                    if constexpr (D::n != 0) sincos(AT(Va, s), &sn_, &cs_);       // inline: rows interleave
-                    else { const double2 e = sincos_ol(AT(Va, s)); cs_ = e.x; sn_ = e.y; }
-                    const double vm = AT(Vm, s);
-                    AT(Vre, s) = vm * cs_;
-                    AT(Vim, s) = vm * sn_;
-                });
+                if constexpr (D::n != 0) {
+                    // all sin/cos of the warp's rows as ONE branch-free group (hpf_device.cuh): the
+                    // dependency chains of the rows interleave, half the instructions of the library
+                    // routine, no per-row branch
+                    double ang[ZR], sn_[ZR], cs_[ZR];
+#pragma unroll
+                    for (int r = 0; r < ZR; ++r) {
+                        const int s = m + warp + r * CW;
+                        ang[r] = (s < nH) ? AT(Va, s) : 0.0;
+                    }
+                    sincos_group<ZR>(ang, sn_, cs_);
+#pragma unroll
+                    for (int r = 0; r < ZR; ++r) {
+                        const int s = m + warp + r * CW;
+                        if (s < nH) {
+                            const double vm = AT(Vm, s);
+                            AT(Vre, s) = vm * cs_[r];
+                            AT(Vim, s) = vm * sn_[r];
+                        }
+                    }
+                } else {
+                    for (int s = m + warp; s < nH; s += CW) {
+                        const double2 e = sincos_ol(AT(Va, s));
+                        const double vm = AT(Vm, s);
+                        AT(Vre, s) = vm * e.x;
+                        AT(Vim, s) = vm * e.y;
+                    }
+                }
                 cp_async_wait<1>();                 // group 0 (I_N, first w_N rows) has landed
             }
         }
