@@ -30,11 +30,27 @@
 // are kept per row: later lines overwrite earlier ones, the diagonal is minus the
 // sequential row sum, bus shunt only for h != 1, pi-shunts matched with the off-by-one
 // index (1-based ID compared with the 0-based row).
+// Optional transformer branches (tau != nullptr), the model of the reference's
+// "Fundamental Power Flow/pi_trafo_pf_test.py" (FPF:117-145): tap ratio tau and phase shift phi
+// (degrees) per branch, Y[f,t] = y / (tau e^{-j phi}), Y[t,f] = y / (tau e^{+j phi}); the
+// pi-shunt of a branch whose toID matches divides the accumulated diagonal by tau^2 (FPF:137-145,
+// same index quirk as HG:163-168, `elif` so a from-match wins).
+__device__ __forceinline__ double2 cdiv_smith(double2 a, double2 b) {      // numpy's complex division
+    if (fabs(b.x) >= fabs(b.y)) {
+        if (b.x == 0.0 && b.y == 0.0) return make_double2(a.x / fabs(b.x), a.y / fabs(b.y));
+        const double rat = b.y / b.x, scl = 1.0 / __dadd_rn(b.x, __dmul_rn(b.y, rat));
+        return make_double2(__dadd_rn(a.x, __dmul_rn(a.y, rat)) * scl, __dadd_rn(a.y, -__dmul_rn(a.x, rat)) * scl);
+    }
+    const double rat = b.x / b.y, scl = 1.0 / __dadd_rn(b.y, __dmul_rn(b.x, rat));
+    return make_double2(__dadd_rn(__dmul_rn(a.x, rat), a.y) * scl, __dadd_rn(__dmul_rn(a.y, rat), -a.x) * scl);
+}
+
 __global__ void ybus_kernel(int n, int H, int L, const int* __restrict__ harmonics,
                             const int* __restrict__ from_id, const int* __restrict__ to_id,
                             const double* __restrict__ R, const double* __restrict__ X,
                             const double* __restrict__ G, const double* __restrict__ Bsh,
-                            const double* __restrict__ X_sh, double2* __restrict__ Y) {
+                            const double* __restrict__ X_sh, const double* __restrict__ tau,
+                            const double* __restrict__ phase_deg, double2* __restrict__ Y) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * H) return;
     const int hi = idx / n, k = idx - hi * n;
@@ -59,8 +75,19 @@ __global__ void ybus_kernel(int n, int H, int L, const int* __restrict__ harmoni
             y = make_double2(rat * scl, -scl);
         }
         y = make_double2(-y.x, -y.y);
-        if (f == k) row[t] = y;
-        if (t == k) row[f] = y;
+        if (tau) {
+            // (tau * exp(-+ j phi)), phi = phase_shift / 180 * pi   (FPF:118-124)
+            const double phi = phase_deg[l] / 180.0 * CUDART_PI;
+            double sn, cs;
+            sincos(phi, &sn, &cs);
+            const double2 dft = make_double2(tau[l] * cs, tau[l] * -sn);
+            const double2 dtf = make_double2(tau[l] * cs, tau[l] * sn);
+            if (f == k) row[t] = cdiv_smith(y, dft);
+            if (t == k) row[f] = cdiv_smith(y, dtf);        // (a self-loop keeps the later assignment)
+        } else {
+            if (f == k) row[t] = y;
+            if (t == k) row[f] = y;
+        }
     }
     double2 s = make_double2(0.0, 0.0);
     for (int j = 0; j < n; ++j) s = cadd(s, row[j]);
@@ -70,9 +97,13 @@ __global__ void ybus_kernel(int n, int H, int L, const int* __restrict__ harmoni
         d.y += -1.0 / (X_sh[k] * h);
     }
     for (int l = 0; l < L; ++l) {
-        if (from_id[l] == k || to_id[l] == k) {
+        if (from_id[l] == k || (!tau && to_id[l] == k)) {
             d.x += G[l] / 2.0;
             d.y += (h * Bsh[l]) / 2.0;
+        } else if (tau && to_id[l] == k) {                   // FPF:142-145
+            const double t2 = tau[l] * tau[l];
+            d.x = (d.x + G[l] / 2.0) / t2;
+            d.y = (d.y + (h * Bsh[l]) / 2.0) / t2;
         }
     }
     row[k] = d;
@@ -944,6 +975,7 @@ struct hpf_handle {
     bool have_net = false, have_dev = false, have_Y = false;
     int *d_harm = nullptr, *d_from = nullptr, *d_to = nullptr, *d_devof = nullptr;
     double *d_R = nullptr, *d_X = nullptr, *d_G = nullptr, *d_B = nullptr, *d_Xsh = nullptr;
+    double *d_tau = nullptr, *d_phase = nullptr;             // optional transformer data (hpf_set_transformers)
     double2 *d_Y = nullptr, *d_YN = nullptr;
     int* d_counter = nullptr;
     double* d_work = nullptr;
@@ -1501,7 +1533,7 @@ int hpf_destroy(hpf_t* h) {
     cudaFree(h->d_R); cudaFree(h->d_X); cudaFree(h->d_G); cudaFree(h->d_B); cudaFree(h->d_Xsh);
     cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work); cudaFree(h->d_io); cudaFree(h->d_Ainv); cudaFree(h->d_Gz);
     cudaFree(h->d_WNL); cudaFree(h->d_wN); cudaFree(h->d_GzT); cudaFree(h->d_nbr_ptr); cudaFree(h->d_nbr_idx);
-    cudaFree(h->d_gstate); cudaFree(h->d_ell_col);
+    cudaFree(h->d_gstate); cudaFree(h->d_ell_col); cudaFree(h->d_tau); cudaFree(h->d_phase);
     for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 4; ++i) if (h->st_io[i]) cudaStreamDestroy(h->st_io[i]);
     for (int i = 0; i < 16; ++i) if (h->ev_io[i]) cudaEventDestroy(h->ev_io[i]);
@@ -1531,6 +1563,7 @@ int hpf_set_network(hpf_t* h, int n, int m, int c, int H, const int* harmonics, 
     CK(upload(&h->d_G, G, (size_t)L));
     CK(upload(&h->d_B, B, (size_t)L));
     CK(upload(&h->d_Xsh, X_sh, (size_t)n));
+    cudaFree(h->d_tau); cudaFree(h->d_phase); h->d_tau = nullptr; h->d_phase = nullptr;
     CK(upload(&h->d_Y, (const double2*)nullptr, (size_t)H * n * n));
     h->have_net = true;
     h->have_Y = false;
@@ -1561,6 +1594,25 @@ int hpf_set_devices(hpf_t* h, int n_dev, int coupled, const double* Y_N, const i
     return HPF_OK;
 }
 
+int hpf_set_transformers(hpf_t* h, const double* tau, const double* phase_shift_deg) {
+    if (!h) return HPF_E_INVALID;
+    if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_set_transformers: call hpf_set_network first");
+    if ((tau == nullptr) != (phase_shift_deg == nullptr))
+        return fail(h, HPF_E_INVALID, "hpf_set_transformers: give both arrays or neither");
+    CK(cudaSetDevice(h->device));
+    cudaFree(h->d_tau); cudaFree(h->d_phase); h->d_tau = nullptr; h->d_phase = nullptr;
+    if (tau) {
+        for (int l = 0; l < h->L; ++l)
+            if (!(tau[l] != 0.0)) return fail(h, HPF_E_INVALID, "hpf_set_transformers: tau must be non-zero");
+        CK(upload(&h->d_tau, tau, (size_t)h->L));
+        CK(upload(&h->d_phase, phase_shift_deg, (size_t)h->L));
+    }
+    h->have_Y = false;                                       // Y(h) must be rebuilt
+    h->struct_state = 0;
+    h->host_consts_valid = false;
+    return HPF_OK;
+}
+
 int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
     if (!h) return HPF_E_INVALID;
     if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_build_Y: call hpf_set_network first");
@@ -1568,7 +1620,7 @@ int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int total = h->n * h->H;
     ybus_kernel<<<(total + 127) / 128, 128, 0, st>>>(h->n, h->H, h->L, h->d_harm, h->d_from, h->d_to,
-                                                      h->d_R, h->d_X, h->d_G, h->d_B, h->d_Xsh, h->d_Y);
+                                                      h->d_R, h->d_X, h->d_G, h->d_B, h->d_Xsh, h->d_tau, h->d_phase, h->d_Y);
     h->launches++;
     CK(cudaGetLastError());
     if (Y_out)

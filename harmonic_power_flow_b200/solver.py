@@ -143,6 +143,20 @@ class BatchSolver:
         _lib.check(self._h, self.lib.hpf_build_Y(self._h, _ptr(Y), self._stream()))
         return Y
 
+    def set_transformers(self, tau=None, phase_shift_deg=None):
+        """Transformer taps / phase shifts per line (FPF/pi_trafo_pf_test.py:117-145) and rebuild
+        Y(h); ``None`` restores plain lines."""
+        if tau is None:
+            _lib.check(self._h, self.lib.hpf_set_transformers(self._h, None, None))
+        else:
+            t = np.ascontiguousarray(tau, dtype=np.float64)
+            p = np.ascontiguousarray(phase_shift_deg, dtype=np.float64)
+            if t.shape != (len(self.net.R),) or p.shape != t.shape:
+                raise ValueError("tau and phase_shift_deg must have one entry per line")
+            _lib.check(self._h, self.lib.hpf_set_transformers(self._h, _np_d(t), _np_d(p)))
+        self.Y = self.build_Y()
+        return self.Y
+
     def set_Y(self, Y):
         """Replace Y(h) by a caller-supplied [H, n, n] complex table (pf(Y, buses), HG:244)."""
         Y = np.ascontiguousarray(Y, dtype=np.complex128)

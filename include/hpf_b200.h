@@ -55,7 +55,7 @@ typedef struct hpf_handle hpf_t;
 #define HPF_ST_NONFINITE    3   /* NaN/Inf in the mismatch or the state            */
 
 /* ABI version of this header: bumped on any signature change. */
-#define HPF_ABI_VERSION 5
+#define HPF_ABI_VERSION 6
 int hpf_abi_version(void);
 
 /* Lifetime.  `device` is the CUDA ordinal the handle is bound to. */
@@ -83,6 +83,15 @@ int hpf_set_network(hpf_t* h, int n, int m, int c, int H, const int* harmonics,
  */
 int hpf_set_devices(hpf_t* h, int n_dev, int coupled, const double* Y_N,
                     const int* dev_of_nl_bus);
+
+/*
+ * Optional transformer branches for the next hpf_build_Y: tap ratio tau[L]
+ * and phase shift phase_shift_deg[L] per line, the branch model of the reference's
+ * "Fundamental Power Flow/pi_trafo_pf_test.py":117-145 (off-diagonals divided by
+ * tau e^{-+j phi}; the pi-shunt of a to-side match divides the accumulated diagonal by tau^2).
+ * Host pointers, copied; both NULL restores plain lines (HG:132-171).  hpf_set_network clears them.
+ */
+int hpf_set_transformers(hpf_t* h, const double* tau, const double* phase_shift_deg);
 
 /*
  * Kernel 1 - per-harmonic bus admittance assembly.  Replaces

@@ -100,6 +100,39 @@ def build_admittance_matrices(net: Net) -> np.ndarray:
     return Y_all
 
 
+def build_admittance_matrices_trafo(net: Net, tau, phase_shift_deg) -> np.ndarray:
+    """Y(h) with transformer branches - restates build_admittance_matrices of the reference's
+    "Fundamental Power Flow/pi_trafo_pf_test.py" (FPF:99-149): off-diagonals divided by
+    tau e^{-+j phi} (FPF:117-124), the pi-shunt of a branch whose toID equals the 0-based row index
+    divides the accumulated diagonal by tau^2, and only if its fromID did not match (FPF:137-145)."""
+    n, H = net.n, net.H
+    Y_all = np.zeros((H, n, n), dtype=complex)
+    for hi, h in enumerate(net.harmonics):
+        h = int(h)
+        Y = np.zeros((n, n), dtype=complex)
+        for l in range(len(net.R)):
+            f, t = int(net.line_from[l]) - 1, int(net.line_to[l]) - 1
+            Y[f, t] = -1 / (net.R[l] + 1j * net.X[l] * h) / \
+                (tau[l] * np.exp(-1j * phase_shift_deg[l] / 180 * np.pi))
+            Y[t, f] = -1 / (net.R[l] + 1j * net.X[l] * h) / \
+                (tau[l] * np.exp(1j * phase_shift_deg[l] / 180 * np.pi))
+        for k in range(n):
+            s = 0
+            for j in range(n):
+                s = s + Y[k, j]
+            if net.X_sh[k] != 0 and h != 1:
+                Y[k, k] = -s + 1 / (1j * net.X_sh[k] * h)
+            else:
+                Y[k, k] = -s
+            for l in range(len(net.R)):
+                if net.line_from[l] == k:
+                    Y[k, k] = Y[k, k] + (net.G[l] + 1j * h * net.B[l]) / 2
+                elif net.line_to[l] == k:
+                    Y[k, k] = (Y[k, k] + (net.G[l] + 1j * h * net.B[l]) / 2) / (tau[l] ** 2)
+        Y_all[hi] = Y
+    return Y_all
+
+
 def init_voltages(net: Net):
     """Flat start: |V|=1 at h=1, 0.1 at h>1, angle 0 (HG:174-184)."""
     V_m = np.full((net.H, net.n), 0.1)

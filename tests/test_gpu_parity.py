@@ -670,3 +670,32 @@ def test_ne_extract_batch_round_trip_and_csv(tmp_path):
     tab = netio.read_ne_csv(path)
     assert np.array_equal(tab.loc["I_N_c"].to_numpy().ravel(), ne0["I_N_c"])
     assert np.array_equal(tab.loc[("Y_N_c", list(freq)), list(freq)].to_numpy(), ne0["Y_N_c"])
+
+
+# ---------------------------------------------------------------- transformer branches in Y(h) (next-3)
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_trafo_ybus_matches_reference_function(tag):
+    """ybus_kernel with hpf_set_transformers against the reference's own
+    FPF/pi_trafo_pf_test.py:build_admittance_matrices outputs; clearing the transformer data
+    restores the plain HG:132-171 result."""
+    import os
+    from harmonic_power_flow_b200 import BatchSolver
+    from harmonic_power_flow_b200.netio import PackedNet
+    d = np.load(os.path.join(GOLDEN, "ybus_trafo.npz"))
+    n = len(d[tag + "_X_sh"])
+    net = PackedNet(n=n, m=n, c=1, harmonics=np.ascontiguousarray(d[tag + "_harmonics"], np.int32),
+                    from_id=np.ascontiguousarray(d[tag + "_frm"], np.int32),
+                    to_id=np.ascontiguousarray(d[tag + "_to"], np.int32),
+                    R=np.ascontiguousarray(d[tag + "_R"]), X=np.ascontiguousarray(d[tag + "_X"]),
+                    G=np.ascontiguousarray(d[tag + "_G"]), B=np.ascontiguousarray(d[tag + "_B"]),
+                    X_sh=np.ascontiguousarray(d[tag + "_X_sh"]), P=np.zeros(n), Q=np.zeros(n))
+    sol = BatchSolver(net)
+    Y_plain = sol.Y.cpu().numpy().copy()
+    Y = sol.set_transformers(d[tag + "_tau"], d[tag + "_ph"]).cpu().numpy()
+    want = d[tag + "_Y"]
+    assert np.abs(Y - want).max() <= 4e-15 * np.abs(want).max()
+    assert ((Y == 0) == (want == 0)).all()
+    assert np.array_equal(sol.set_transformers(None).cpu().numpy(), Y_plain)
+    with pytest.raises(Exception):
+        sol.set_transformers(np.zeros(len(net.R)), np.zeros(len(net.R)))      # tau = 0
+    sol.close()

@@ -129,3 +129,22 @@ def test_ne_oracle_matches_reference_script(name):
     for k in range(N - 1):
         v = np.zeros(N, dtype=complex); v[0] = d["Vf"][0]; v[k + 1] = d["Vh"][0][k]
         assert np.abs(NO.forward(Yc, Ic, v) - d["I_h"][0][k]).max() <= 1e-9 * np.abs(d["I_h"][0][k]).max()
+
+
+# ---------------------------------------------------------------- transformer branches in Y(h) (next-3)
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_trafo_ybus_oracle_matches_reference_function(tag):
+    """oracle build_admittance_matrices_trafo against the outputs of the reference's own
+    FPF/pi_trafo_pf_test.py:build_admittance_matrices (fixtures from oracle/make_golden_trafo.py)."""
+    d = np.load(os.path.join(GOLDEN, "ybus_trafo.npz"))
+    n = len(d[tag + "_X_sh"])
+    net = O.Net(n=n, m=n, c=1, harmonics=d[tag + "_harmonics"], line_from=d[tag + "_frm"], line_to=d[tag + "_to"],
+                R=d[tag + "_R"], X=d[tag + "_X"], G=d[tag + "_G"], B=d[tag + "_B"], X_sh=d[tag + "_X_sh"],
+                P=np.zeros(n), Q=np.zeros(n))
+    Y = O.build_admittance_matrices_trafo(net, d[tag + "_tau"], d[tag + "_ph"])
+    assert np.array_equal(Y, d[tag + "_Y"])
+    # tau = 1, phi = 0 and no to-side shunt match reduces to the plain-line model where both apply
+    Y1 = O.build_admittance_matrices_trafo(net, np.ones_like(d[tag + "_tau"]), np.zeros_like(d[tag + "_ph"]))
+    Y0 = O.build_admittance_matrices(net)
+    off = ~np.eye(n, dtype=bool)
+    assert np.abs(Y1[:, off] - Y0[:, off]).max() <= 1e-15 * np.abs(Y0).max()
