@@ -15,7 +15,7 @@ HPF_OK, HPF_E_INVALID, HPF_E_CUDA, HPF_E_UNSUPPORTED, HPF_E_NOMEM = 0, -1, -2, -
 ST_CONVERGED, ST_MAXITER, ST_SINGULAR, ST_NONFINITE = 0, 1, 2, 3
 SOLVE_RAW = 1
 SOLVE_DENSE = 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
 _ip, _dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -30,6 +30,7 @@ SIGNATURES = {
     "hpf_set_network": (_i, [_vp, _i, _i, _i, _i, _ip, _i, _ip, _ip, _dp, _dp, _dp, _dp, _dp]),
     "hpf_set_devices": (_i, [_vp, _i, _i, _dp, _ip]),
     "hpf_set_transformers": (_i, [_vp, _dp, _dp]),
+    "hpf_set_y_options": (_i, [_vp, _i]),
     "hpf_build_Y": (_i, [_vp, _vp, _vp]),
     "hpf_set_Y": (_i, [_vp, _dp]),
     "hpf_struct_info": (_i, [_vp, _ip, _ip, _dp, _dp]),

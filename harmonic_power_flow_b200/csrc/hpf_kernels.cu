@@ -50,7 +50,7 @@ __global__ void ybus_kernel(int n, int H, int L, const int* __restrict__ harmoni
                             const double* __restrict__ R, const double* __restrict__ X,
                             const double* __restrict__ G, const double* __restrict__ Bsh,
                             const double* __restrict__ X_sh, const double* __restrict__ tau,
-                            const double* __restrict__ phase_deg, double2* __restrict__ Y) {
+                            const double* __restrict__ phase_deg, const int yflags, double2* __restrict__ Y) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * H) return;
     const int hi = idx / n, k = idx - hi * n;
@@ -82,8 +82,17 @@ __global__ void ybus_kernel(int n, int H, int L, const int* __restrict__ harmoni
             sincos(phi, &sn, &cs);
             const double2 dft = make_double2(tau[l] * cs, tau[l] * -sn);
             const double2 dtf = make_double2(tau[l] * cs, tau[l] * sn);
-            if (f == k) row[t] = cdiv_smith(y, dft);
-            if (t == k) row[f] = cdiv_smith(y, dtf);        // (a self-loop keeps the later assignment)
+            const double2 yft = cdiv_smith(y, dft), ytf = cdiv_smith(y, dtf);
+            if (yflags & HPF_Y_SUM_PARALLEL) {
+                if (f == k) row[t] = cadd(row[t], yft);
+                if (t == k) row[f] = cadd(row[f], ytf);
+            } else {
+                if (f == k) row[t] = yft;
+                if (t == k) row[f] = ytf;                    // (a self-loop keeps the later assignment)
+            }
+        } else if (yflags & HPF_Y_SUM_PARALLEL) {
+            if (f == k) row[t] = cadd(row[t], y);
+            if (t == k) row[f] = cadd(row[f], y);
         } else {
             if (f == k) row[t] = y;
             if (t == k) row[f] = y;
@@ -96,11 +105,12 @@ __global__ void ybus_kernel(int n, int H, int L, const int* __restrict__ harmoni
         // 1 / (j X_sh h) = -j / (X_sh h)
         d.y += -1.0 / (X_sh[k] * h);
     }
+    const int ko = (yflags & HPF_Y_FIX_SHUNT_INDEX) ? k + 1 : k;   // reference: 1-based ID compared with 0-based row
     for (int l = 0; l < L; ++l) {
-        if (from_id[l] == k || (!tau && to_id[l] == k)) {
+        if (from_id[l] == ko || (!tau && to_id[l] == ko)) {
             d.x += G[l] / 2.0;
             d.y += (h * Bsh[l]) / 2.0;
-        } else if (tau && to_id[l] == k) {                   // FPF:142-145
+        } else if (tau && to_id[l] == ko) {                  // FPF:142-145
             const double t2 = tau[l] * tau[l];
             d.x = (d.x + G[l] / 2.0) / t2;
             d.y = (d.y + (h * Bsh[l]) / 2.0) / t2;
@@ -976,6 +986,7 @@ struct hpf_handle {
     int *d_harm = nullptr, *d_from = nullptr, *d_to = nullptr, *d_devof = nullptr;
     double *d_R = nullptr, *d_X = nullptr, *d_G = nullptr, *d_B = nullptr, *d_Xsh = nullptr;
     double *d_tau = nullptr, *d_phase = nullptr;             // optional transformer data (hpf_set_transformers)
+    int y_flags = 0;                                         // HPF_Y_* (hpf_set_y_options)
     double2 *d_Y = nullptr, *d_YN = nullptr;
     int* d_counter = nullptr;
     double* d_work = nullptr;
@@ -1613,6 +1624,17 @@ int hpf_set_transformers(hpf_t* h, const double* tau, const double* phase_shift_
     return HPF_OK;
 }
 
+int hpf_set_y_options(hpf_t* h, int flags) {
+    if (!h) return HPF_E_INVALID;
+    if (flags & ~(HPF_Y_FIX_SHUNT_INDEX | HPF_Y_SUM_PARALLEL))
+        return fail(h, HPF_E_INVALID, "hpf_set_y_options: unknown flag");
+    h->y_flags = flags;
+    h->have_Y = false;                                       // Y(h) must be rebuilt
+    h->struct_state = 0;
+    h->host_consts_valid = false;
+    return HPF_OK;
+}
+
 int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
     if (!h) return HPF_E_INVALID;
     if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_build_Y: call hpf_set_network first");
@@ -1620,7 +1642,7 @@ int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int total = h->n * h->H;
     ybus_kernel<<<(total + 127) / 128, 128, 0, st>>>(h->n, h->H, h->L, h->d_harm, h->d_from, h->d_to,
-                                                      h->d_R, h->d_X, h->d_G, h->d_B, h->d_Xsh, h->d_tau, h->d_phase, h->d_Y);
+                                                      h->d_R, h->d_X, h->d_G, h->d_B, h->d_Xsh, h->d_tau, h->d_phase, h->y_flags, h->d_Y);
     h->launches++;
     CK(cudaGetLastError());
     if (Y_out)

@@ -157,6 +157,13 @@ class BatchSolver:
         self.Y = self.build_Y()
         return self.Y
 
+    def set_y_options(self, fix_shunt_index=False, sum_parallel=False):
+        """Opt-in corrections of the reference's Y(h) quirks (hpf_set_y_options); rebuilds Y(h)."""
+        flags = (1 if fix_shunt_index else 0) | (2 if sum_parallel else 0)
+        _lib.check(self._h, self.lib.hpf_set_y_options(self._h, flags))
+        self.Y = self.build_Y()
+        return self.Y
+
     def set_Y(self, Y):
         """Replace Y(h) by a caller-supplied [H, n, n] complex table (pf(Y, buses), HG:244)."""
         Y = np.ascontiguousarray(Y, dtype=np.complex128)

@@ -55,7 +55,7 @@ typedef struct hpf_handle hpf_t;
 #define HPF_ST_NONFINITE    3   /* NaN/Inf in the mismatch or the state            */
 
 /* ABI version of this header: bumped on any signature change. */
-#define HPF_ABI_VERSION 6
+#define HPF_ABI_VERSION 7
 int hpf_abi_version(void);
 
 /* Lifetime.  `device` is the CUDA ordinal the handle is bound to. */
@@ -92,6 +92,17 @@ int hpf_set_devices(hpf_t* h, int n_dev, int coupled, const double* Y_N,
  * Host pointers, copied; both NULL restores plain lines (HG:132-171).  hpf_set_network clears them.
  */
 int hpf_set_transformers(hpf_t* h, const double* tau, const double* phase_shift_deg);
+
+/*
+ * Opt-in corrections of two quirks of build_admittance_matrices (default 0 = reference behaviour,
+ * which every parity test uses): HPF_Y_FIX_SHUNT_INDEX puts the pi-line shunt (G + jhB)/2 on
+ * the buses the line actually connects (HG:163-168 compares the 1-based ID with the 0-based
+ * row, so it lands one bus too low); HPF_Y_SUM_PARALLEL adds parallel branches instead of
+ * letting the later one overwrite (HG:150-155).  Takes effect at the next hpf_build_Y.
+ */
+#define HPF_Y_FIX_SHUNT_INDEX 1
+#define HPF_Y_SUM_PARALLEL    2
+int hpf_set_y_options(hpf_t* h, int flags);
 
 /*
  * Kernel 1 - per-harmonic bus admittance assembly.  Replaces

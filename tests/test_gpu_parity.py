@@ -721,3 +721,38 @@ def test_config5_meshed_1000_bus_nominal_against_oracle_run(tmp_path):
     assert r["V_m"][0, :, 0].max() == pytest.approx(1.1649555668183993, rel=1e-11)
     assert r["V_m"][1, :, 0].max() == pytest.approx(0.5791799507662769, rel=1e-11)
     sol.close()
+
+
+def test_ybus_corrected_options_match_textbook_admittance_matrix():
+    """hpf_set_y_options(FIX_SHUNT_INDEX | SUM_PARALLEL) against the textbook nodal admittance
+    matrix (incidence form) on a seeded 6-bus network with parallel branches and pi-shunts; the
+    default flags keep the reference's behaviour (covered by test_ybus_matches_reference)."""
+    from harmonic_power_flow_b200 import BatchSolver
+    from harmonic_power_flow_b200.netio import PackedNet
+    rng = np.random.default_rng(4)
+    n, L = 6, 9
+    frm = np.array([1, 2, 3, 4, 5, 1, 2, 2, 6], np.int32); to = np.array([2, 3, 4, 5, 6, 3, 5, 3, 1], np.int32)
+    R, X = rng.uniform(1e-3, 6e-3, L), rng.uniform(3e-3, 3e-2, L)
+    G, B = rng.uniform(0, 1e-2, L), rng.uniform(0, 1e-3, L)
+    X_sh = np.array([3e-5, 0, 0, 2e-4, 0, 0])
+    harmonics = np.arange(1, 26, 2).astype(np.int32)
+    net = PackedNet(n=n, m=n, c=1, harmonics=harmonics, from_id=frm, to_id=to, R=R, X=X, G=G, B=B, X_sh=X_sh,
+                    P=np.zeros(n), Q=np.zeros(n))
+    sol = BatchSolver(net)
+    Y_ref_behaviour = sol.Y.cpu().numpy().copy()
+    Y = sol.set_y_options(fix_shunt_index=True, sum_parallel=True).cpu().numpy()
+    want = np.zeros((len(harmonics), n, n), dtype=complex)
+    for hi, h in enumerate(harmonics):
+        for l in range(L):
+            f, t = frm[l] - 1, to[l] - 1
+            y = 1 / (R[l] + 1j * X[l] * h)
+            sh = (G[l] + 1j * h * B[l]) / 2
+            want[hi, f, f] += y + sh; want[hi, t, t] += y + sh
+            want[hi, f, t] -= y; want[hi, t, f] -= y
+        for k in range(n):
+            if X_sh[k] != 0 and h != 1:
+                want[hi, k, k] += 1 / (1j * X_sh[k] * h)
+    assert np.abs(Y - want).max() <= 1e-13 * np.abs(want).max()
+    assert np.abs(Y - Y_ref_behaviour).max() > 1e-3 * np.abs(want).max()      # the quirks do matter here
+    assert np.array_equal(sol.set_y_options().cpu().numpy(), Y_ref_behaviour)
+    sol.close()
