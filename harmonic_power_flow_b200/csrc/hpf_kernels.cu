@@ -302,8 +302,10 @@ solve_kernel(const DevNet net, const SolveArgs a) {
     const int tid = threadIdx.x;
     const int n = net.n, c = net.c, nH = net.nH, N = net.N, Nf = net.Nf, H = net.H, q = net.q;
     const int ld = GMEM ? lub_ld(N) : odd_ld(N);
-    if (GMEM) s.A = a.workspace + (size_t)blockIdx.x * ld * (N + 1);
     double* lub = smem + scn_smem_doubles_aligned(n, H, q, N);      // GMEM only
+    // (blocked LU: the matrix sits in the per-CTA global workspace, or - small systems, when it
+    // fits - in shared memory behind the LU work area)
+    if (GMEM) s.A = a.workspace ? a.workspace + (size_t)blockIdx.x * ld * (N + 1) : lub + a.lub_doubles;
     const size_t B = (size_t)a.B;
 
     for (;;) {
@@ -726,8 +728,8 @@ lu_solve_kernel(const DevNet net, const LuArgs a) {
     extern __shared__ __align__(16) double smem[];
     ScnSmem s = carve(smem, net, !GMEM);
     const int N = net.N, ld = GMEM ? lub_ld(N) : odd_ld(N);
-    if (GMEM) s.A = a.workspace + (size_t)blockIdx.x * ld * (N + 1);
     double* lub = smem + scn_smem_doubles_aligned(net.n, net.H, net.q, N);   // GMEM only
+    if (GMEM) s.A = a.workspace ? a.workspace + (size_t)blockIdx.x * ld * (N + 1) : lub + a.lub_doubles;
     const size_t B = (size_t)a.B;
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         __syncthreads();
@@ -1012,6 +1014,7 @@ struct hpf_handle {
     int harm_minb = 1;
     int no_specialise = 0;        // $HPF_NO_SPECIALISE=1: always use the runtime-dimension kernels
     int mismatch_tile = 0;        // $HPF_MISMATCH_TILE=1: standalone mismatch through the tile kernel
+    int dense_blocked = 0;        // $HPF_DENSE_BLOCKED=1: blocked tensor-core LU also for smem-sized systems
     int force_variant = 0;        // $HPF_STRUCT_VARIANT=2|3: force a per-CTA variant of the harmonic stage
     // host mirror of the network constants for kernels that take them as parameters
     // (constant bank): fetched lazily from the device tables, see host_consts()
@@ -1075,6 +1078,19 @@ static bool fits_smem_lu(const hpf_t* h, const DevNet& net) {
            scn_smem_bytes(net.n, net.H, net.q, net.N, true) <= (size_t)h->smem_optin;
 }
 
+// Blocked tensor-core LU on a matrix that still fits shared memory (N <= 192): chosen with
+// $HPF_DENSE_BLOCKED=1 instead of the classic shared-memory LU.  Returns the LU work area in
+// doubles (even), or 0 if it does not fit.
+static size_t smem_blocked_lub_doubles(const hpf_t* h, const DevNet& net) {
+    if (!h->dense_blocked) return 0;
+    const size_t state = scn_smem_doubles_aligned(net.n, net.H, net.q, net.N);
+    const size_t mat = (size_t)lub_ld(net.N) * (net.N + 1);
+    const size_t cap = (size_t)h->smem_optin / sizeof(double);
+    if (state + mat + LUB_SMEM_DOUBLES + 4 > cap) return 0;
+    size_t lubd = lub_smem_doubles_for(net.N, (cap - state - mat - 4) * sizeof(double));
+    return lubd & ~(size_t)1;
+}
+
 static int ensure_workspace(hpf_t* h, size_t doubles) {
     if (doubles <= h->work_doubles) return HPF_OK;
     if (h->d_work) { CK(cudaDeviceSynchronize()); cudaFree(h->d_work); h->d_work = nullptr; h->work_doubles = 0; }
@@ -1124,8 +1140,12 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
         net.H = 1; net.nH = net.n;
         gm = !fits_smem_lu(h, net);
     }
-    const size_t lubd = gm ? gmem_kernel_lub_doubles(net.n, net.H, net.q, net.N, (size_t)h->smem_optin) : 0;
-    const size_t smem = gm ? (scn_smem_doubles_aligned(net.n, net.H, net.q, net.N) + lubd) * sizeof(double) + 16
+    const size_t lubs = gm ? 0 : smem_blocked_lub_doubles(h, net);     // > 0: blocked LU, matrix in smem
+    const bool ws_smem = lubs > 0;
+    if (ws_smem) gm = true;
+    const size_t lubd = ws_smem ? lubs : (gm ? gmem_kernel_lub_doubles(net.n, net.H, net.q, net.N, (size_t)h->smem_optin) : 0);
+    const size_t smem = gm ? (scn_smem_doubles_aligned(net.n, net.H, net.q, net.N) + lubd +
+                              (ws_smem ? (size_t)lub_ld(net.N) * (net.N + 1) : 0)) * sizeof(double) + 16
                            : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
     int occ = 0;
     rc = gm ? prep_kernel(h, solve_kernel<true>, smem, who, &occ, HPF_THREADS_GMEM)
@@ -1143,7 +1163,7 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     long long grid = (long long)occ * h->sm_count;
     if (grid > B) grid = B;
     a.workspace = nullptr;
-    if (gm) {
+    if (gm && !ws_smem) {
         rc = ensure_workspace(h, (size_t)grid * lub_ld(net.N) * (net.N + 1));
         if (rc) return rc;
         a.workspace = h->d_work;
@@ -1525,6 +1545,7 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_NO_SPECIALISE")) h->no_specialise = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_MISMATCH_TILE")) h->mismatch_tile = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_STRUCT_VARIANT")) h->force_variant = atoi(ev);
+    if (const char* ev = getenv("HPF_DENSE_BLOCKED")) h->dense_blocked = atoi(ev) ? 1 : 0;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     e = cudaMalloc((void**)&h->d_counter, 8 * sizeof(int));
@@ -1998,9 +2019,13 @@ int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, 
     const DevNet net = devnet(h);
     LuArgs a;
     a.B = B; a.J = J; a.f = f; a.dx = dx; a.info = info; a.stride = hpf_jacobian_stride(h);
-    const bool gm = !fits_smem_lu(h, net);
-    const size_t lubd = gm ? gmem_kernel_lub_doubles(net.n, net.H, net.q, net.N, (size_t)h->smem_optin) : 0;
-    const size_t smem = gm ? (scn_smem_doubles_aligned(net.n, net.H, net.q, net.N) + lubd) * sizeof(double) + 16
+    bool gm = !fits_smem_lu(h, net);
+    const size_t lubs = gm ? 0 : smem_blocked_lub_doubles(h, net);
+    const bool ws_smem = lubs > 0;
+    if (ws_smem) gm = true;
+    const size_t lubd = ws_smem ? lubs : (gm ? gmem_kernel_lub_doubles(net.n, net.H, net.q, net.N, (size_t)h->smem_optin) : 0);
+    const size_t smem = gm ? (scn_smem_doubles_aligned(net.n, net.H, net.q, net.N) + lubd +
+                              (ws_smem ? (size_t)lub_ld(net.N) * (net.N + 1) : 0)) * sizeof(double) + 16
                            : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
     a.lub_doubles = (int)lubd;
     int occ = 0;
@@ -2011,9 +2036,11 @@ int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, 
     if (grid > B) grid = B;
     a.workspace = nullptr;
     if (gm) {
-        rc = ensure_workspace(h, (size_t)grid * lub_ld(net.N) * (net.N + 1));
-        if (rc) return rc;
-        a.workspace = h->d_work;
+        if (!ws_smem) {
+            rc = ensure_workspace(h, (size_t)grid * lub_ld(net.N) * (net.N + 1));
+            if (rc) return rc;
+            a.workspace = h->d_work;
+        }
         lu_solve_kernel<true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, (cudaStream_t)stream>>>(net, a);
     } else {
         lu_solve_kernel<false><<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a);

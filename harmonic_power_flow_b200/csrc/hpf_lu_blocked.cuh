@@ -97,8 +97,14 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
     if (tid == 0) *sflag = 0;
     __syncthreads();
 
+    // permutation of the last register panel as lists (see step 2)
+    int* srcTop = reinterpret_cast<int*>(stage + 64);   // [NB] panel-relative source row of top position t
+    int* mvSrc = srcTop + LUB_NB;                       // [<= NB] rows that leave the top block ...
+    int* mvDst = mvSrc + LUB_NB;                        //         ... and the positions they end at
+    int* mvCnt = mvDst + LUB_NB;
     for (int k0 = 0; k0 < N;) {
         const int rows = N - k0;
+        bool perm_lists = false;
         int nbw = LUB_NB;                               // widest panel whose rows fit the stage
         while (nbw > 8 && (size_t)rows * nbw > (size_t)stage_doubles) nbw >>= 1;
         const bool staged = (size_t)rows * nbw <= (size_t)stage_doubles;
@@ -115,6 +121,8 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
             double* prow = stage;                                // [32] current pivot row
             double v[LUB_NB];
             int pos = (tid < rows) ? tid : -1;
+            if (tid == 0) *mvCnt = 0;                            // (visible after the first barrier below)
+            perm_lists = true;
             if (pos >= 0) {
 #pragma unroll
                 for (int j = 0; j < LUB_NB; ++j) v[j] = A[(size_t)(k0 + j) * ld + k0 + tid];
@@ -123,37 +131,38 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
                 for (int j = 0; j < LUB_NB; ++j) v[j] = 0.0;
             }
             const int aw = (rows + 31) >> 5;                     // warps that own rows
+            unsigned* rkey = reinterpret_cast<unsigned*>(redv);  // [aw][2] (hi, lo) of the warp maxima
 #pragma unroll
             for (int j = 0; j < LUB_NB; ++j) {
-                double best = -1.0;
-                int bi = 0x7fffffff;
+                // argmax of |v[j]| over the rows at positions >= j, idamax tie-breaking (smallest
+                // position), with warp REDUX instructions on the bit pattern: for non-negative
+                // doubles the (hi, lo) words order like the values, so three 32-bit reductions
+                // (max hi, max lo among the hi-maxima, min position among the exact maxima) replace
+                // five shuffle rounds on (double, int) pairs
+                unsigned mhi = 0u, mlo = 0u;
+                int p = 0x7fffffff;
                 if (warp < aw) {                                 // (the other warps only keep the barriers)
-                    best = (pos >= j) ? fabs(v[j]) : -1.0;
-                    bi = (pos >= j) ? pos : 0x7fffffff;
-                    if (best != best) best = CUDART_INF;         // a NaN candidate must surface as a bad pivot
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-                    }
-                    if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
+                    const bool cand = pos >= j;
+                    double av = fabs(v[j]);
+                    if (av != av) av = CUDART_INF;               // a NaN candidate must surface as a bad pivot
+                    const unsigned hi = cand ? (unsigned)__double2hiint(av) : 0u;
+                    const unsigned lo = cand ? (unsigned)__double2loint(av) : 0u;
+                    mhi = __reduce_max_sync(0xffffffffu, hi);
+                    mlo = __reduce_max_sync(0xffffffffu, (hi == mhi) ? lo : 0u);
+                    p = (int)__reduce_min_sync(0xffffffffu, (cand && hi == mhi && lo == mlo) ? (unsigned)pos : 0x7fffffffu);
+                    if (lane == 0) { rkey[2 * warp] = mhi; rkey[2 * warp + 1] = mlo; redi[warp] = p; }
                 }
                 __syncthreads();
                 if (warp < aw) {
                     // every row-owning warp reduces the partials redundantly (no second barrier)
-                    best = (lane < aw) ? redv[lane] : -1.0;
-                    bi = (lane < aw) ? redi[lane] : 0x7fffffff;
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-                    }
-                    best = __shfl_sync(0xffffffffu, best, 0);
-                    bi = __shfl_sync(0xffffffffu, bi, 0);
+                    const unsigned hi = (lane < aw) ? rkey[2 * lane] : 0u;
+                    const unsigned lo = (lane < aw) ? rkey[2 * lane + 1] : 0u;
+                    const unsigned pp = (lane < aw) ? (unsigned)redi[lane] : 0x7fffffffu;
+                    mhi = __reduce_max_sync(0xffffffffu, hi);
+                    mlo = __reduce_max_sync(0xffffffffu, (hi == mhi) ? lo : 0u);
+                    p = (int)__reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? pp : 0x7fffffffu);
                 }
-                const int p = bi;
+                const double best = __hiloint2double((int)mhi, (int)mlo);
                 if (!(best > 0.0) || !(best < CUDART_INF)) {
                     if (tid == 0 && *sflag == 0) *sflag = k0 + j + 1;
                 }
@@ -175,6 +184,14 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
             if (pos >= 0) {
 #pragma unroll
                 for (int j = 0; j < LUB_NB; ++j) A[(size_t)(k0 + j) * ld + k0 + pos] = v[j];
+                // the interchanges as a permutation: rows that end in the top block come from
+                // anywhere, rows that end below it always come from the top block
+                if (pos < LUB_NB) srcTop[pos] = tid;
+                else if (pos != tid) {
+                    const int e = atomicAdd(mvCnt, 1);
+                    mvSrc[e] = tid;
+                    mvDst[e] = pos;
+                }
             }
             __syncthreads();
         } else {
@@ -249,17 +266,25 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
         // ---------------- 2. interchanges + U12 = L11^{-1} A12 (incl. the rhs column N) ----------------
         for (int c = cr + tid; c <= N; c += nthr) {
             double* col = A + (size_t)c * ld;
-            for (int t = 0; t < nb; ++t) {
-                const int p = piv[t];
-                if (p != k0 + t) {
-                    const double x = col[k0 + t];
-                    col[k0 + t] = col[p];
-                    col[p] = x;
-                }
-            }
             double v[LUB_NB];
+            if (perm_lists) {
+                // independent loads instead of 32 dependent swaps (each an L2 round trip)
 #pragma unroll
-            for (int t = 0; t < LUB_NB; ++t) v[t] = (t < nb) ? col[k0 + t] : 0.0;
+                for (int t = 0; t < LUB_NB; ++t) v[t] = col[k0 + srcTop[t]];
+                const int cnt = *mvCnt;
+                for (int e = 0; e < cnt; ++e) col[k0 + mvDst[e]] = col[k0 + mvSrc[e]];
+            } else {
+                for (int t = 0; t < nb; ++t) {
+                    const int p = piv[t];
+                    if (p != k0 + t) {
+                        const double x = col[k0 + t];
+                        col[k0 + t] = col[p];
+                        col[p] = x;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < LUB_NB; ++t) v[t] = (t < nb) ? col[k0 + t] : 0.0;
+            }
 #pragma unroll
             for (int t = 1; t < LUB_NB; ++t) {
                 double acc = v[t];
@@ -268,8 +293,8 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
                 v[t] = (t < nb) ? acc : 0.0;
             }
 #pragma unroll
-            for (int t = 1; t < LUB_NB; ++t)
-                if (t < nb) col[k0 + t] = v[t];
+            for (int t = 0; t < LUB_NB; ++t)
+                if (t < nb && (t > 0 || perm_lists)) col[k0 + t] = v[t];
         }
         __syncthreads();
         if (cr >= N) break;                                      // nothing below the panel

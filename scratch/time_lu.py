@@ -25,3 +25,7 @@ Jv = sol.jacobian_view(J)
 res = (torch.einsum("bij,jb->ib", Jv[:64], dx[:, :64]) - f[:, :64]).abs().max().item()
 print("lu_solve N=%d B=%d: %.3f ms  %.2f TFLOP/s  info!=0: %d  max residual (64 scen) %.2e  |dx| max %.2e" % (
     N, B, best, fl * B / best / 1e9, int((info != 0).sum()), res, dx.abs().max().item()))
+r = sol.solve(dP, dQ, dI, dense=True); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); r = sol.solve(dP, dQ, dI, dense=True, out=r); e1.record(); torch.cuda.synchronize()
+print("dense fused solve B=%d: %.1f ms  %.0f solves/s  conv %d  mean it %.2f" % (B, e0.elapsed_time(e1), B / e0.elapsed_time(e1) * 1e3, int((r.status == 0).sum()), r.n_iter_h.double().mean().item()))
