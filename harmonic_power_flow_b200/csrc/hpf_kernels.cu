@@ -827,6 +827,7 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
             for (int k = tid; k < q; k += blockDim.x) {
                 const int sk = m + k;
                 double2 acc = make_double2(s.Vre[sk] + W[k].x, s.Vim[sk] + W[k].y);
+#pragma unroll 8
                 for (int i = 0; i < m; ++i)
                     acc = cfma(acc, ldg2(sn.GT + (size_t)i * nZ + k), make_double2(s.Vre[i], s.Vim[i]));
                 U0[k] = cneg(acc);
@@ -898,6 +899,7 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 const int sz = z + m;
                 double2 acc = make_double2(s.Vre[sz] + W[z].x, s.Vim[sz] + W[z].y);
                 const double2* gcol = sn.GT + z;
+#pragma unroll 8
                 for (int i = 0; i < m; ++i) acc = cfma(acc, ldg2(gcol + (size_t)i * nZ), UFs[i]);
                 const double2 wv = cmul(make_double2(s.Ere[sz], -s.Eim[sz]), cneg(acc));
                 const double vm = s.Vm[sz];

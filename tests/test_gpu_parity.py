@@ -756,3 +756,48 @@ def test_ybus_corrected_options_match_textbook_admittance_matrix():
     assert np.abs(Y - Y_ref_behaviour).max() > 1e-3 * np.abs(want).max()      # the quirks do matter here
     assert np.array_equal(sol.set_y_options().cpu().numpy(), Y_ref_behaviour)
     sol.close()
+
+
+@pytest.mark.parametrize("variant", [0, 2, 3])
+def test_degenerate_shapes_linear_only_and_fundamental_only(tmp_path, monkeypatch, variant):
+    """Edge shapes of the data contract: a network WITHOUT nonlinear buses (q = 0: the harmonic
+    stage has nothing to inject, harmonic voltages go to zero) and a fundamental-only run
+    (H = 1: the harmonic Newton loop works on the fundamental alone), through the tile kernel
+    and both per-CTA variants, against the oracle."""
+    from harmonic_power_flow_b200 import BatchSolver, netio
+    if variant:
+        monkeypatch.setenv("HPF_STRUCT_VARIANT", str(variant))
+    # (a) q = 0: net2 with its SMPS bus turned into a linear PQ load
+    pb, pl = helpers.write_net_csvs("net2", str(tmp_path))
+    txt = open(pb).read().replace("nonlinear", "PQ")
+    open(pb, "w").write(txt)
+    st = netio.Settings(H_MAX=9, ne_dir=str(tmp_path))
+    buses, lines, m, n, c = netio.init_network(pb, pl, st)
+    assert m == n
+    net = netio.pack_network(buses, lines, m, n, c, st.HARMONICS)
+    sol = BatchSolver(net)
+    B = 5
+    rng = np.random.default_rng(1)
+    P = net.P[:, None] * rng.uniform(0.9, 1.1, (n, B)); Q = net.Q[:, None] * rng.uniform(0.9, 1.1, (n, B))
+    res = sol.solve(P, Q, np.zeros((0, net.H, B), complex)).to_host()
+    on = helpers.oracle_net(net)
+    on.I_N = np.zeros((0, net.H), complex); on.Y_N = np.zeros((0, net.H, net.H), complex)
+    for b in range(B):
+        o = O.hpf(on, P=P[:, b], Q=Q[:, b], I_N=on.I_N)
+        assert res["status"][b] == o["status"] == 0
+        assert res["n_iter_f"][b] == o["n_iter_f"] and res["n_iter_h"][b] == o["n_iter_h"]
+        assert np.abs(res["V_m"][0, :, b] - o["V_m"][0]).max() <= 1e-12
+        assert np.abs(res["V_m"][1:, :, b]).max() <= 1e-12 and np.abs(o["V_m"][1:]).max() <= 1e-12
+    sol.close()
+    # (b) H = 1: net3 with the SMPS equivalent restricted to the fundamental
+    net1, _, _ = helpers.packed_from_files("net3", 1, True, tmp_path)
+    assert net1.H == 1 and net1.q == 1
+    sol = BatchSolver(net1)
+    res = sol.solve(net1.P[:, None], net1.Q[:, None], net1.I_N[:, :, None]).to_host()
+    o = O.hpf(helpers.oracle_net(net1))
+    assert res["status"][0] == o["status"]
+    assert res["n_iter_f"][0] == o["n_iter_f"] and res["n_iter_h"][0] == o["n_iter_h"]
+    if o["status"] == 0:
+        Vo, Vg = helpers.phasor(o["V_m"], o["V_a"]), helpers.phasor(res["V_m"][:, :, 0], res["V_a"][:, :, 0])
+        assert np.abs(Vo - Vg).max() <= 1e-9 * np.abs(Vo).max()
+    sol.close()
