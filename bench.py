@@ -535,7 +535,7 @@ def run_ours(a):
             t_kernel = ms_harm / 1e3
             fl_iter = fl_struct
         else:
-            kname = "solve_kernel<false> (fused fundamental + harmonic Newton, dense LU)"
+            kname = "solve_kernel<0> (fused fundamental + harmonic Newton, dense LU)"
             flops = it_h * fl_dense + it_f * fl_f
             t_kernel = ms_harm / 1e3
             fl_iter = fl_dense
@@ -580,7 +580,7 @@ def run_ours(a):
                 "value": dense_info["conv"] / (dense_info["ms"] / 1e3), "unit": UNIT,
                 "ms_per_step": dense_info["ms"],
                 "iteration_count_mismatches_vs_structured": dense_info["iter_mismatch_vs_structured"],
-                "roofline": {"kernel": "solve_kernel<false> (fused Newton, dense smem LU, warp-shuffle pivoting)",
+                "roofline": {"kernel": "solve_kernel<0> (fused Newton, dense smem LU, warp-shuffle pivoting)",
                              "bound": "fp64", "achieved": achd, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": achd / fp64_peak if fp64_peak else None,
                              "flops_per_nr_iteration": fl_dense}}

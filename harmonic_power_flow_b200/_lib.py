@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libhpf_b200.so")
+# $HPF_LIB: load another build of the same ABI (A/B measurements); default = the in-tree library
+LIB_PATH = os.environ.get("HPF_LIB") or os.path.join(PKG, "libhpf_b200.so")
 
 HPF_OK, HPF_E_INVALID, HPF_E_CUDA, HPF_E_UNSUPPORTED, HPF_E_NOMEM = 0, -1, -2, -3, -4
 ST_CONVERGED, ST_MAXITER, ST_SINGULAR, ST_NONFINITE = 0, 1, 2, 3

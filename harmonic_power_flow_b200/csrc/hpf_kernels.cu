@@ -294,9 +294,12 @@ static inline size_t gmem_kernel_lub_doubles(int n, int H, int q, int N, size_t 
     const size_t state = scn_smem_doubles_aligned(n, H, q, N) * sizeof(double) + 16;
     return lub_smem_doubles_for(N, optin > state ? optin - state : 0);
 }
-template <bool GMEM>
-__global__ void __launch_bounds__(GMEM ? HPF_THREADS_GMEM : HPF_THREADS)
+// LU: 0 = shared-memory LU (matrix in smem), 1 = blocked LU (matrix in the global workspace or
+// behind the work area), 2 = blocked LU for systems whose panels do not fit the staging buffer
+template <int LU>
+__global__ void __launch_bounds__(LU ? HPF_THREADS_GMEM : HPF_THREADS)
 solve_kernel(const DevNet net, const SolveArgs a) {
+    constexpr bool GMEM = LU != 0;
     extern __shared__ __align__(16) double smem[];
     ScnSmem s = carve(smem, net, !GMEM);
     const int tid = threadIdx.x;
@@ -338,7 +341,7 @@ solve_kernel(const DevNet net, const SolveArgs a) {
             cta_zero(s.A, (size_t)ld * Nf);
             __syncthreads();
             cta_fund_jacobian(net, s, s.A, 1, ld);
-            const int info = GMEM ? lu_solve_blocked(s.A, Nf, ld, lub, a.lub_doubles, s.flag)
+            const int info = GMEM ? lu_solve_blocked_t<LU == 2>(s.A, Nf, ld, lub, a.lub_doubles, s.flag)
                                   : lu_solve_smem(s.A, Nf, ld, s.rinv, s.flag);
             if (info) status = HPF_ST_SINGULAR;
             for (int t = tid; t < Nf; t += blockDim.x) {       // HG:226-235
@@ -378,7 +381,7 @@ solve_kernel(const DevNet net, const SolveArgs a) {
             cta_zero(s.A, (size_t)ld * N);
             __syncthreads();
             cta_harmonic_jacobian(net, s, s.A, 1, ld);
-            const int info = GMEM ? lu_solve_blocked(s.A, N, ld, lub, a.lub_doubles, s.flag)
+            const int info = GMEM ? lu_solve_blocked_t<LU == 2>(s.A, N, ld, lub, a.lub_doubles, s.flag)
                                   : lu_solve_smem(s.A, N, ld, s.rinv, s.flag);
             if (info && status == HPF_ST_CONVERGED) status = HPF_ST_SINGULAR;
             for (int t = tid; t < N; t += blockDim.x) {        // HG:476-485
@@ -722,9 +725,10 @@ struct LuArgs {
     int lub_doubles;
 };
 
-template <bool GMEM>
-__global__ void __launch_bounds__(GMEM ? HPF_THREADS_GMEM : HPF_THREADS)
+template <int LU>
+__global__ void __launch_bounds__(LU ? HPF_THREADS_GMEM : HPF_THREADS)
 lu_solve_kernel(const DevNet net, const LuArgs a) {
+    constexpr bool GMEM = LU != 0;
     extern __shared__ __align__(16) double smem[];
     ScnSmem s = carve(smem, net, !GMEM);
     const int N = net.N, ld = GMEM ? lub_ld(N) : odd_ld(N);
@@ -740,7 +744,7 @@ lu_solve_kernel(const DevNet net, const LuArgs a) {
         }
         double* rhs = s.A + (size_t)N * ld;
         for (int t = threadIdx.x; t < N; t += blockDim.x) rhs[t] = a.f[t * B + b];
-        const int info = GMEM ? lu_solve_blocked(s.A, N, ld, lub, a.lub_doubles, s.flag)
+        const int info = GMEM ? lu_solve_blocked_t<LU == 2>(s.A, N, ld, lub, a.lub_doubles, s.flag)
                               : lu_solve_smem(s.A, N, ld, s.rinv, s.flag);
         for (int t = threadIdx.x; t < N; t += blockDim.x) a.dx[t * B + b] = rhs[t];
         if (threadIdx.x == 0) a.info[b] = info;
@@ -768,7 +772,7 @@ static inline size_t harm_cta_gmem_lub_doubles(int nx, size_t optin) {
     return lub_smem_doubles_for(nx, optin - 80 * sizeof(double));
 }
 
-template <int THREADS>
+template <int THREADS, bool BIGLU>
 __global__ void __launch_bounds__(THREADS)
 harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -876,7 +880,7 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
             }
             int info = 0;
             if (nx > 0) {                                                   // (both start with a barrier)
-                if (gst) { __syncthreads(); info = lu_solve_blocked(Mb, nx, ldb, lub, a.lub_doubles, s.flag); }
+                if (gst) { __syncthreads(); info = lu_solve_blocked_t<BIGLU>(Mb, nx, ldb, lub, a.lub_doubles, s.flag); }
                 else info = lu_solve_smem(Mb, nx, ldb, brinv, s.flag);
             } else {
                 __syncthreads();
@@ -1150,8 +1154,10 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
                               (ws_smem ? (size_t)lub_ld(net.N) * (net.N + 1) : 0)) * sizeof(double) + 16
                            : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
     int occ = 0;
-    rc = gm ? prep_kernel(h, solve_kernel<true>, smem, who, &occ, HPF_THREADS_GMEM)
-            : prep_kernel(h, solve_kernel<false>, smem, who, &occ);
+    const bool big = gm && lub_needs_big(net.N, lubd);
+    rc = !gm ? prep_kernel(h, solve_kernel<0>, smem, who, &occ)
+             : big ? prep_kernel(h, solve_kernel<2>, smem, who, &occ, HPF_THREADS_GMEM)
+                   : prep_kernel(h, solve_kernel<1>, smem, who, &occ, HPF_THREADS_GMEM);
     if (rc) return rc;
     SolveArgs a;
     a.B = B; a.mode = mode; a.flags = flags; a.P = P; a.Q = Q; a.I_N = (const double2*)I_N;
@@ -1171,8 +1177,9 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
         a.workspace = h->d_work;
     }
     if (h->profiling) { CK(cudaEventRecord(h->ev[1], st)); }
-    if (gm) solve_kernel<true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, a);
-    else solve_kernel<false><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, a);
+    if (!gm) solve_kernel<0><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, a);
+    else if (big) solve_kernel<2><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, a);
+    else solve_kernel<1><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, a);
     if (net.H != H_full) {
         const size_t cnt = (size_t)(H_full - 1) * net.n * B;
         flat_start_fill_kernel<<<(unsigned)((cnt + 255) / 256 < 65535 * 8 ? (cnt + 255) / 256 : 65535 * 8), 256, 0, st>>>(
@@ -1392,8 +1399,10 @@ static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const H
                                 : harm_cta_smem_bytes(net.n, net.H, net.m, net.c, net.q, net.N);
         int occ = 0;
         // global-state variant: every phase waits on L2 / HBM, so it runs with twice the warps
-        int rc = gst ? prep_kernel(h, harm_cta_kernel<HPF_THREADS_GMEM>, smem, "hpf_solve", &occ, HPF_THREADS_GMEM)
-                     : prep_kernel(h, harm_cta_kernel<HPF_THREADS>, smem, "hpf_solve", &occ);
+        const bool big = gst && lub_needs_big(sn.nx, lubd);
+        int rc = !gst ? prep_kernel(h, harm_cta_kernel<HPF_THREADS, false>, smem, "hpf_solve", &occ)
+                      : big ? prep_kernel(h, harm_cta_kernel<HPF_THREADS_GMEM, true>, smem, "hpf_solve", &occ, HPF_THREADS_GMEM)
+                            : prep_kernel(h, harm_cta_kernel<HPF_THREADS_GMEM, false>, smem, "hpf_solve", &occ, HPF_THREADS_GMEM);
         if (rc) return rc;
         long long grid = ha.B;
         if ((persistent || gst) && grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
@@ -1409,8 +1418,9 @@ static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const H
             }
             ha2.gstate = h->d_gstate; ha2.gstate_stride = stride;
         }
-        if (gst) harm_cta_kernel<HPF_THREADS_GMEM><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, sn, ha2);
-        else harm_cta_kernel<HPF_THREADS><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, sn, ha2);
+        if (!gst) harm_cta_kernel<HPF_THREADS, false><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, sn, ha2);
+        else if (big) harm_cta_kernel<HPF_THREADS_GMEM, true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, sn, ha2);
+        else harm_cta_kernel<HPF_THREADS_GMEM, false><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, sn, ha2);
         h->launches++;
         CK(cudaGetLastError());
         return HPF_OK;
@@ -2031,8 +2041,10 @@ int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, 
                            : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
     a.lub_doubles = (int)lubd;
     int occ = 0;
-    rc = gm ? prep_kernel(h, lu_solve_kernel<true>, smem, "hpf_lu_solve", &occ, HPF_THREADS_GMEM)
-            : prep_kernel(h, lu_solve_kernel<false>, smem, "hpf_lu_solve", &occ);
+    const bool big = gm && lub_needs_big(net.N, lubd);
+    rc = !gm ? prep_kernel(h, lu_solve_kernel<0>, smem, "hpf_lu_solve", &occ)
+             : big ? prep_kernel(h, lu_solve_kernel<2>, smem, "hpf_lu_solve", &occ, HPF_THREADS_GMEM)
+                   : prep_kernel(h, lu_solve_kernel<1>, smem, "hpf_lu_solve", &occ, HPF_THREADS_GMEM);
     if (rc) return rc;
     long long grid = (long long)occ * h->sm_count;
     if (grid > B) grid = B;
@@ -2043,9 +2055,10 @@ int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, 
             if (rc) return rc;
             a.workspace = h->d_work;
         }
-        lu_solve_kernel<true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, (cudaStream_t)stream>>>(net, a);
+        if (big) lu_solve_kernel<2><<<(unsigned)grid, HPF_THREADS_GMEM, smem, (cudaStream_t)stream>>>(net, a);
+        else lu_solve_kernel<1><<<(unsigned)grid, HPF_THREADS_GMEM, smem, (cudaStream_t)stream>>>(net, a);
     } else {
-        lu_solve_kernel<false><<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a);
+        lu_solve_kernel<0><<<(unsigned)grid, HPF_THREADS, smem, (cudaStream_t)stream>>>(net, a);
     }
     h->launches++;
     CK(cudaGetLastError());

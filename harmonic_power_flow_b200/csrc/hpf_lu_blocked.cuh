@@ -82,13 +82,18 @@ __device__ __forceinline__ void lub_argmax(double& best, int& bi, double* redv, 
 
 // A: N x (N+1) column-major in global memory, ld even; sm: sm_doubles >= LUB_SMEM_DOUBLES doubles
 // of SHARED memory (more = wider panels for large N); sflag: one int of shared memory.
-__device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N, const int ld,
-                                             double* sm, const int sm_doubles, int* sflag) {
+// Two instances: BIG = false for systems whose first (tallest) panel fits the staging buffer - the
+// common case, compiled without the in-place global-memory panel path (its 32-element row buffer
+// costs the other paths registers: 8 % on the 200-bus configuration); BIG = true otherwise.
+template <bool BIG>
+__device__ __noinline__ int lu_solve_blocked_t(double* __restrict__ A, const int N, const int ld,
+                                               double* sm, const int sm_doubles, int* sflag) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
     double* L11 = sm;                                   // [NB][NB+1]  L11[r][c]
     double* redv = L11 + LUB_NB * (LUB_NB + 1);         // 33
     int* redi = reinterpret_cast<int*>(redv + 34);      // 33 ints
     int* piv = redi + 34;                               // NB ints
+    double* prw = redv + 72;                            // [NB] pivot row of the current panel column
     double* stage = sm + LUB_FIXED_DOUBLES;             // panel staging | L21 / U12 slices
     const int stage_doubles = sm_doubles - LUB_FIXED_DOUBLES;
     double* Ls = stage;                                 // [NB][SL]    Ls[k][r] = L21[r][k]
@@ -105,10 +110,10 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
     for (int k0 = 0; k0 < N;) {
         const int rows = N - k0;
         bool perm_lists = false;
-        int nbw = LUB_NB;                               // widest panel whose rows fit the stage
-        while (nbw > 8 && (size_t)rows * nbw > (size_t)stage_doubles) nbw >>= 1;
-        const bool staged = (size_t)rows * nbw <= (size_t)stage_doubles;
-        const int nb = min(nbw, N - k0);
+        // the panel is always 32 columns wide (a narrower panel would stream the whole trailing
+        // matrix through HBM 2-4 times more often); it is staged in shared memory when it fits
+        const bool staged = !BIG || (size_t)rows * LUB_NB <= (size_t)stage_doubles;
+        const int nb = min(LUB_NB, N - k0);
         // ---------------- 1. panel ----------------
         if (nb == LUB_NB && rows <= nthr) {
             // REGISTER panel: thread t owns one row of the panel (32 values in registers) for all
@@ -232,17 +237,44 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
                 // column j+1 feeds the next pivot search
                 best = -1.0;
                 bi = j + 1;
-                for (int i = j + 1 + tid; i < rows; i += nthr) {
-                    const double l = cj0[i] * r;
-                    cj0[i] = l;
-                    for (int jj = j + 1; jj < nb; ++jj) {
-                        double* cj = PB + (size_t)jj * ps;
-                        const double v = cj[i] - l * cj[j];
-                        cj[i] = v;
-                        if (jj == j + 1) {
-                            const double av = fabs(v);
-                            if (av > best) { best = av; bi = i; }
+                if (!BIG || staged) {
+                    for (int i = j + 1 + tid; i < rows; i += nthr) {
+                        const double l = cj0[i] * r;
+                        cj0[i] = l;
+                        for (int jj = j + 1; jj < nb; ++jj) {
+                            double* cj = PB + (size_t)jj * ps;
+                            const double v = cj[i] - l * cj[j];
+                            cj[i] = v;
+                            if (jj == j + 1) {
+                                const double av = fabs(v);
+                                if (av > best) { best = av; bi = i; }
+                            }
                         }
+                    }
+                } else {
+                    // panel in place in global memory (more rows than the stage holds): the pivot row
+                    // is first copied to shared memory, then every row issues all its loads before
+                    // the first FMA - 31 dependent L2 round trips per row become one
+                    __syncthreads();
+                    if (tid < nb) prw[tid] = PB[(size_t)tid * ps + j];
+                    __syncthreads();
+                    for (int i = j + 1 + tid; i < rows; i += nthr) {
+                        const double l = cj0[i] * r;
+                        cj0[i] = l;
+                        double t[LUB_NB];
+#pragma unroll
+                        for (int jj = 1; jj < LUB_NB; ++jj)
+                            if (jj > j && jj < nb) t[jj] = PB[(size_t)jj * ps + i];
+#pragma unroll
+                        for (int jj = 1; jj < LUB_NB; ++jj)
+                            if (jj > j && jj < nb) {
+                                t[jj] = fma(-l, prw[jj], t[jj]);
+                                PB[(size_t)jj * ps + i] = t[jj];
+                                if (jj == j + 1) {
+                                    const double av = fabs(t[jj]);
+                                    if (av > best) { best = av; bi = i; }
+                                }
+                            }
                     }
                 }
                 if (j + 1 < nb) lub_argmax(best, bi, redv, redi);   // (contains the barriers)
@@ -397,4 +429,10 @@ __device__ __noinline__ int lu_solve_blocked(double* __restrict__ A, const int N
         __syncthreads();
     }
     return *sflag;
+}
+
+// Which instance a system of order N needs with a work area of sm_doubles (host side: the kernels
+// are instantiated per instance - linking both into one kernel costs the small one 10 %).
+__host__ __device__ inline bool lub_needs_big(int N, size_t sm_doubles) {
+    return (size_t)N * LUB_NB > sm_doubles - LUB_FIXED_DOUBLES;
 }
