@@ -86,7 +86,7 @@ __device__ __forceinline__ void lub_argmax(double& best, int& bi, double* redv, 
 // common case, compiled without the in-place global-memory panel path (its 32-element row buffer
 // costs the other paths registers: 8 % on the 200-bus configuration); BIG = true otherwise.
 template <bool BIG>
-__device__ __noinline__ int lu_solve_blocked_t(double* __restrict__ A, const int N, const int ld,
+__device__ __forceinline__ int lu_solve_blocked_t(double* __restrict__ A, const int N, const int ld,
                                                double* sm, const int sm_doubles, int* sflag) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
     double* L11 = sm;                                   // [NB][NB+1]  L11[r][c]
