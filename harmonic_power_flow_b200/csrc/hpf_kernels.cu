@@ -1024,7 +1024,7 @@ struct hpf_handle {
     int force_variant = 0;        // $HPF_STRUCT_VARIANT=2|3: force a per-CTA variant of the harmonic stage
     // host mirror of the network constants for kernels that take them as parameters
     // (constant bank): fetched lazily from the device tables, see host_consts()
-    std::vector<double2> hY, hYN;
+    std::vector<double2> hY, hYN, hWNL;
     std::vector<int> hdev;
     bool host_consts_valid = false;
     double pivot_min = 0.0, pivot_max = 0.0;
@@ -1332,6 +1332,11 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(prh, pr, sizeof(prh), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(AZF); cudaFree(ipiv); cudaFree(pr); cudaFree(tmp);
+    h->hWNL.clear();
+    if (variant == 1 && e == cudaSuccess && qH > 0 && (size_t)nZ * qH <= 1024) {   // small operators: host mirror
+        h->hWNL.resize((size_t)nZ * qH);
+        e = cudaMemcpy(h->hWNL.data(), h->d_WNL, h->hWNL.size() * sizeof(double2), cudaMemcpyDeviceToHost);
+    }
     if (variant == 3) { cudaFree(h->d_Ainv); h->d_Ainv = nullptr; }    // (GBs for the 1000-bus network)
     if (e != cudaSuccess) return fail(h, HPF_E_CUDA, std::string("structured setup: ") + cudaGetErrorString(e));
     h->pivot_min = prh[0]; h->pivot_max = prh[1];
@@ -1353,6 +1358,22 @@ static int launch_wn(hpf_t* h, const DevNet& net, const StructNet& sn, int B, co
     if (qH == 0) { CK(cudaMemsetAsync(h->d_wN + off, 0, (need - off) * sizeof(double2), st)); return HPF_OK; }
     WnArgs wa;
     wa.B = B; wa.I_N = (const double2*)I_N; wa.wN = h->d_wN + off;
+    if (!h->no_specialise && h->struct_state == 1 && !h->hWNL.empty()) {
+        auto lane = [&](auto dims) -> bool {
+            using D = decltype(dims);
+            if (!(net.n == D::n && net.m == D::m && net.c == D::c && net.H == D::H && net.q == D::q)) return false;
+            static_assert(sizeof(WnConsts<D>) + sizeof(WnArgs) <= 32000, "kernel parameter space");
+            WnConsts<D> C;
+            memcpy(C.W, h->hWNL.data(), sizeof(C.W));
+            wn_lane_kernel<D><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(C, wa);
+            return true;
+        };
+        if (lane(Dims<4, 3, 2, 13, 1>()) || lane(Dims<4, 2, 1, 10, 2>())) {
+            h->launches++;
+            CK(cudaGetLastError());
+            return HPF_OK;
+        }
+    }
     const size_t smem = (size_t)(qH < HPF_WN_UCH ? qH : HPF_WN_UCH) * HPF_T * sizeof(double2) + 16;
     int occ = 0;
     int rc = prep_kernel(h, wn_tile_kernel, smem, "hpf_solve", &occ, 256);

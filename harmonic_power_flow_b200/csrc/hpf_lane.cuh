@@ -211,3 +211,35 @@ mismatch_lane_kernel(const __grid_constant__ LaneConsts<D> C, const MismatchArgs
     for (int h = 1; h < H; ++h) harmonic(std::false_type{}, h);
     a.err[b] = __longlong_as_double(mxb);
 }
+
+// Per-scenario constant of the harmonic stage, w_N = W_NL I_N (see hpf_structured.cuh), for the
+// shape-specialised 4-bus networks: one thread per scenario, its Norton currents in registers,
+// the (nZ x qH) operator a kernel parameter (constant bank), rows in a rolled loop.  Same
+// summation order as wn_tile_kernel (bit-identical results), a quarter of its time: the tile
+// kernel re-reads every current from shared memory for every row.
+template <class D>
+struct WnConsts {
+    double2 W[(D::n * D::H - D::m) * (D::q * D::H)];
+};
+
+template <class D>
+__global__ void __launch_bounds__(128)
+wn_lane_kernel(const __grid_constant__ WnConsts<D> C, const WnArgs a) {
+    constexpr int nZ = D::n * D::H - D::m, qH = D::q * D::H;
+    const size_t B = (size_t)a.B;
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double2 in[qH];
+#pragma unroll
+    for (int u = 0; u < qH; ++u) in[u] = a.I_N[(size_t)u * B + b];
+    double2* out = a.wN + b;
+#pragma unroll 1
+    for (int z = 0; z < nZ; ++z) {
+        const double2* row = C.W + z * qH;
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < qH; ++u) acc = cadd(acc, cmul(row[u], in[u]));
+        *out = acc;
+        out += B;
+    }
+}
