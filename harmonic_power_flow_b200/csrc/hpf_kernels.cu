@@ -1861,9 +1861,18 @@ int hpf_fund_solve(hpf_t* h, int B, const double* P, const double* Q, double thr
                         n_iter_f, nullptr, nullptr, err_f, nullptr, err_hist_f, nullptr, stream);
 }
 
-int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const double* I_N, double thresh_f,
-                   int max_iter_f, double thresh_h, int max_iter_h, double* V_m, double* V_a,
-                   double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status) {
+} // extern "C"
+
+// Device copies of the results that hpf_solve_host_keep leaves behind ([rows, B] layout).
+struct HostKeep {
+    double *V_m = nullptr, *V_a = nullptr, *I_inj = nullptr, *err_h = nullptr;
+    int *n_iter_f = nullptr, *n_iter_h = nullptr, *status = nullptr;
+};
+
+static int solve_host_impl(hpf_t* h, int B, const double* P, const double* Q, const double* I_N, double thresh_f,
+                           int max_iter_f, double thresh_h, int max_iter_h, double* V_m, double* V_a,
+                           double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status,
+                           const HostKeep* keep) {
     int rc = ready(h, "hpf_solve_host", true);
     if (rc) return rc;
     if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_solve_host: B < 0");
@@ -1945,6 +1954,18 @@ int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const doub
         if (e == cudaSuccess) e = cudaMemcpyAsync(n_iter_f + b0, di, Bc * sizeof(int), cudaMemcpyDeviceToHost, s_out);
         if (e == cudaSuccess) e = cudaMemcpyAsync(n_iter_h + b0, di + Bc, Bc * sizeof(int), cudaMemcpyDeviceToHost, s_out);
         if (e == cudaSuccess) e = cudaMemcpyAsync(status + b0, di + 2 * Bc, Bc * sizeof(int), cudaMemcpyDeviceToHost, s_out);
+        if (e == cudaSuccess && keep) {
+            // also leave the results on the device in the full [rows, B] layout (device-to-device
+            // 2-D copies on the compute stream, ~20 us for the whole batch)
+            e = cp2d(keep->V_m + b0, p8, dVm, w8, w8, n * H, cudaMemcpyDeviceToDevice, s_cmp);
+            if (e == cudaSuccess) e = cp2d(keep->V_a + b0, p8, dVa, w8, w8, n * H, cudaMemcpyDeviceToDevice, s_cmp);
+            if (e == cudaSuccess && keep->I_inj && I_inj && q)
+                e = cp2d(keep->I_inj + 2 * b0, p16, dInj, w16, w16, q * H, cudaMemcpyDeviceToDevice, s_cmp);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(keep->err_h + b0, dErr, Bc * sizeof(double), cudaMemcpyDeviceToDevice, s_cmp);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(keep->n_iter_f + b0, di, Bc * sizeof(int), cudaMemcpyDeviceToDevice, s_cmp);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(keep->n_iter_h + b0, di + Bc, Bc * sizeof(int), cudaMemcpyDeviceToDevice, s_cmp);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(keep->status + b0, di + 2 * Bc, Bc * sizeof(int), cudaMemcpyDeviceToDevice, s_cmp);
+        }
         if (e != cudaSuccess) break;
     }
     h->cur_slot = 0;
@@ -1955,6 +1976,29 @@ int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const doub
         if (!rc && e2 != cudaSuccess) rc = fail(h, HPF_E_CUDA, std::string("hpf_solve_host: ") + cudaGetErrorString(e2));
     }
     return rc;
+}
+
+extern "C" {
+
+int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const double* I_N, double thresh_f,
+                   int max_iter_f, double thresh_h, int max_iter_h, double* V_m, double* V_a,
+                   double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status) {
+    return solve_host_impl(h, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, V_m, V_a, I_inj,
+                           n_iter_f, n_iter_h, err_h, status, nullptr);
+}
+
+int hpf_solve_host_keep(hpf_t* h, int B, const double* P, const double* Q, const double* I_N, double thresh_f,
+                        int max_iter_f, double thresh_h, int max_iter_h, double* V_m, double* V_a,
+                        double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status,
+                        double* dV_m, double* dV_a, double* dI_inj, int* dn_iter_f, int* dn_iter_h,
+                        double* derr_h, int* dstatus) {
+    if (!dV_m || !dV_a || !dn_iter_f || !dn_iter_h || !derr_h || !dstatus)
+        return fail(h, HPF_E_INVALID, "hpf_solve_host_keep: NULL device buffer");
+    HostKeep k;
+    k.V_m = dV_m; k.V_a = dV_a; k.I_inj = dI_inj; k.err_h = derr_h;
+    k.n_iter_f = dn_iter_f; k.n_iter_h = dn_iter_h; k.status = dstatus;
+    return solve_host_impl(h, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, V_m, V_a, I_inj,
+                           n_iter_f, n_iter_h, err_h, status, &k);
 }
 
 int hpf_mismatch(hpf_t* h, int B, const double* V_m, const double* V_a, const double* P, const double* Q,

@@ -223,8 +223,11 @@ class BatchSolver:
             _ptr(out.err_hist_f), _ptr(out.err_hist_h), self._stream()))
         return out
 
-    def solve_host(self, P, Q, I_N, thresh_f=1e-6, max_iter_f=30, thresh_h=1e-4, max_iter_h=50):
-        """hpf_solve_host: numpy in, numpy out, all copies inside the C call."""
+    def solve_host(self, P, Q, I_N, thresh_f=1e-6, max_iter_f=30, thresh_h=1e-4, max_iter_h=50, keep=None):
+        """hpf_solve_host: numpy in, numpy out, all copies inside the C call.  ``keep``: a
+        BatchResult of device tensors that additionally receives the results (hpf_solve_host_keep),
+        e.g. for the NCCL gather of a multi-GPU run; ``keep=True`` allocates one (returned under
+        the key "device")."""
         n = self.net
         P = np.ascontiguousarray(P, dtype=np.float64)
         Q = np.ascontiguousarray(Q, dtype=np.float64)
@@ -239,10 +242,20 @@ class BatchSolver:
             self._host_out_key = key
         V_m, V_a, I_inj, nf, nh, st, err = self._host_out
         vp = lambda a: C.c_void_p(a.ctypes.data)
-        _lib.check(self._h, self.lib.hpf_solve_host(
+        if keep is None:
+            _lib.check(self._h, self.lib.hpf_solve_host(
+                self._h, B, vp(P), vp(Q), vp(I_N), thresh_f, max_iter_f, thresh_h, max_iter_h,
+                vp(V_m), vp(V_a), vp(I_inj), vp(nf), vp(nh), vp(err), vp(st)))
+            return dict(V_m=V_m, V_a=V_a, I_inj=I_inj, n_iter_f=nf, n_iter_h=nh, err_h=err, status=st)
+        if keep is True:
+            keep = BatchResult(self._f64(n.H, n.n, B), self._f64(n.H, n.n, B), self._c128(n.q, n.H, B),
+                               self._i32(B), self._i32(B), self._f64(B), self._i32(B))
+        _lib.check(self._h, self.lib.hpf_solve_host_keep(
             self._h, B, vp(P), vp(Q), vp(I_N), thresh_f, max_iter_f, thresh_h, max_iter_h,
-            vp(V_m), vp(V_a), vp(I_inj), vp(nf), vp(nh), vp(err), vp(st)))
-        return dict(V_m=V_m, V_a=V_a, I_inj=I_inj, n_iter_f=nf, n_iter_h=nh, err_h=err, status=st)
+            vp(V_m), vp(V_a), vp(I_inj), vp(nf), vp(nh), vp(err), vp(st),
+            _ptr(keep.V_m), _ptr(keep.V_a), _ptr(keep.I_inj), _ptr(keep.n_iter_f), _ptr(keep.n_iter_h),
+            _ptr(keep.err_h), _ptr(keep.status)))
+        return dict(V_m=V_m, V_a=V_a, I_inj=I_inj, n_iter_f=nf, n_iter_h=nh, err_h=err, status=st, device=keep)
 
     def fund_solve(self, P, Q, thresh_f=1e-6, max_iter_f=30, history=False):
         P, Q, _ = self.prepare(P, Q, None) if self.net.q == 0 else (self._dev(P, torch.float64),

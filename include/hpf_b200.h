@@ -55,7 +55,7 @@ typedef struct hpf_handle hpf_t;
 #define HPF_ST_NONFINITE    3   /* NaN/Inf in the mismatch or the state            */
 
 /* ABI version of this header: bumped on any signature change. */
-#define HPF_ABI_VERSION 7
+#define HPF_ABI_VERSION 8
 int hpf_abi_version(void);
 
 /* Lifetime.  `device` is the CUDA ordinal the handle is bound to. */
@@ -152,6 +152,18 @@ int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const doub
                    double thresh_f, int max_iter_f, double thresh_h, int max_iter_h,
                    double* V_m, double* V_a, double* I_inj,
                    int* n_iter_f, int* n_iter_h, double* err_h, int* status);
+
+/*
+ * hpf_solve_host that ALSO leaves the results on the device (d* pointers: device memory, same
+ * [rows, B] layouts) - for a caller that returns the results to its host AND feeds them to a
+ * device-side consumer, e.g. the final NCCL gather of a multi-GPU run.  dI_inj may be NULL.
+ */
+int hpf_solve_host_keep(hpf_t* h, int B, const double* P, const double* Q, const double* I_N,
+                        double thresh_f, int max_iter_f, double thresh_h, int max_iter_h,
+                        double* V_m, double* V_a, double* I_inj,
+                        int* n_iter_f, int* n_iter_h, double* err_h, int* status,
+                        double* dV_m, double* dV_a, double* dI_inj, int* dn_iter_f, int* dn_iter_h,
+                        double* derr_h, int* dstatus);
 
 /*
  * Fundamental stage only: pf() (HG:244-275).  V_m, V_a [H, n, B] receive the flat

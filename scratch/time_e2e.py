@@ -14,3 +14,8 @@ ts = []
 for _ in range(10):
     t = time.perf_counter(); r = sol.solve_host(hP, hQ, hI); ts.append(time.perf_counter() - t)
 print("chunks=%s  e2e best %.3f ms  median %.3f ms  -> %.1f M solves/s" % (os.environ.get("HPF_HOST_CHUNKS", "default"), min(ts) * 1e3, sorted(ts)[5] * 1e3, B / sorted(ts)[5] / 1e6))
+r = sol.solve_host(hP, hQ, hI, keep=True); keep = r["device"]
+ts = []
+for _ in range(10):
+    t = time.perf_counter(); r = sol.solve_host(hP, hQ, hI, keep=keep); ts.append(time.perf_counter() - t)
+print("with keep: e2e best %.3f ms  median %.3f ms" % (min(ts) * 1e3, sorted(ts)[5] * 1e3))

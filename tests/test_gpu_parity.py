@@ -287,6 +287,20 @@ def test_host_buffer_entry_point_is_bit_identical(solvers):
         assert np.array_equal(a[k], b[k]), k
 
 
+def test_host_entry_point_keeps_device_copy(solvers):
+    """hpf_solve_host_keep: the device-resident copy of the results (what a multi-GPU run feeds to
+    its final NCCL gather) equals the host results bit for bit, on a chunked batch."""
+    from harmonic_power_flow_b200 import scenarios
+    sol, net, _ = solvers("net3_c_h25")
+    B = 20000
+    P, Q, I_N = scenarios.make_batch(net, B, "tight", exact_prefix=16)
+    r = sol.solve_host(P, Q, I_N, keep=True)
+    dev = r["device"].to_host()
+    for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status"):
+        assert np.array_equal(dev[k], r[k]), k
+    assert (r["status"] == 0).all()
+
+
 def test_host_entry_point_chunked_pipeline(solvers, tmp_path):
     """B large enough for the 4-chunk copy/solve/copy pipeline with a ragged last chunk: same
     bits as the device-resident call (results do not depend on the position in the batch)."""
