@@ -1768,10 +1768,13 @@ long long hpf_jacobian_stride(const hpf_t* h) {
     return (N * N + 1) & ~1LL;
 }
 
-int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I_N, double thresh_f,
-              int max_iter_f, double thresh_h, int max_iter_h, int flags, double* V_m, double* V_a,
-              double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status,
-              double* err_hist_f, double* err_hist_h, void* stream) {
+} // extern "C"
+
+// hpf_solve proper; hpf_solve_host calls it per chunk with its own scratch slot selected.
+static int solve_dispatch(hpf_t* h, int B, const double* P, const double* Q, const double* I_N, double thresh_f,
+                          int max_iter_f, double thresh_h, int max_iter_h, int flags, double* V_m, double* V_a,
+                          double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status,
+                          double* err_hist_f, double* err_hist_h, void* stream) {
     // default strategy: structured Newton step; dense LU when forced, when the per-iteration
     // error history is wanted, or when the network does not admit the structured set-up
     if (h && !(flags & HPF_SOLVE_DENSE) && !err_hist_f && !err_hist_h && B > 0) {
@@ -1788,6 +1791,17 @@ int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I
     }
     return solve_common(h, 0, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a,
                         I_inj, n_iter_f, n_iter_h, err_h, nullptr, status, err_hist_f, err_hist_h, stream);
+}
+
+extern "C" {
+
+int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I_N, double thresh_f,
+              int max_iter_f, double thresh_h, int max_iter_h, int flags, double* V_m, double* V_a,
+              double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status,
+              double* err_hist_f, double* err_hist_h, void* stream) {
+    if (h) { h->cur_slot = 0; h->wN_slot_stride = 0; }      // (a failed hpf_solve_host may have left them set)
+    return solve_dispatch(h, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a, I_inj,
+                          n_iter_f, n_iter_h, err_h, status, err_hist_f, err_hist_h, stream);
 }
 
 int hpf_struct_info(hpf_t* h, int* available, int* nZ, double* pivot_min, double* pivot_max) {
@@ -1941,7 +1955,7 @@ static int solve_host_impl(hpf_t* h, int B, const double* P, const double* Q, co
         if (e == cudaSuccess) e = cudaEventRecord(h->ev_io[k], s_in);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(s_cmp, h->ev_io[k], 0);
         if (e != cudaSuccess) break;
-        rc = hpf_solve(h, (int)Bc, dP, dQ, dI, thresh_f, max_iter_f, thresh_h, max_iter_h, 0, dVm, dVa,
+        rc = solve_dispatch(h, (int)Bc, dP, dQ, dI, thresh_f, max_iter_f, thresh_h, max_iter_h, 0, dVm, dVa,
                        I_inj ? dInj : nullptr, di, di + Bc, dErr, di + 2 * Bc, nullptr, nullptr, s_cmp);
         if (rc) break;
         e = cudaEventRecord(h->ev_io[8 + k], s_cmp);
