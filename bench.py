@@ -85,12 +85,12 @@ def load_other(kind):
     for d in ("smps", "ev"):
         netio.write_ne_csv(os.path.join(tmp, d + "_NE.csv"), dev[d + "__freqs"], dev[d + "__Y_N_c"],
                            dev[d + "__I_N_c"], dev[d + "__Y_N_uc"], dev[d + "__I_N_uc"])
-    if kind == "net2ev":
-        tab = json.load(open(os.path.join(g, "networks.json")))["net2ev"]
-        pb, pl = os.path.join(tmp, "net2ev_buses.csv"), os.path.join(tmp, "net2ev_lines.csv")
+    if kind in ("net2ev", "net1"):
+        tab = json.load(open(os.path.join(g, "networks.json")))[kind]
+        pb, pl = os.path.join(tmp, kind + "_buses.csv"), os.path.join(tmp, kind + "_lines.csv")
         pd.DataFrame(tab["buses"]).to_csv(pb, sep=";", index=False)
         pd.DataFrame(tab["lines"]).to_csv(pl, sep=";", index=False)
-        h_max = 19
+        h_max = 19 if kind == "net2ev" else 51
     elif kind == "radial200":
         pb, pl = synthetic.radial_feeder(tmp, tmp, n=200, load_scale=0.005)
         h_max = 25
@@ -104,6 +104,8 @@ def load_other(kind):
 
 
 OTHER_CONFIGS = [
+    ("configs[0]: net1 (20 buses, 7 SMPS loads) coupled, odd harmonics <= 51 (N=1038), ONE scenario (latency)",
+     "net1", 1, 5),
     ("configs[1]: net2 + SMPS/EV Norton loads, odd harmonics <= 19 (N=78)", "net2ev", 1024, 3),
     ("configs[3]: synthetic 200-bus radial feeder, 40% nonlinear buses, odd harmonics <= 25 (N=5198)",
      "radial200", 8192, 2),
