@@ -1477,17 +1477,25 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
         int warps = 4;
         while (warps > 1 && per_warp * warps > (size_t)h->smem_optin / 2) warps >>= 1;
         const size_t smem = per_warp * warps;
-        CK(cudaFuncSetAttribute(fund_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fund_tile_kernel, warps * 32, smem));
-        if (occ < 1) return fail(h, HPF_E_UNSUPPORTED, "hpf_solve: fundamental tile kernel does not fit");
         FundTileArgs fa;
         fa.B = B; fa.P = P; fa.Q = Q; fa.thresh_f = thresh_f; fa.max_f = max_f;
         fa.V_m = V_m; fa.V_a = V_a; fa.n_iter_f = n_iter_f; fa.status = status;
         const long long tiles = ((long long)B + HPF_T - 1) / HPF_T;
-        long long grid = (tiles + warps - 1) / warps;
-        if (grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
-        fund_tile_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(net, fa);
+        auto launch = [&](auto kernel) -> int {
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, warps * 32, smem));
+            if (occ < 1) return fail(h, HPF_E_UNSUPPORTED, "hpf_solve: fundamental tile kernel does not fit");
+            long long grid = (tiles + warps - 1) / warps;
+            if (grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
+            kernel<<<(unsigned)grid, warps * 32, smem, st>>>(net, fa);
+            return HPF_OK;
+        };
+        int rcf;
+        if (!h->no_specialise && net.n == 4 && net.c == 2) rcf = launch(fund_tile_kernel<Dims<4, 3, 2, 13, 1>>);
+        else if (!h->no_specialise && net.n == 4 && net.c == 1) rcf = launch(fund_tile_kernel<Dims<4, 2, 1, 10, 2>>);
+        else rcf = launch(fund_tile_kernel<DynDims>);
+        if (rcf) return rcf;
         h->launches++;
         CK(cudaGetLastError());
     }

@@ -316,6 +316,60 @@ __device__ __forceinline__ int lane_gauss_solve(double* M, const int nx, const i
     return bad;
 }
 
+// Shape specialisation: when the network dimensions are compile-time constants every loop
+// bound and every shared-memory offset folds into immediates (about a third of the generic
+// kernel's instructions are integer address arithmetic).  Dims<0,...> = runtime dimensions.
+template <int N_, int M_, int C_, int H_, int Q_>
+struct Dims {
+    static constexpr int n = N_, m = M_, c = C_, H = H_, q = Q_;
+};
+typedef Dims<0, 0, 0, 0, 0> DynDims;
+
+// ---------------------------------------------------------------------------------------
+// Small per-lane dense solve in REGISTERS (NX known at compile time): loads the augmented
+// system from the strided smem array, Gaussian elimination with partial pivoting (per lane),
+// leaves the solution in x[].  Returns nonzero for a zero / non-finite pivot.
+template <int NX>
+__device__ __forceinline__ int lane_gauss_solve_reg(const double* M, const int lane, double* x) {
+    double A[NX][NX + 1];
+#pragma unroll
+    for (int r = 0; r < NX; ++r)
+#pragma unroll
+        for (int cc = 0; cc <= NX; ++cc) A[r][cc] = M[(r * (NX + 1) + cc) * HPF_T + lane];
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < NX; ++k) {
+        // partial pivoting without dynamic register indexing: bubble the largest row up
+#pragma unroll
+        for (int i = k + 1; i < NX; ++i) {
+            const bool sw = fabs(A[i][k]) > fabs(A[k][k]);
+#pragma unroll
+            for (int cc = k; cc <= NX; ++cc) {
+                const double t0 = A[k][cc], t1 = A[i][cc];
+                A[k][cc] = sw ? t1 : t0;
+                A[i][cc] = sw ? t0 : t1;
+            }
+        }
+        const double pv = fabs(A[k][k]);
+        if (!(pv > 0.0) || !(pv < CUDART_INF)) bad = 1;
+        const double r = 1.0 / A[k][k];
+#pragma unroll
+        for (int i = k + 1; i < NX; ++i) {
+            const double l = A[i][k] * r;
+#pragma unroll
+            for (int cc = k + 1; cc <= NX; ++cc) A[i][cc] -= l * A[k][cc];
+        }
+    }
+#pragma unroll
+    for (int k = NX - 1; k >= 0; --k) {
+        double sv = A[k][NX];
+#pragma unroll
+        for (int cc = k + 1; cc < NX; ++cc) sv -= A[k][cc] * x[cc];
+        x[k] = sv / A[k][k];
+    }
+    return bad;
+}
+
 // ---------------------------------------------------------------------------------------
 // Fundamental Newton-Raphson (HG:244-275), one lane per scenario, warps independent.
 // Writes the fundamental solution into rows 0..n-1 of V_m / V_a [H, n, B] (the harmonic
@@ -334,11 +388,15 @@ __host__ __device__ inline size_t fund_tile_doubles_per_warp(int n, int Nf) {
     return (size_t)(6 * n + 2 * n + 2 * n + Nf * (Nf + 1)) * HPF_T;
 }
 
+// (D: compile-time dimensions for the BASELINE 4-bus shapes - loops unroll, indices fold, the
+// (2n-1-c)-sized system is solved in registers; same arithmetic as the runtime-dimension instance)
+template <class D>
 __global__ void __launch_bounds__(128)
 fund_tile_kernel(const DevNet net, const FundTileArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int n = net.n, c = net.c, Nf = net.Nf;
+    const int n = D::n ? D::n : net.n, c = D::n ? D::c : net.c, Nf = D::n ? 2 * D::n - 1 - D::c : net.Nf;
+    constexpr int NFC = D::n ? 2 * D::n - 1 - D::c : 1;
     const size_t B = (size_t)a.B;
     double* base = smem + (size_t)warp * fund_tile_doubles_per_warp(n, Nf);
     double* Vm = base;            double* Va = Vm + n * HPF_T;
@@ -416,7 +474,15 @@ fund_tile_kernel(const DevNet net, const FundTileArgs a) {
                         if (j >= c) M[(ri * w + cv) * HPF_T + lane] = dV.y;
                     }
                 }
-            const int bad = lane_gauss_solve(M, Nf, lane);
+            int bad;
+            if constexpr (D::n != 0) {
+                double xs[NFC];
+                bad = lane_gauss_solve_reg<NFC>(M, lane, xs);
+#pragma unroll
+                for (int t = 0; t < NFC; ++t) M[(t * w + Nf) * HPF_T + lane] = xs[t];
+            } else {
+                bad = lane_gauss_solve(M, Nf, lane);
+            }
             if (running) {
                 if (bad) status = HPF_ST_SINGULAR;
                 for (int t = 0; t < Nf; ++t) {          // x -= dx  (HG:226-235)
@@ -533,51 +599,6 @@ __device__ __noinline__ double mod_twopi(double va) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Small per-lane dense solve in REGISTERS (NX known at compile time): loads the augmented
-// system from the strided smem array, Gaussian elimination with partial pivoting (per lane),
-// leaves the solution in x[].  Returns nonzero for a zero / non-finite pivot.
-template <int NX>
-__device__ __forceinline__ int lane_gauss_solve_reg(const double* M, const int lane, double* x) {
-    double A[NX][NX + 1];
-#pragma unroll
-    for (int r = 0; r < NX; ++r)
-#pragma unroll
-        for (int cc = 0; cc <= NX; ++cc) A[r][cc] = M[(r * (NX + 1) + cc) * HPF_T + lane];
-    int bad = 0;
-#pragma unroll
-    for (int k = 0; k < NX; ++k) {
-        // partial pivoting without dynamic register indexing: bubble the largest row up
-#pragma unroll
-        for (int i = k + 1; i < NX; ++i) {
-            const bool sw = fabs(A[i][k]) > fabs(A[k][k]);
-#pragma unroll
-            for (int cc = k; cc <= NX; ++cc) {
-                const double t0 = A[k][cc], t1 = A[i][cc];
-                A[k][cc] = sw ? t1 : t0;
-                A[i][cc] = sw ? t0 : t1;
-            }
-        }
-        const double pv = fabs(A[k][k]);
-        if (!(pv > 0.0) || !(pv < CUDART_INF)) bad = 1;
-        const double r = 1.0 / A[k][k];
-#pragma unroll
-        for (int i = k + 1; i < NX; ++i) {
-            const double l = A[i][k] * r;
-#pragma unroll
-            for (int cc = k + 1; cc <= NX; ++cc) A[i][cc] -= l * A[k][cc];
-        }
-    }
-#pragma unroll
-    for (int k = NX - 1; k >= 0; --k) {
-        double sv = A[k][NX];
-#pragma unroll
-        for (int cc = k + 1; cc < NX; ++cc) sv -= A[k][cc] * x[cc];
-        x[k] = sv / A[k][k];
-    }
-    return bad;
-}
-
-// ---------------------------------------------------------------------------------------
 // Harmonic Newton-Raphson, structured step, 32 scenarios per CTA (lane = scenario).
 //
 // Because f_I = A_ZZ V_Z + A_ZF V_F + I_N,Z is linear in V, the product -A_ZZ^{-1} f_I of the
@@ -642,15 +663,6 @@ __device__ __forceinline__ void row_loop(int start, int end, int stride, F f) {
         for (int s = start; s < end; s += stride) f(s);
     }
 }
-
-// Shape specialisation: when the network dimensions are compile-time constants every loop
-// bound and every shared-memory offset folds into immediates (about a third of the generic
-// kernel's instructions are integer address arithmetic).  Dims<0,...> = runtime dimensions.
-template <int N_, int M_, int C_, int H_, int Q_>
-struct Dims {
-    static constexpr int n = N_, m = M_, c = C_, H = H_, q = Q_;
-};
-typedef Dims<0, 0, 0, 0, 0> DynDims;
 
 template <int NW, int MINB, class D>
 __global__ void __launch_bounds__(NW * 32, MINB)
