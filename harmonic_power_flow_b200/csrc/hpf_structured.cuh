@@ -680,6 +680,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     constexpr int LR = D::n ? (D::m * (D::H - 1) + CW - 1) / CW : 0;
     const size_t B = (size_t)a.B;
 #define AT(X, i) X[(i) * HPF_T + lane]
+#define ATV(i) V2[(i) * HPF_T + lane]
     // ---- shared memory: network constants, then per-lane arrays ----
     double2* sY = reinterpret_cast<double2*>(smem);
     double2* sYN = sY + (size_t)H * n * n;
@@ -687,8 +688,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     double* p = reinterpret_cast<double*>(sG + (size_t)nZ * m);
     double* Vm = p;  p += nH * HPF_T;
     double* Va = p;  p += nH * HPF_T;
-    double* Vre = p; p += nH * HPF_T;
-    double* Vim = p; p += nH * HPF_T;
+    double2* V2 = reinterpret_cast<double2*>(p); p += 2 * nH * HPF_T;   // phasors (re, im) interleaved: one LDS.128 per operand
     double* Wre = p; p += nZ * HPF_T;      // w_N (index z = s - m), constant per scenario
     double* Wim = p; p += nZ * HPF_T;
     double* INre = p; p += q * H * HPF_T;  // I_N of the lane's scenario
@@ -761,8 +761,8 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 for (int s = 0; s < m; ++s) {
                     const double2 e = sincos_ol(AT(Va, s));
                     const double vm = AT(Vm, s);
-                    AT(Vre, s) = vm * e.x;                        // V = V_m e^{j theta} (HG:403)
-                    AT(Vim, s) = vm * e.y;
+                    ATV(s) = make_double2(vm * e.x, vm * e.y);                        // V = V_m e^{j theta} (HG:403)
+                    
                 }
             } else {
                 if (isnew) {
@@ -821,16 +821,16 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                         const int s = m + warp + r * CW;
                         if (s < nH) {
                             const double vm = AT(Vm, s);
-                            AT(Vre, s) = vm * cs_[r];
-                            AT(Vim, s) = vm * sn_[r];
+                            ATV(s) = make_double2(vm * cs_[r], vm * sn_[r]);
+                            
                         }
                     }
                 } else {
                     for (int s = m + warp; s < nH; s += CW) {
                         const double2 e = sincos_ol(AT(Va, s));
                         const double vm = AT(Vm, s);
-                        AT(Vre, s) = vm * e.x;
-                        AT(Vim, s) = vm * e.y;
+                        ATV(s) = make_double2(vm * e.x, vm * e.y);
+                        
                     }
                 }
                 cp_async_wait<1>();                 // group 0 (I_N, first w_N rows) has landed
@@ -851,10 +851,10 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                         acc = make_double2(0.0, 0.0);
                         for (int pp = 0; pp < H; ++pp) {
                             const int t2 = pp * n + i;
-                            acc = cfma(acc, row[pp], make_double2(AT(Vre, t2), AT(Vim, t2)));
+                            acc = cfma(acc, row[pp], ATV(t2));
                         }
                     } else {
-                        acc = cmul(sYN[(size_t)dev * H + h], make_double2(AT(Vre, s), AT(Vim, s)));
+                        acc = cmul(sYN[(size_t)dev * H + h], ATV(s));
                     }
                     const double2 inj = make_double2(AT(INre, u) - acc.x, AT(INim, u) - acc.y);
                     AT(IJre, u) = inj.x; AT(IJim, u) = inj.y;
@@ -862,7 +862,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     double2 f = make_double2(0.0, 0.0);
                     for (int j = 0; j < n; ++j) {
                         const int t2 = h * n + j;
-                        f = cfma(f, Yrow[j], make_double2(AT(Vre, t2), AT(Vim, t2)));
+                        f = cfma(f, Yrow[j], ATV(t2));
                     }
                     f = cadd(f, inj);
                     const double v1 = fabs(f.x), v2 = fabs(f.y);      // s >= m >= c: both parts are rows
@@ -877,7 +877,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     double2 f = make_double2(0.0, 0.0);
                     for (int j = 0; j < n; ++j) {
                         const int t2 = h * n + j;
-                        f = cfma(f, Yrow[j], make_double2(AT(Vre, t2), AT(Vim, t2)));
+                        f = cfma(f, Yrow[j], ATV(t2));
                     }
                     const double v1 = fabs(f.x), v2 = fabs(f.y);
                     const double v = (v2 != v2 || v2 > v1) ? v2 : v1;
@@ -888,10 +888,10 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 for (int i = 0; i < m; ++i) {
                     const double2* Yrow = sY + (size_t)i * n;
                     double2 f = make_double2(0.0, 0.0);
-                    for (int j = 0; j < n; ++j) f = cfma(f, Yrow[j], make_double2(AT(Vre, j), AT(Vim, j)));
+                    for (int j = 0; j < n; ++j) f = cfma(f, Yrow[j], ATV(j));
                     AT(I1re, i) = f.x; AT(I1im, i) = f.y;
                     if (i == 0) continue;                            // slack: no row
-                    const double2 v = make_double2(AT(Vre, i), AT(Vim, i));
+                    const double2 v = ATV(i);
                     const double2 sl = cmul(v, make_double2(f.x, -f.y));
                     const double2 fs = make_double2(AT(Pl, i) + sl.x, AT(Ql, i) + sl.y);
                     AT(FSre, i) = fs.x; AT(FSim, i) = fs.y;
@@ -906,7 +906,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                 const int w = nx + 1;
                 for (int i = 1; i < m; ++i) {
                     const double rvi = 1.0 / AT(Vm, i);
-                    const double2 vi = make_double2(AT(Vre, i), AT(Vim, i));
+                    const double2 vi = ATV(i);
                     const double2 ei = make_double2(vi.x * rvi, vi.y * rvi);         // V / V_m (HG:455)
                     const double2 i1 = make_double2(AT(I1re, i), AT(I1im, i));
                     const double2 jvi = cmulj(vi);
@@ -923,7 +923,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                         } else {
                             const double2 y = sY[(size_t)i * n + j];
                             const double rvj = 1.0 / AT(Vm, j);
-                            vj = make_double2(AT(Vre, j), AT(Vim, j));
+                            vj = ATV(j);
                             ej = make_double2(vj.x * rvj, vj.y * rvj);
                             if (is_v) {                               // dS_i/dV_m,j  (HG:458-459)
                                 e = cmul(vi, cconj(cmul(y, ej)));
@@ -939,7 +939,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                             const double2 y = sY[(size_t)i * n + bk];
                             if (y.x == 0.0 && y.y == 0.0) continue;
                             const double vmb = AT(Vm, bk), rvb = 1.0 / vmb;
-                            const double2 vb = make_double2(AT(Vre, bk), AT(Vim, bk));
+                            const double2 vb = ATV(bk);
                             const double2 eb = make_double2(vb.x * rvb, vb.y * rvb);
                             const double2 ak = cmul(jvi, cconj(cneg(cmul(y, vb))));    // dS_i/dtheta_b
                             const double2 vk = cmul(vi, cconj(cmul(y, eb)));           // dS_i/dV_m,b
@@ -947,7 +947,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                             if (is_rhs) {            // u0 of row z = k (closed form)
                                 uu = make_double2(vb.x + AT(Wre, k), vb.y + AT(Wim, k));
                                 for (int i2 = 0; i2 < m; ++i2)
-                                    uu = cfma(uu, sG[(size_t)k * m + i2], make_double2(AT(Vre, i2), AT(Vim, i2)));
+                                    uu = cfma(uu, sG[(size_t)k * m + i2], ATV(i2));
                                 uu = cneg(uu);
                             } else {                 // column of G T_F: G (j V_j) or G E_j
                                 uu = cmul(sG[(size_t)k * m + j], is_v ? ej : cmulj(vj));
@@ -979,7 +979,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     const double dth = AT(DXF, i - 1);
                     const double dvm = (i >= c) ? AT(DXF, nth + i - c) : 0.0;
                     const double rvi = 1.0 / AT(Vm, i);
-                    const double2 vi = make_double2(AT(Vre, i), AT(Vim, i));
+                    const double2 vi = ATV(i);
                     AT(UFre, i) = -vi.y * dth + (vi.x * rvi) * dvm;      // u_F = (j V_i) dtheta + E_i dV_m
                     AT(UFim, i) = vi.x * dth + (vi.y * rvi) * dvm;
                 }
@@ -1035,10 +1035,11 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
             // u_z = -V_z - sum_i G[z][i] (V_i + u_F,i) - w_N,z ; polar conversion; update
             row_loop<ZR>(warp, nZ, CW, [&](int z) {
                 const int s = z + m;
-                const double2 vs = make_double2(AT(Vre, s), AT(Vim, s));
+                const double2 vs = ATV(s);
                 double2 acc = make_double2(vs.x + AT(Wre, z), vs.y + AT(Wim, z));
                 for (int i = 0; i < m; ++i) {
-                    const double2 tot = make_double2(AT(Vre, i) + AT(UFre, i), AT(Vim, i) + AT(UFim, i));
+                    const double2 vf = ATV(i);
+                    const double2 tot = make_double2(vf.x + AT(UFre, i), vf.y + AT(UFim, i));
                     acc = cfma(acc, sG[(size_t)z * m + i], tot);
                 }
                 // conj(E) u with E = V / V_m:  dV_m = Re(conj(V) u) / V_m,  dtheta = Im(conj(V) u) / V_m^2
@@ -1098,4 +1099,5 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
         cur ^= 1;
     }
 #undef AT
+#undef ATV
 }
