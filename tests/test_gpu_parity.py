@@ -603,6 +603,10 @@ def test_synthetic_networks_small_against_oracle(kind, n, scale, variant, tmp_pa
     res = sol.solve(P, Q, I_N).to_host()
     assert (res["status"] == 0).all()
     _check_against_oracle(net, res, P, Q, I_N, range(0, B, 5), 1e-9)
+    # the host-buffer entry point goes through the same variant and gives the same bits
+    rh = sol.solve_host(P, Q, I_N)
+    for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status"):
+        assert np.array_equal(rh[k], res[k]), k
     sol.close()
 
 
