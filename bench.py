@@ -402,33 +402,42 @@ def run_ours(a):
 
     # ---- end to end through the host-buffer C-ABI entry point (e2e) ----
     npP, npQ, npI = hP.numpy(), hQ.numpy(), hI.numpy()
-    res_e2e, pin_cache = None, {}
+    # N > 1: the results of a rank live in ONE contiguous device slab (fields = views), so that the
+    # final gather is one NCCL collective and the copy back to the host one D2H - with several
+    # processes per host the number of driver calls per step matters
+    res_e2e = slab = host_slab = None
     d2h_stream = torch.cuda.Stream()
+    if world > 1:
+        from harmonic_power_flow_b200 import solver as hsolver
+        res_e2e, slab = sol.alloc_result_slab(B)
+        host_slab = torch.empty(slab.numel(), dtype=torch.uint8).pin_memory()
     for _ in range(max(1, a.warmup - 1)):
         r = sol.solve_host(npP, npQ, npI)
         if world > 1:
-            res_e2e = sol.solve(dP, dQ, dI, out=res_e2e)
-            hdist.gather_result(res_e2e, B * world, rank_major=True)
-            res_e2e.to_pinned(pin_cache)
+            sol.solve(dP, dQ, dI, out=res_e2e)
+            hdist.gather_slab(slab)
+            host_slab.copy_(slab)
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         if world == 1:
             r = sol.solve_host(npP, npQ, npI)
         else:
-            # shard in (pinned H2D), solve, then the single collective of the path (final NCCL gather
-            # of flags + results, rank-major, on the compute stream) OVERLAPPED with the copy of this
-            # rank's own results back to its pinned host buffers on a second stream (NVLink and PCIe
-            # are independent links)
-            res = sol.solve(hP.to(dev, non_blocking=True), hQ.to(dev, non_blocking=True),
-                            hI.to(dev, non_blocking=True), out=res_e2e)
-            res_e2e = res
+            # shard in (pinned H2D), solve into the slab, then the single collective of the path (final
+            # NCCL gather of flags + results, rank-major, on the compute stream) OVERLAPPED with the
+            # copy of this rank's own slab back to pinned host memory on a second stream (NVLink and
+            # PCIe are independent links)
+            sol.solve(hP.to(dev, non_blocking=True), hQ.to(dev, non_blocking=True),
+                      hI.to(dev, non_blocking=True), out=res_e2e)
             done = torch.cuda.Event(); done.record()
-            gathered = hdist.gather_result(res, B * world, rank_major=True)
+            gathered = hdist.gather_slab(slab)
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(done)
-                r = res.to_pinned(pin_cache)            # synchronises d2h_stream only
+                host_slab.copy_(slab, non_blocking=True)
+                d2h_stream.synchronize()
             torch.cuda.current_stream().synchronize()
+            rr = hsolver.result_from_slab(host_slab, net.H, net.n, net.q, B)
+            r = {k: getattr(rr, k).numpy() for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status")}
     barrier()
     t_e2e = time.perf_counter() - t0
     clk = clocks.stop()       # sampled over the device-timed AND the end-to-end region
@@ -557,8 +566,9 @@ def run_ours(a):
                 "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_max / a.steps * 1e3,
                         "path": ("BatchSolver.solve_host -> hpf_solve_host (C ABI, host buffers)" if world == 1 else
-                                 "per rank: pinned H2D of its shard -> hpf_solve -> NCCL all_gather of flags and "
-                                 "results (rank-major) overlapped with the D2H of the rank's own results")},
+                                 "per rank: pinned H2D of its shard -> hpf_solve into one contiguous result slab -> "
+                                 "ONE NCCL all_gather of the slabs (rank-major) overlapped with ONE D2H of the "
+                                 "rank's own slab")},
                 "roofline": {"kernel": kname, "bound": "fp64", "achieved": ach, "peak": fp64_peak,
                              "unit": "TFLOP/s", "frac": (ach / fp64_peak) if fp64_peak else None,
                              "traffic": ncu_traffic("harm_tile_kernel") if strategy == "structured" else None,

@@ -68,3 +68,13 @@ def gather_result(res, B: int, group=None, rank_major: bool = False) -> dict:
         v = getattr(res, k)
         out[k] = None if v is None else f(v, B, group)
     return out
+
+
+def gather_slab(slab: torch.Tensor, group=None) -> torch.Tensor:
+    """The final gather as ONE collective: every rank contributes its contiguous result slab
+    (solver.alloc_result_slab; equal shard sizes), the result is the rank-major [world, nbytes]
+    stack; rank r's fields are ``solver.result_from_slab(out[r], ...)`` views."""
+    world = dist.get_world_size(group)
+    out = slab.new_empty(world * slab.numel())             # concatenation along dim 0 (gloo and NCCL)
+    dist.all_gather_into_tensor(out, slab, group=group)
+    return out.view(world, slab.numel())

@@ -70,6 +70,33 @@ class BatchResult:
         return out
 
 
+def result_slab_layout(H, n, q, B):
+    """Byte offsets of the result fields in ONE contiguous slab (multi-GPU runs gather and copy
+    the slab with one collective / one D2H instead of seven): -> (dict name -> (offset, shape,
+    dtype), total bytes).  Every field starts on a 256-byte boundary."""
+    fields = [("V_m", (H, n, B), torch.float64), ("V_a", (H, n, B), torch.float64),
+              ("I_inj", (q, H, B), torch.complex128), ("err_h", (B,), torch.float64),
+              ("n_iter_f", (B,), torch.int32), ("n_iter_h", (B,), torch.int32), ("status", (B,), torch.int32)]
+    lay, off = {}, 0
+    for name, shape, dt in fields:
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        lay[name] = (off, shape, dt)
+        off = (off + nbytes + 255) // 256 * 256
+    return lay, off
+
+
+def result_from_slab(slab, H, n, q, B):
+    """BatchResult (or dict of numpy views for a CPU slab) whose fields are VIEWS into `slab`
+    (1-D uint8 tensor of result_slab_layout(...)[1] bytes)."""
+    lay, total = result_slab_layout(H, n, q, B)
+    assert slab.dtype == torch.uint8 and slab.numel() >= total
+    views = {}
+    for name, (off, shape, dt) in lay.items():
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        views[name] = slab[off:off + nbytes].view(dt).view(shape) if nbytes else None
+    return BatchResult(**views)
+
+
 class BatchSolver:
     """One handle = one GPU.  ``net`` is a PackedNet (netio.pack_network)."""
 
@@ -222,6 +249,13 @@ class BatchSolver:
             _ptr(out.n_iter_f), _ptr(out.n_iter_h), _ptr(out.err_h), _ptr(out.status),
             _ptr(out.err_hist_f), _ptr(out.err_hist_h), self._stream()))
         return out
+
+    def alloc_result_slab(self, B):
+        """-> (BatchResult whose fields are views into one contiguous device slab, the slab)."""
+        n = self.net
+        _, total = result_slab_layout(n.H, n.n, n.q, B)
+        slab = torch.empty(total, dtype=torch.uint8, device=self.device)
+        return result_from_slab(slab, n.H, n.n, n.q, B), slab
 
     def solve_host(self, P, Q, I_N, thresh_f=1e-6, max_iter_f=30, thresh_h=1e-4, max_iter_h=50, keep=None):
         """hpf_solve_host: numpy in, numpy out, all copies inside the C call.  ``keep``: a

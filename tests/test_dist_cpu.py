@@ -54,3 +54,48 @@ def test_gather_is_identity_permutation_world2(B):
         assert p.exitcode == 0
     got = sorted(q.get(timeout=10) for _ in range(2))
     assert got == [(0, True), (1, True)]
+
+
+def _slab_worker(rank, world, port, B, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from harmonic_power_flow_b200 import solver
+        H, n, nq = 3, 4, 2
+        lay, total = solver.result_slab_layout(H, n, nq, B)
+        slab = torch.zeros(total, dtype=torch.uint8)
+        res = solver.result_from_slab(slab, H, n, nq, B)
+        g = torch.Generator().manual_seed(100 + rank)
+        res.V_m.copy_(torch.rand((H, n, B), dtype=torch.float64, generator=g))
+        res.I_inj.copy_(torch.complex(torch.rand((nq, H, B), dtype=torch.float64, generator=g),
+                                      torch.rand((nq, H, B), dtype=torch.float64, generator=g)))
+        res.status.copy_(torch.randint(0, 4, (B,), dtype=torch.int32, generator=g))
+        out = hdist.gather_slab(slab)
+        ok = out.shape == (world, total)
+        for r in range(world):                       # every rank's fields come back bit for bit
+            gr = torch.Generator().manual_seed(100 + r)
+            want_V = torch.rand((H, n, B), dtype=torch.float64, generator=gr)
+            want_I = torch.complex(torch.rand((nq, H, B), dtype=torch.float64, generator=gr),
+                                   torch.rand((nq, H, B), dtype=torch.float64, generator=gr))
+            want_s = torch.randint(0, 4, (B,), dtype=torch.int32, generator=gr)
+            rr = solver.result_from_slab(out[r], H, n, nq, B)
+            ok = ok and torch.equal(rr.V_m, want_V) and torch.equal(rr.I_inj, want_I) and torch.equal(rr.status, want_s)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_result_slab_single_collective_world2():
+    """The result fields as views into one contiguous slab: one all_gather returns every rank's
+    V, I and flags bit for bit (what the multi-GPU bench uses for its final gather)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, 37, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=10) for _ in range(2))
+    assert got == [(0, True), (1, True)]
