@@ -128,3 +128,28 @@ def test_shard_bounds_cover_batch_exactly():
             for s in range(0, B, max(1, B // 13)):
                 r = s // per
                 assert spans[r][0] <= s < spans[r][1]
+
+
+def test_binary_ne_format_round_trip(tmp_path):
+    """<device>_NE.npz (next-4: the faster NE format the reference leaves as a TODO, HG:282) gives
+    exactly the table the CSV gives, and import_Norton_Equivalents picks it up when no CSV exists."""
+    import numpy as np
+    from conftest import GOLDEN
+    import os
+    from harmonic_power_flow_b200 import netio
+    dev = np.load(os.path.join(GOLDEN, "ne_devices.npz"))
+    args = (dev["smps__freqs"], dev["smps__Y_N_c"], dev["smps__I_N_c"], dev["smps__Y_N_uc"], dev["smps__I_N_uc"])
+    d_csv, d_npz = tmp_path / "csv", tmp_path / "npz"
+    d_csv.mkdir(); d_npz.mkdir()
+    netio.write_ne_csv(str(d_csv / "smps_NE.csv"), *args)
+    netio.write_ne_npz(str(d_npz / "SMPS_NE.npz"), *args)
+    a, b = netio.read_ne_csv(str(d_csv / "smps_NE.csv")), netio.read_ne_npz(str(d_npz / "SMPS_NE.npz"))
+    assert list(a.index) == list(b.index) and list(a.columns) == list(b.columns)
+    assert np.array_equal(a.to_numpy(), b.to_numpy())
+    import pandas as pd
+    buses = pd.DataFrame({"type": ["slack", "nonlinear"], "component": ["generator", "smps"]})
+    for coupled in (True, False):
+        st1, st2 = netio.Settings(H_MAX=25, ne_dir=str(d_csv)), netio.Settings(H_MAX=25, ne_dir=str(d_npz))
+        n1 = netio.import_Norton_Equivalents(buses, coupled, st1)["smps"]
+        n2 = netio.import_Norton_Equivalents(buses, coupled, st2)["smps"]
+        assert np.array_equal(np.asarray(n1[0]), np.asarray(n2[0])) and np.array_equal(np.asarray(n1[1]), np.asarray(n2[1]))
