@@ -77,10 +77,36 @@ def init_buses_from_csv(filename, settings: Settings):
     return df
 
 
-def init_network(filename_buses, filename_lines, settings: Settings):
-    """-> (buses, lines, m, n, c) with m = index of the first nonlinear bus (HG:113-128)."""
+def sort_network(buses, lines):
+    """Reorder the buses into the order the solver relies on - slack, PV.., PQ.., nonlinear..
+    (HG:83; the reference leaves the sorting as a TODO, HG:114) - keeping the file order inside
+    each class, renumber the IDs 1..n and remap the line end points.
+    -> (buses, lines, order) with order[k] = original row of the bus now at position k."""
+    rank = {"slack": 0, "PV": 1, "PQ": 2, "nonlinear": 3}
+    unknown = [t for t in buses["type"] if t not in rank]
+    if unknown:
+        raise ValueError("unknown bus type(s) %s" % sorted(set(map(str, unknown))))
+    if int((buses["type"] == "slack").sum()) != 1:
+        raise ValueError("exactly one slack bus is required")
+    order = np.array(sorted(range(len(buses)), key=lambda i: (rank[buses["type"].iloc[i]], i)))
+    old_ids = buses["ID"].to_numpy()[order]
+    new_id = {int(o): k + 1 for k, o in enumerate(old_ids)}
+    b2 = buses.iloc[order].reset_index(drop=True).copy()
+    b2["ID"] = np.arange(1, len(b2) + 1)
+    l2 = lines.copy()
+    l2["fromID"] = [new_id[int(v)] for v in lines["fromID"]]
+    l2["toID"] = [new_id[int(v)] for v in lines["toID"]]
+    return b2, l2, order
+
+
+def init_network(filename_buses, filename_lines, settings: Settings, auto_sort=False):
+    """-> (buses, lines, m, n, c) with m = index of the first nonlinear bus (HG:113-128).
+    auto_sort=True first brings the buses into the required order (``sort_network``); the default
+    keeps the reference's behaviour and refuses an unsorted file."""
     buses = init_buses_from_csv(filename_buses, settings)
     lines = init_lines_from_csv(filename_lines, settings)
+    if auto_sort:
+        buses, lines, _ = sort_network(buses, lines)
     nl = buses.index[buses["type"] == "nonlinear"]
     m = int(min(nl)) if len(nl) > 0 else len(buses)
     n = len(buses)

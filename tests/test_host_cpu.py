@@ -153,3 +153,37 @@ def test_binary_ne_format_round_trip(tmp_path):
         n1 = netio.import_Norton_Equivalents(buses, coupled, st1)["smps"]
         n2 = netio.import_Norton_Equivalents(buses, coupled, st2)["smps"]
         assert np.array_equal(np.asarray(n1[0]), np.asarray(n2[0])) and np.array_equal(np.asarray(n1[1]), np.asarray(n2[1]))
+
+
+def test_bus_auto_sorting(tmp_path):
+    """next-4: a bus file in arbitrary order (the reference's TODO, HG:114) is brought into
+    slack, PV.., PQ.., nonlinear.. order with consistent line end points; Y(h) of the sorted
+    network is the permuted Y(h) of a hand-sorted one (checked with the oracle's assembly)."""
+    import numpy as np
+    import pandas as pd
+    import hpf_oracle as O
+    from harmonic_power_flow_b200 import netio
+    st = netio.Settings(H_MAX=7)
+    buses = pd.DataFrame({"ID": [1, 2, 3, 4, 5], "type": ["PQ", "nonlinear", "slack", "PV", "PQ"],
+                          "component": ["l1", "smps", "gen", "g2", "l2"], "S": [0.0] * 5,
+                          "P": [0.1, 0.25, 0.0, -0.2, 0.05], "Q": [0.1, 0.1, 0.0, 0.0, 0.02],
+                          "X_sh": [0.0, 0.0, 3e-5, 0.0, 0.0]})
+    lines = pd.DataFrame({"ID": [1, 2, 3, 4, 5], "fromID": [3, 1, 4, 5, 2], "toID": [1, 4, 5, 2, 3],
+                          "R": [0.003, 0.006, 0.003, 0.004, 0.005], "X": [0.003, 0.025, 0.006, 0.01, 0.02],
+                          "G": [0.0] * 5, "B": [0.0] * 5})
+    with pytest.raises(ValueError):
+        netio.check_bus_order(buses, 1, 2)
+    b2, l2, order = netio.sort_network(buses, lines)
+    assert list(b2["type"]) == ["slack", "PV", "PQ", "PQ", "nonlinear"] and list(order) == [2, 3, 0, 4, 1]
+    assert list(b2["ID"]) == [1, 2, 3, 4, 5] and list(b2["component"]) == ["gen", "g2", "l1", "l2", "smps"]
+    netio.check_bus_order(b2, 4, 2)
+    # same physical branches: end points map through the permutation
+    pos = {int(old): k + 1 for k, old in enumerate(buses["ID"].to_numpy()[order])}
+    assert list(l2["fromID"]) == [pos[v] for v in lines["fromID"]] and list(l2["toID"]) == [pos[v] for v in lines["toID"]]
+    mk = lambda b, l: O.Net(n=5, m=4, c=2, harmonics=np.array([1, 3, 5, 7]), line_from=l["fromID"].to_numpy(),
+                            line_to=l["toID"].to_numpy(), R=l["R"].to_numpy(), X=l["X"].to_numpy(),
+                            G=l["G"].to_numpy(), B=l["B"].to_numpy(), X_sh=b["X_sh"].to_numpy(),
+                            P=b["P"].to_numpy(), Q=b["Q"].to_numpy())
+    Y_sorted = O.build_admittance_matrices(mk(b2, l2))
+    Y_orig = O.build_admittance_matrices(mk(buses, lines))
+    assert np.abs(Y_sorted - Y_orig[:, order][:, :, order]).max() <= 1e-12 * np.abs(Y_orig).max()
