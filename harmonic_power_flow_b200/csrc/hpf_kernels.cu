@@ -984,6 +984,41 @@ __global__ void thd_kernel(int n, int H, const int* __restrict__ harmonics, int 
 }
 
 // =======================================================================================
+// Per-bus current spectra I = Y(h) V (post-processing next to get_THD; the quantity the
+// reference logs in the I_log.json layout): one thread per (harmonic, bus, scenario), coalesced
+// over the batch, through the sparsity pattern of Y(h) when the handle has one.
+__global__ void bus_currents_kernel(const DevNet net, int B, const double* __restrict__ V_m,
+                                    const double* __restrict__ V_a, double2* __restrict__ I_bus) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)net.nH * B;
+    if (idx >= total) return;
+    const int s = (int)(idx / B), h = s / net.n, i = s - h * net.n;
+    const size_t b = idx - (size_t)s * B;
+    const double2* Yrow = net.Y + ((size_t)h * net.n + i) * net.n;
+    double2 acc = make_double2(0.0, 0.0);
+    auto term = [&](int j) {
+        const double2 y = ldg2(Yrow + j);
+        if (y.x == 0.0 && y.y == 0.0) return;
+        const size_t t = (size_t)(h * net.n + j) * B + b;
+        double sn, cs;
+        sincos(V_a[t], &sn, &cs);
+        const double vm = V_m[t];
+        acc = cfma(acc, y, make_double2(vm * cs, vm * sn));
+    };
+    if (net.ell_col) {
+        const int* cols = net.ell_col + (size_t)i * net.ell_w;
+        for (int e = 0; e < net.ell_w; ++e) {
+            const int j = cols[e];
+            if (j < 0) break;
+            term(j);
+        }
+    } else {
+        for (int j = 0; j < net.n; ++j) term(j);
+    }
+    I_bus[idx] = acc;
+}
+
+// =======================================================================================
 // Host side: handle + C ABI
 struct hpf_handle {
     int device = 0;
@@ -1739,6 +1774,21 @@ int hpf_thd(hpf_t* h, int B, const double* V_m, double* thd, void* stream) {
     const size_t total = (size_t)h->n * B;
     thd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->n, h->H, h->d_harm, B,
                                                                                     V_m, thd);
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+int hpf_bus_currents(hpf_t* h, int B, const double* V_m, const double* V_a, double* I_bus, void* stream) {
+    int rc = ready(h, "hpf_bus_currents", false);
+    if (rc) return rc;
+    if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_bus_currents: B < 0");
+    if (!V_m || !V_a || !I_bus) return fail(h, HPF_E_INVALID, "hpf_bus_currents: NULL buffer");
+    CK(cudaSetDevice(h->device));
+    const DevNet net = devnet(h);
+    const size_t total = (size_t)net.nH * B;
+    bus_currents_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        net, B, V_m, V_a, (double2*)I_bus);
     h->launches++;
     CK(cudaGetLastError());
     return HPF_OK;

@@ -170,6 +170,14 @@ class BatchSolver:
         _lib.check(self._h, self.lib.hpf_build_Y(self._h, _ptr(Y), self._stream()))
         return Y
 
+    def bus_currents(self, V_m, V_a):
+        """Per-bus current spectra I = Y(h) V, complex [H, n, B] (hpf_bus_currents)."""
+        V_m, V_a = self._dev(V_m, torch.float64), self._dev(V_a, torch.float64)
+        B = V_m.shape[2]
+        out = self._c128(self.net.H, self.net.n, B)
+        _lib.check(self._h, self.lib.hpf_bus_currents(self._h, B, _ptr(V_m), _ptr(V_a), _ptr(out), self._stream()))
+        return out
+
     def set_transformers(self, tau=None, phase_shift_deg=None):
         """Transformer taps / phase shifts per line (FPF/pi_trafo_pf_test.py:117-145) and rebuild
         Y(h); ``None`` restores plain lines."""

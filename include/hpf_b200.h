@@ -55,7 +55,7 @@ typedef struct hpf_handle hpf_t;
 #define HPF_ST_NONFINITE    3   /* NaN/Inf in the mismatch or the state            */
 
 /* ABI version of this header: bumped on any signature change. */
-#define HPF_ABI_VERSION 8
+#define HPF_ABI_VERSION 9
 int hpf_abi_version(void);
 
 /* Lifetime.  `device` is the CUDA ordinal the handle is bound to. */
@@ -231,6 +231,13 @@ int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a,
  *   in : V_m [H, n, B];  out: thd [2, n, B]  (plane 0 = THD_F, plane 1 = THD_R)
  */
 int hpf_thd(hpf_t* h, int B, const double* V_m, double* thd, void* stream);
+
+/*
+ * Post-processing after the path: per-bus current spectra I[h][i] = sum_j Y(h)[i][j] V[h][j] (what
+ * the reference logs in the I_log.json layout: harmonic x bus, real and imaginary part).
+ *   in : V_m, V_a [H, n, B];  out: I_bus complex [H, n, B]
+ */
+int hpf_bus_currents(hpf_t* h, int B, const double* V_m, const double* V_a, double* I_bus, void* stream);
 
 /*
  * Before the path - Norton-equivalent extraction from simulated measurements, the arithmetic of

@@ -819,3 +819,19 @@ def test_degenerate_shapes_linear_only_and_fundamental_only(tmp_path, monkeypatc
         Vo, Vg = helpers.phasor(o["V_m"], o["V_a"]), helpers.phasor(res["V_m"][:, :, 0], res["V_a"][:, :, 0])
         assert np.abs(Vo - Vg).max() <= 1e-9 * np.abs(Vo).max()
     sol.close()
+
+
+@pytest.mark.parametrize("case", ["net3_c_h25", "net1_c_h25"])
+def test_bus_current_spectra(solvers, case):
+    """hpf_bus_currents (next-2): I = Y(h) V per harmonic and bus against numpy on the reference's
+    converged voltages; at the nonlinear buses the current balance makes it equal -I_inj."""
+    sol, net, d = solvers(case)
+    r = sol.solve(net.P[:, None], net.Q[:, None], net.I_N[:, :, None])
+    I = sol.bus_currents(r.V_m, r.V_a).cpu().numpy()[:, :, 0]
+    V = helpers.phasor(r.V_m.cpu().numpy()[:, :, 0], r.V_a.cpu().numpy()[:, :, 0])
+    Y = sol.Y.cpu().numpy()
+    want = np.einsum("hij,hj->hi", Y, V)
+    assert np.abs(I - want).max() <= 1e-12 * np.abs(want).max()
+    inj = r.I_inj.cpu().numpy()[:, :, 0]                       # [q, H]
+    resid = np.abs(I[:, net.m:].T + inj).max()
+    assert resid <= 2e-4                                        # the accepted current mismatch (thresh_h = 1e-4)
