@@ -338,20 +338,13 @@ __device__ __forceinline__ int lu_solve_blocked_t(double* __restrict__ A, const 
                 Ls[k * LUB_SL + r] = (k < nb && r0 + r < N) ? A[(size_t)(k0 + k) * ld + r0 + r] : 0.0;
             }
             for (int c0 = cr; c0 <= N; c0 += LUB_TC) {
-                __syncthreads();                                 // previous Us consumers done (and Ls visible)
-                for (int t = tid; t < LUB_TC * LUB_NB; t += nthr) {
-                    const int c = t / LUB_NB, k = t - c * LUB_NB;
-                    Us[c * LUB_SU + k] = (k < nb && c0 + c <= N) ? -A[(size_t)(c0 + c) * ld + k0 + k] : 0.0;
-                }
-                __syncthreads();
                 constexpr int SUBR = LUB_TR / 32, SUBC = LUB_TC / 32;
-                for (int st = warp; st < SUBR * SUBC; st += nw) {
+                const int fr = lane >> 2, fk = lane & 3;         // fragment row / k index
+                double acc[4][4][2];
+                // C fragment of sub-tile st: D[c = cb + 8 ic + fr][r = rb + 8 ir + 2 fk + {0,1}]
+                auto load_c = [&](const int st) {
                     const int sc = st / SUBR, sr = st - sc * SUBR;
                     const int cb = c0 + sc * 32, rb = r0 + sr * 32;
-                    if (cb > N || rb >= N) continue;
-                    const int fr = lane >> 2, fk = lane & 3;     // fragment row / k index
-                    double acc[4][4][2];
-                    // C fragment: D[c = cb + 8 ic + fr][r = rb + 8 ir + 2 fk + {0,1}]
 #pragma unroll
                     for (int ic = 0; ic < 4; ++ic)
 #pragma unroll
@@ -365,6 +358,18 @@ __device__ __forceinline__ int lu_solve_blocked_t(double* __restrict__ A, const 
                                 acc[ic][ir][1] = 0.0;
                             }
                         }
+                };
+                __syncthreads();                                 // previous Us consumers done (and Ls visible)
+                for (int t = tid; t < LUB_TC * LUB_NB; t += nthr) {
+                    const int c = t / LUB_NB, k = t - c * LUB_NB;
+                    Us[c * LUB_SU + k] = (k < nb && c0 + c <= N) ? -A[(size_t)(c0 + c) * ld + k0 + k] : 0.0;
+                }
+                __syncthreads();
+                for (int st = warp; st < SUBR * SUBC; st += nw) {
+                    const int sc = st / SUBR, sr = st - sc * SUBR;
+                    const int cb = c0 + sc * 32, rb = r0 + sr * 32;
+                    if (cb > N || rb >= N) continue;
+                    load_c(st);
                     const double* us = Us + (sc * 32 + fr) * LUB_SU + fk;
                     const double* ls = Ls + fk * LUB_SL + sr * 32 + fr;
                     const int nbk = (nb + 3) & ~3;               // (rows k >= nb of the slices are zero)
