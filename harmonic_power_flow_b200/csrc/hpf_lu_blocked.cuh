@@ -48,6 +48,14 @@ __host__ __device__ inline size_t lub_smem_doubles_for(int N, size_t cap_bytes) 
 
 __host__ __device__ inline int lub_ld(int N) { return (N + 7) & ~7; }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); nbytes = 0 writes zeros without reading
+__device__ __forceinline__ void lub_cp_async16(void* sdst, const void* gsrc, const int nbytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(sa), "l"(gsrc), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void lub_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void lub_cp_async_wait() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 __device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -80,6 +88,106 @@ __device__ __forceinline__ void lub_argmax(double& best, int& bi, double* redv, 
     bi = redi[32];
 }
 
+// Trailing update of the large-matrix instance: C[r][c] -= sum_{k < K} L[r][kbase + k] U[kbase + k][c]
+// for rows rb <= r < re and columns cb <= c <= ce, on the FP64 tensor cores.  K = 32 (one panel)
+// or 64 (a PAIR of panels: the trailing matrix then streams through HBM once per 64 columns
+// instead of once per 32, see lu_solve_blocked_t).  Called by every thread of the CTA after a
+// barrier; ends with a barrier.  Kept out of line: one copy of the code for its three call sites
+// and its own register allocation.
+#define LUB_STAGE_DOUBLES_K64 (64 * LUB_SL + LUB_TC * (64 + 4))
+__device__ __noinline__ void lub_update_big(double* __restrict__ A, const int ld, const int kbase, const int K,
+                                            const int rb, const int re, const int cb0, const int ce,
+                                            double* stage, const int stage_doubles) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
+    const int su = K + 4, ksh = (K == 64) ? 6 : 5;               // (stride mod 16 == 4: conflict-free fragments)
+    double* Ls = stage;                                          // [K][SL]   Ls[k][r] = -L[r0 + r][kbase + k]
+    double* Us = Ls + K * LUB_SL;                                // [TC][su]  Us[c][k] = U[kbase + k][c]
+    constexpr int SUBR = LUB_TR / 32, SUBC = LUB_TC / 32;
+    // the U slice of the NEXT column tile is copied asynchronously (LDGSTS, no registers) into a
+    // second buffer while this tile is multiplied, when the work area holds two of them; the
+    // sign of the product therefore lives in the L slice
+    const bool dbuf = stage_doubles >= K * LUB_SL + 2 * LUB_TC * su;
+    double* Us1 = dbuf ? Us + LUB_TC * su : Us;
+    auto stage_u = [&](double* U, const int c0) {
+        for (int t = tid; t < LUB_TC * (K >> 1); t += nthr) {
+            const int c = t >> (ksh - 1), k = (t & ((K >> 1) - 1)) << 1;
+            const bool in = c0 + c <= ce;
+            lub_cp_async16(U + c * su + k, in ? A + (size_t)(c0 + c) * ld + kbase + k : A, in ? 16 : 0);
+        }
+        lub_cp_async_commit();
+    };
+    const int fr = lane >> 2, fk = lane & 3;                     // fragment row / k index
+    for (int r0 = rb; r0 < re; r0 += LUB_TR) {
+        for (int t = tid; t < K * LUB_TR; t += nthr) {
+            const int k = t / LUB_TR, r = t - k * LUB_TR;
+            Ls[k * LUB_SL + r] = (r0 + r < re) ? -A[(size_t)(kbase + k) * ld + r0 + r] : 0.0;
+        }
+        int buf = 0;
+        if (dbuf) stage_u(Us, cb0);
+        for (int c0 = cb0; c0 <= ce; c0 += LUB_TC) {
+            if (!dbuf) {
+                __syncthreads();                                 // previous Us consumers done
+                stage_u(Us, c0);
+            }
+            lub_cp_async_wait();
+            __syncthreads();                                     // slices visible; the other buffer is free
+            const double* Uc = buf ? Us1 : Us;
+            if (dbuf) {
+                if (c0 + LUB_TC <= ce) stage_u(buf ? Us : Us1, c0 + LUB_TC);
+                buf ^= 1;
+            }
+            for (int st = warp; st < SUBR * SUBC; st += nw) {
+                const int sc = st / SUBR, sr = st - sc * SUBR;
+                const int cb = c0 + sc * 32, rbb = r0 + sr * 32;
+                if (cb > ce || rbb >= re) continue;
+                double acc[4][4][2];
+                // C fragment: D[c = cb + 8 ic + fr][r = rbb + 8 ir + 2 fk + {0,1}]
+#pragma unroll
+                for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                    for (int ir = 0; ir < 4; ++ir) {
+                        const int c = cb + 8 * ic + fr, r = rbb + 8 * ir + 2 * fk;
+                        if (c <= ce && r + 1 < re) {
+                            const double2 v2 = *reinterpret_cast<const double2*>(A + (size_t)c * ld + r);
+                            acc[ic][ir][0] = v2.x; acc[ic][ir][1] = v2.y;
+                        } else {
+                            acc[ic][ir][0] = (c <= ce && r < re) ? A[(size_t)c * ld + r] : 0.0;
+                            acc[ic][ir][1] = 0.0;
+                        }
+                    }
+                const double* us = Uc + (sc * 32 + fr) * su + fk;
+                const double* ls = Ls + fk * LUB_SL + sr * 32 + fr;
+#pragma unroll 2
+                for (int kk = 0; kk < K; kk += 4) {
+                    double af[4], bf[4];
+#pragma unroll
+                    for (int ic = 0; ic < 4; ++ic) af[ic] = us[(8 * ic) * su + kk];
+#pragma unroll
+                    for (int ir = 0; ir < 4; ++ir) bf[ir] = ls[kk * LUB_SL + 8 * ir];
+#pragma unroll
+                    for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                        for (int ir = 0; ir < 4; ++ir)
+                            dmma884(acc[ic][ir][0], acc[ic][ir][1], af[ic], bf[ir]);
+                }
+#pragma unroll
+                for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                    for (int ir = 0; ir < 4; ++ir) {
+                        const int c = cb + 8 * ic + fr, r = rbb + 8 * ir + 2 * fk;
+                        if (c <= ce && r + 1 < re) {
+                            *reinterpret_cast<double2*>(A + (size_t)c * ld + r) =
+                                make_double2(acc[ic][ir][0], acc[ic][ir][1]);
+                        } else if (c <= ce && r < re) {
+                            A[(size_t)c * ld + r] = acc[ic][ir][0];
+                        }
+                    }
+            }
+        }
+        __syncthreads();                                         // before Ls is overwritten
+    }
+}
+
 // A: N x (N+1) column-major in global memory, ld even; sm: sm_doubles >= LUB_SMEM_DOUBLES doubles
 // of SHARED memory (more = wider panels for large N); sflag: one int of shared memory.
 // Two instances: BIG = false for systems whose first (tallest) panel fits the staging buffer - the
@@ -107,6 +215,7 @@ __device__ __forceinline__ int lu_solve_blocked_t(double* __restrict__ A, const 
     int* mvSrc = srcTop + LUB_NB;                       // [<= NB] rows that leave the top block ...
     int* mvDst = mvSrc + LUB_NB;                        //         ... and the positions they end at
     int* mvCnt = mvDst + LUB_NB;
+    bool deferred = false;                              // (BIG) first panel of a pair factored, its update pending
     for (int k0 = 0; k0 < N;) {
         const int rows = N - k0;
         bool perm_lists = false;
@@ -289,6 +398,55 @@ __device__ __forceinline__ int lu_solve_blocked_t(double* __restrict__ A, const 
             }
         }
         const int cr = k0 + nb;                                  // first row / column of the trailing part
+        if constexpr (BIG) {
+            if (deferred) {
+                // SECOND panel of a pair (columns k0 .. k0+31; the first one is k0-32 .. k0-1 and
+                // has been applied to this panel's columns only).
+                // 2a. this panel's interchanges, on the columns to the right AND on the first
+                //     panel's L21 (its rows move with the rows of the trailing matrix)
+                for (int t2 = tid; t2 < LUB_NB + (N + 1 - cr); t2 += nthr) {
+                    double* col = A + (size_t)(t2 < LUB_NB ? k0 - LUB_NB + t2 : cr + (t2 - LUB_NB)) * ld;
+                    for (int t = 0; t < nb; ++t) {
+                        const int p = piv[t];
+                        if (p != k0 + t) {
+                            const double x = col[k0 + t];
+                            col[k0 + t] = col[p];
+                            col[p] = x;
+                        }
+                    }
+                }
+                __syncthreads();
+                // 2b. the first panel's contribution to this panel's 32 pivot rows
+                lub_update_big(A, ld, k0 - LUB_NB, LUB_NB, k0, cr, cr, N, stage, stage_doubles);
+                for (int t = tid; t < nb * nb; t += nthr) {
+                    const int c = t / nb, r = t - c * nb;
+                    L11[r * (LUB_NB + 1) + c] = A[(size_t)(k0 + c) * ld + k0 + r];
+                }
+                __syncthreads();
+                // 2c. U12 = L11^{-1} A12 for this panel's rows
+                for (int c = cr + tid; c <= N; c += nthr) {
+                    double* col = A + (size_t)c * ld;
+                    double v[LUB_NB];
+#pragma unroll
+                    for (int t = 0; t < LUB_NB; ++t) v[t] = col[k0 + t];
+#pragma unroll
+                    for (int t = 1; t < LUB_NB; ++t) {
+                        double acc = v[t];
+#pragma unroll
+                        for (int s2 = 0; s2 < t; ++s2) acc = fma(-L11[t * (LUB_NB + 1) + s2], v[s2], acc);
+                        v[t] = acc;
+                    }
+#pragma unroll
+                    for (int t = 1; t < LUB_NB; ++t) col[k0 + t] = v[t];
+                }
+                __syncthreads();
+                // 3. rank-64 update of the trailing matrix with both panels
+                lub_update_big(A, ld, k0 - LUB_NB, 2 * LUB_NB, cr, N, cr, N, stage, stage_doubles);
+                deferred = false;
+                k0 = cr;
+                continue;
+            }
+        }
         // L11 -> smem
         for (int t = tid; t < nb * nb; t += nthr) {
             const int c = t / nb, r = t - c * nb;
@@ -331,76 +489,87 @@ __device__ __forceinline__ int lu_solve_blocked_t(double* __restrict__ A, const 
         __syncthreads();
         if (cr >= N) break;                                      // nothing below the panel
         // ---------------- 3. trailing update on the tensor cores ----------------
-        for (int r0 = cr; r0 < N; r0 += LUB_TR) {
-            // L21 slice: Ls[k][r] = A[r0 + r][k0 + k]
-            for (int t = tid; t < LUB_NB * LUB_TR; t += nthr) {
-                const int k = t / LUB_TR, r = t - k * LUB_TR;
-                Ls[k * LUB_SL + r] = (k < nb && r0 + r < N) ? A[(size_t)(k0 + k) * ld + r0 + r] : 0.0;
-            }
-            for (int c0 = cr; c0 <= N; c0 += LUB_TC) {
-                constexpr int SUBR = LUB_TR / 32, SUBC = LUB_TC / 32;
-                const int fr = lane >> 2, fk = lane & 3;         // fragment row / k index
-                double acc[4][4][2];
-                // C fragment of sub-tile st: D[c = cb + 8 ic + fr][r = rb + 8 ir + 2 fk + {0,1}]
-                auto load_c = [&](const int st) {
-                    const int sc = st / SUBR, sr = st - sc * SUBR;
-                    const int cb = c0 + sc * 32, rb = r0 + sr * 32;
-#pragma unroll
-                    for (int ic = 0; ic < 4; ++ic)
-#pragma unroll
-                        for (int ir = 0; ir < 4; ++ir) {
-                            const int c = cb + 8 * ic + fr, r = rb + 8 * ir + 2 * fk;
-                            if (c <= N && r + 1 < N) {
-                                const double2 v2 = *reinterpret_cast<const double2*>(A + (size_t)c * ld + r);
-                                acc[ic][ir][0] = v2.x; acc[ic][ir][1] = v2.y;
-                            } else {
-                                acc[ic][ir][0] = (c <= N && r < N) ? A[(size_t)c * ld + r] : 0.0;
-                                acc[ic][ir][1] = 0.0;
-                            }
-                        }
-                };
-                __syncthreads();                                 // previous Us consumers done (and Ls visible)
-                for (int t = tid; t < LUB_TC * LUB_NB; t += nthr) {
-                    const int c = t / LUB_NB, k = t - c * LUB_NB;
-                    Us[c * LUB_SU + k] = (k < nb && c0 + c <= N) ? -A[(size_t)(c0 + c) * ld + k0 + k] : 0.0;
+        if constexpr (BIG) {
+            // Panels are processed in PAIRS while they are factored in place / from the stage (more
+            // rows than threads): the first panel is applied to the second panel's 32 columns only,
+            // the rest of the trailing matrix then takes both panels in one rank-64 pass - half the
+            // HBM traffic of the update, which bounds the large instance.
+            const bool pair = nb == LUB_NB && !perm_lists && N - cr > nthr &&
+                              stage_doubles >= LUB_STAGE_DOUBLES_K64;
+            lub_update_big(A, ld, k0, LUB_NB, cr, N, cr, pair ? cr + LUB_NB - 1 : N, stage, stage_doubles);
+            deferred = pair;
+        } else {
+            for (int r0 = cr; r0 < N; r0 += LUB_TR) {
+                // L21 slice: Ls[k][r] = A[r0 + r][k0 + k]
+                for (int t = tid; t < LUB_NB * LUB_TR; t += nthr) {
+                    const int k = t / LUB_TR, r = t - k * LUB_TR;
+                    Ls[k * LUB_SL + r] = (k < nb && r0 + r < N) ? A[(size_t)(k0 + k) * ld + r0 + r] : 0.0;
                 }
-                __syncthreads();
-                for (int st = warp; st < SUBR * SUBC; st += nw) {
-                    const int sc = st / SUBR, sr = st - sc * SUBR;
-                    const int cb = c0 + sc * 32, rb = r0 + sr * 32;
-                    if (cb > N || rb >= N) continue;
-                    load_c(st);
-                    const double* us = Us + (sc * 32 + fr) * LUB_SU + fk;
-                    const double* ls = Ls + fk * LUB_SL + sr * 32 + fr;
-                    const int nbk = (nb + 3) & ~3;               // (rows k >= nb of the slices are zero)
-#pragma unroll 2
-                    for (int kk = 0; kk < nbk; kk += 4) {
-                        double af[4], bf[4];
-#pragma unroll
-                        for (int ic = 0; ic < 4; ++ic) af[ic] = us[(8 * ic) * LUB_SU + kk];
-#pragma unroll
-                        for (int ir = 0; ir < 4; ++ir) bf[ir] = ls[kk * LUB_SL + 8 * ir];
-#pragma unroll
+                for (int c0 = cr; c0 <= N; c0 += LUB_TC) {
+                    constexpr int SUBR = LUB_TR / 32, SUBC = LUB_TC / 32;
+                    const int fr = lane >> 2, fk = lane & 3;         // fragment row / k index
+                    double acc[4][4][2];
+                    // C fragment of sub-tile st: D[c = cb + 8 ic + fr][r = rb + 8 ir + 2 fk + {0,1}]
+                    auto load_c = [&](const int st) {
+                        const int sc = st / SUBR, sr = st - sc * SUBR;
+                        const int cb = c0 + sc * 32, rb = r0 + sr * 32;
+    #pragma unroll
                         for (int ic = 0; ic < 4; ++ic)
-#pragma unroll
-                            for (int ir = 0; ir < 4; ++ir)
-                                dmma884(acc[ic][ir][0], acc[ic][ir][1], af[ic], bf[ir]);
-                    }
-#pragma unroll
-                    for (int ic = 0; ic < 4; ++ic)
-#pragma unroll
-                        for (int ir = 0; ir < 4; ++ir) {
-                            const int c = cb + 8 * ic + fr, r = rb + 8 * ir + 2 * fk;
-                            if (c <= N && r + 1 < N) {
-                                *reinterpret_cast<double2*>(A + (size_t)c * ld + r) =
-                                    make_double2(acc[ic][ir][0], acc[ic][ir][1]);
-                            } else if (c <= N && r < N) {
-                                A[(size_t)c * ld + r] = acc[ic][ir][0];
+    #pragma unroll
+                            for (int ir = 0; ir < 4; ++ir) {
+                                const int c = cb + 8 * ic + fr, r = rb + 8 * ir + 2 * fk;
+                                if (c <= N && r + 1 < N) {
+                                    const double2 v2 = *reinterpret_cast<const double2*>(A + (size_t)c * ld + r);
+                                    acc[ic][ir][0] = v2.x; acc[ic][ir][1] = v2.y;
+                                } else {
+                                    acc[ic][ir][0] = (c <= N && r < N) ? A[(size_t)c * ld + r] : 0.0;
+                                    acc[ic][ir][1] = 0.0;
+                                }
                             }
+                    };
+                    __syncthreads();                                 // previous Us consumers done (and Ls visible)
+                    for (int t = tid; t < LUB_TC * LUB_NB; t += nthr) {
+                        const int c = t / LUB_NB, k = t - c * LUB_NB;
+                        Us[c * LUB_SU + k] = (k < nb && c0 + c <= N) ? -A[(size_t)(c0 + c) * ld + k0 + k] : 0.0;
+                    }
+                    __syncthreads();
+                    for (int st = warp; st < SUBR * SUBC; st += nw) {
+                        const int sc = st / SUBR, sr = st - sc * SUBR;
+                        const int cb = c0 + sc * 32, rb = r0 + sr * 32;
+                        if (cb > N || rb >= N) continue;
+                        load_c(st);
+                        const double* us = Us + (sc * 32 + fr) * LUB_SU + fk;
+                        const double* ls = Ls + fk * LUB_SL + sr * 32 + fr;
+                        const int nbk = (nb + 3) & ~3;               // (rows k >= nb of the slices are zero)
+    #pragma unroll 2
+                        for (int kk = 0; kk < nbk; kk += 4) {
+                            double af[4], bf[4];
+    #pragma unroll
+                            for (int ic = 0; ic < 4; ++ic) af[ic] = us[(8 * ic) * LUB_SU + kk];
+    #pragma unroll
+                            for (int ir = 0; ir < 4; ++ir) bf[ir] = ls[kk * LUB_SL + 8 * ir];
+    #pragma unroll
+                            for (int ic = 0; ic < 4; ++ic)
+    #pragma unroll
+                                for (int ir = 0; ir < 4; ++ir)
+                                    dmma884(acc[ic][ir][0], acc[ic][ir][1], af[ic], bf[ir]);
                         }
+    #pragma unroll
+                        for (int ic = 0; ic < 4; ++ic)
+    #pragma unroll
+                            for (int ir = 0; ir < 4; ++ir) {
+                                const int c = cb + 8 * ic + fr, r = rb + 8 * ir + 2 * fk;
+                                if (c <= N && r + 1 < N) {
+                                    *reinterpret_cast<double2*>(A + (size_t)c * ld + r) =
+                                        make_double2(acc[ic][ir][0], acc[ic][ir][1]);
+                                } else if (c <= N && r < N) {
+                                    A[(size_t)c * ld + r] = acc[ic][ir][0];
+                                }
+                            }
+                    }
                 }
+                __syncthreads();                                     // before Ls is overwritten
             }
-            __syncthreads();                                     // before Ls is overwritten
         }
         k0 = cr;
     }
