@@ -21,9 +21,15 @@
 //      Why tensor cores here: a register-tiled FMA update needs 8 shared-memory operand loads
 //      per 16 FMAs (4 x 4 tile), the DMMA path 8 fragment loads per 16 x 256 MACs, and the
 //      DMMA pipe has twice the FMA pipe's FP64 rate on this part.
+//      Large instance (BIG, matrix streamed from HBM): while the panels have more rows than
+//      the CTA has threads they are taken in PAIRS - panel 1 is applied to panel 2's columns
+//      only; after panel 2 is factored its interchanges are also applied to panel 1's L21, panel
+//      1 is applied to panel 2's 32 pivot rows, and the rest of the trailing matrix takes both
+//      panels in ONE rank-64 pass (lub_update_big) - and the U slice of the next column tile
+//      is copied asynchronously (LDGSTS) while the current tile is multiplied.
 //   4. blocked back substitution (32 x 32 diagonal blocks solved by one warp).
 // L is not kept (the right-hand side is carried as column N), so columns left of the panel
-// are never touched again.  Returns 0 or k+1 for a zero / non-finite pivot at step k, like
+// (pair) are never touched again.  Returns 0 or k+1 for a zero / non-finite pivot at step k, like
 // lu_solve_smem.
 #pragma once
 #include <cuda_runtime.h>
