@@ -126,7 +126,7 @@ def run_other_configs(torch, dist, BatchSolver, scenarios, local, rank, world):
         info = sol.struct_info()
         torch.cuda.synchronize()
         t_setup = time.perf_counter() - t0
-        P, Q, I_N = scenarios.make_batch(net, B, SPREAD, seed0=rank * B, exact_prefix=8)
+        P, Q, I_N = scenarios.make_batch(net, B, SPREAD, seed0=rank * B)
         dP, dQ, dI = sol.prepare(P, Q, I_N)
         r = sol.solve(dP, dQ, dI)                                   # warm-up
         if world > 1:
@@ -340,7 +340,7 @@ def run_ours(a):
     net = load_net()
     sol = BatchSolver(net, local)
     B = a.batch
-    P, Q, I_N = scenarios.make_batch(net, B, SPREAD, seed0=rank * B, exact_prefix=256)
+    P, Q, I_N = scenarios.make_batch(net, B, SPREAD, seed0=rank * B)
     hP = torch.as_tensor(P).pin_memory(); hQ = torch.as_tensor(Q).pin_memory()
     hI = torch.as_tensor(I_N).pin_memory()
     dP, dQ, dI = sol.prepare(hP, hQ, hI)

@@ -1,0 +1,355 @@
+// Harmonic Newton-Raphson (HG:511-560, structured step - see hpf_structured.cuh), the kernel the
+// BASELINE 4-bus shapes run on: ONE WARP PER HARMONIC, lane = scenario.
+//
+// harm_tile_kernel spreads the stacked rows of a scenario over 7 warps, so every operand of
+// every complex MAC is a shared-memory load (ncu, round 1: shared-memory wavefronts 62 % of
+// peak, FP64 pipe 32 %, 16 warps per SM).  Here thread (lane, h) OWNS the n phasors of harmonic
+// h of its scenario:
+//   * state V_m, V_a [n] and the phasors V [n] live in REGISTERS for the whole Newton loop;
+//   * Y(h), Y_N, G and the reduced fundamental operator are kernel parameters
+//     (__grid_constant__, constant bank): the harmonic index is made warp-uniform with a
+//     warp reduction (CREDUX writes a uniform register), so every constant is a
+//     `c[0x0][UR + imm]` operand of the DFMA itself - no load instruction, no shared memory;
+//   * the rows (Y_h V_h)_i of a harmonic need nothing but the thread's own registers; the only
+//     exchange between the warps of a tile is the Norton contraction (HG:313-323), which reads
+//     the nonlinear buses' phasors of all harmonics (q H complex per scenario, shared memory),
+//     V_F + u_F of the linear buses (m complex) and the mismatch norm (one shared atomic max
+//     on the sign-cleared bit patterns per thread).
+// The fundamental warp (h = 0) also owns the power rows (HG:372-380) and the border system for
+// the polar unknowns x_F of the linear buses.  That system is assembled in its reduced complex
+// form: with u_b = u0_k - sum_j G[k][j] u_j for the fundamental nonlinear buses,
+//     dS_i = u_i conj(I_i) + V_i conj(sum_{j<m} Yeff_ij u_j) + V_i conj(sum_k Y_{i,m+k} u0_k),
+//     Yeff_ij = Y1_ij - sum_k Y1_{i,m+k} G[k][j]        (constant, computed once per network),
+// so that with t_ij = V_i conj(Yeff_ij V_j) and s_i = V_i conj(I_i)
+//     d/dtheta_j : j ([i=j] s_i - t_ij)        d/dV_m,j : ([i=j] s_i + t_ij) / V_m,j
+//     rhs_i = -(P_i + jQ_i) - V_i conj(sum_{j<m} Yeff_ij V_j - sum_k Y1_{i,m+k} w_N,k)
+// - the same Newton step dx = J^{-1} f as hpf_structured.cuh describes, a quarter of the
+// instructions of the entry-by-entry assembly (no per-entry polar conversion of u_b).
+//
+// One round = one Newton iteration of every lane:
+//   A  refilled lanes load their scenario; sin/cos of the thread's n angles; publish the
+//      nonlinear buses' phasors                                                    | barrier
+//   B  mismatch rows of harmonic h (HG:326-357) incl. the Norton contraction; warp 0: power
+//      rows + border system -> V_F + u_F; ||f||_inf by shared atomic max           | barrier
+//   C  decisions (every warp computes the same ones); finished lanes write their results;
+//      u_z = -V_z - G (V_F + u_F) - w_N, polar conversion, state update in registers;
+//      finished lanes are refilled from the global queue                           | barrier (only if a lane finished)
+// Lanes are refilled individually because iteration counts differ (8..40).
+#pragma once
+#include "hpf_structured.cuh"
+// (needs absmax_bits of hpf_lane.cuh: include after it)
+
+template <class D, bool COUPLED>
+struct HwConsts {
+    static constexpr int nZ = D::n * D::H - D::m;
+    double2 Y[D::H * D::n * D::n];                               // Y(h) [H][n][n]
+    double2 YNk[COUPLED ? D::q * D::H * D::H : D::q * D::H];     // Y_N per nonlinear bus [q][H][H] / [q][H]
+    double2 G[nZ * D::m];                                        // G = A_ZZ^-1 A_ZF  [nZ][m]
+    double2 Yeff[D::m * D::m];                                   // reduced fundamental operator (rows 0..m-1)
+};
+
+template <class D>
+__host__ __device__ constexpr size_t harm_hw_smem_bytes() {
+    // sVnl [q][H][32] c128 | sW [nZ][32] c128 | sTot [m][32] c128 | sP, sQ [m][32] | red [2][32] | sbase
+    return ((size_t)(2 * D::q * D::H + 2 * (D::n * D::H - D::m) + 2 * D::m + 2 * D::m + 2) * 32) * sizeof(double) + 64;
+}
+
+// Gaussian elimination with partial pivoting on a register-resident augmented system (every index
+// is a compile-time constant after unrolling: the pivot row is bubbled up with selects).
+template <int NX>
+__device__ __forceinline__ int gauss_regs(double (&A)[NX][NX + 1], double (&x)[NX]) {
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < NX; ++k) {
+#pragma unroll
+        for (int i = k + 1; i < NX; ++i) {
+            const bool sw = fabs(A[i][k]) > fabs(A[k][k]);
+#pragma unroll
+            for (int cc = k; cc <= NX; ++cc) {
+                const double t0 = A[k][cc], t1 = A[i][cc];
+                A[k][cc] = sw ? t1 : t0;
+                A[i][cc] = sw ? t0 : t1;
+            }
+        }
+        const double pv = fabs(A[k][k]);
+        if (!(pv > 0.0) || !(pv < CUDART_INF)) bad = 1;
+        const double r = 1.0 / A[k][k];
+#pragma unroll
+        for (int i = k + 1; i < NX; ++i) {
+            const double l = A[i][k] * r;
+#pragma unroll
+            for (int cc = k + 1; cc <= NX; ++cc) A[i][cc] -= l * A[k][cc];
+        }
+        A[k][k] = r;                                         // keep the reciprocal for the back substitution
+    }
+#pragma unroll
+    for (int k = NX - 1; k >= 0; --k) {
+        double sv = A[k][NX];
+#pragma unroll
+        for (int cc = k + 1; cc < NX; ++cc) sv -= A[k][cc] * x[cc];
+        x[k] = sv * A[k][k];
+    }
+    return bad;
+}
+
+__device__ __forceinline__ void hw_cp_async16(void* sdst, const void* gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gsrc) : "memory");
+}
+
+template <class D, bool COUPLED, int MINB>
+__global__ void __launch_bounds__(D::H * 32, MINB)
+harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArgs a) {
+    constexpr int n = D::n, m = D::m, c = D::c, H = D::H, q = D::q, nH = n * H, nZ = nH - m;
+    constexpr int nth = m - 1, nv = m - c, nx = nth + nv;
+    constexpr int T = 32;
+    extern __shared__ __align__(16) double smem[];
+    double2* sVnl = reinterpret_cast<double2*>(smem);             // [q][H][T] phasors of the nonlinear buses
+    double2* sW = sVnl + q * H * T;                               // [nZ][T]   w_N (row z = s - m)
+    double2* sTot = sW + nZ * T;                                  // [m][T]    V_F + u_F
+    double* sP = reinterpret_cast<double*>(sTot + m * T);         // [m][T]
+    double* sQ = sP + m * T;                                      // [m][T]
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(sQ + m * T);   // [2][T] ||f||_inf bit patterns
+    int* sbase = reinterpret_cast<int*>(red + 2 * T);
+
+    const int lane = threadIdx.x & 31;
+    // warp-uniform harmonic index in a UNIFORM register: constants become c[0x0][UR + imm] operands
+    const int h = __reduce_min_sync(0xffffffffu, threadIdx.x >> 5);
+    const size_t B = (size_t)a.B;
+    const unsigned lt = (1u << lane) - 1u;
+
+    if (threadIdx.x == 0) sbase[0] = atomicAdd(a.work_counter, T);
+    if (threadIdx.x < 2 * T) red[threadIdx.x] = 0ull;
+    __syncthreads();
+    int sc = sbase[0] + lane;
+    if ((size_t)sc >= B) sc = -1;
+    bool isnew = true;
+    int itc = 0, stat = 0, cur = 0;
+    double Vm[n], Va[n];
+    double2 V[n], IN[q], inj[q];
+#pragma unroll
+    for (int k = 0; k < q; ++k) inj[k] = make_double2(0.0, 0.0);
+
+    for (;;) {
+        // ================= A: refill, phasors =================
+        if (isnew) {
+            itc = 0;
+            if (h == 0) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    Vm[i] = (sc >= 0) ? __ldcs(a.V_m + (size_t)i * B + sc) : 1.0;
+                    Va[i] = (sc >= 0) ? __ldcs(a.V_a + (size_t)i * B + sc) : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < m; ++i) {
+                    sP[i * T + lane] = (sc >= 0) ? __ldcs(a.P + (size_t)i * B + sc) : 0.0;
+                    sQ[i * T + lane] = (sc >= 0) ? __ldcs(a.Q + (size_t)i * B + sc) : 0.0;
+                }
+                stat = (sc >= 0) ? a.status[sc] : 0;
+            } else {
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    Vm[i] = (sc >= 0) ? 0.1 : 1.0;                  // flat start of the harmonics (HG:183)
+                    Va[i] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < q; ++k)
+                IN[k] = (sc >= 0) ? __ldcs(a.I_N + (size_t)(k * H + h) * B + sc) : make_double2(0.0, 0.0);
+            // w_N rows of this thread: thread-private columns of sW, fetched asynchronously (consumed in
+            // phase C, warp 0's z < q rows in phase B)
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const int z = h * n + i - m;
+                if (z >= 0) {
+                    if (sc >= 0) hw_cp_async16(&sW[z * T + lane], a.wN + (size_t)z * B + sc);
+                    else sW[z * T + lane] = make_double2(0.0, 0.0);
+                }
+            }
+        }
+        cp_async_commit();
+        {
+            double sn_[n], cs_[n];
+            sincos_group<n>(Va, sn_, cs_);
+#pragma unroll
+            for (int i = 0; i < n; ++i) V[i] = make_double2(Vm[i] * cs_[i], Vm[i] * sn_[i]);   // V = V_m e^{j theta} (HG:403)
+        }
+        if (COUPLED) {
+#pragma unroll
+            for (int k = 0; k < q; ++k) sVnl[(k * H + h) * T + lane] = V[m + k];
+        }
+        __syncthreads();
+        // ================= B: mismatch rows (HG:360-388); border system =================
+        long long mxb = 0;
+        auto yrow = [&](const int i) {
+            double2 f = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < n; ++j) f = cfma(f, C.Y[(h * n + i) * n + j], V[j]);
+            return f;
+        };
+        // nonlinear bus k: (Y_h V_h)_i + I_N - sum_p Y_N[h][p] V_p,i   (HG:313-323,335-354)
+        auto nlrow = [&](const int k, double2 f) {
+            double2 acc;
+            if (COUPLED) {
+                acc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int p = 0; p < H; ++p) acc = cfma(acc, C.YNk[(k * H + h) * H + p], sVnl[(k * H + p) * T + lane]);
+            } else {
+                acc = cmul(C.YNk[k * H + h], V[m + k]);
+            }
+            inj[k] = make_double2(IN[k].x - acc.x, IN[k].y - acc.y);
+            f = cadd(f, inj[k]);
+            absmax_bits(mxb, f.x);
+            absmax_bits(mxb, f.y);
+        };
+        double xF[nx > 0 ? nx : 1];
+        if (h != 0) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const double2 f = yrow(i);
+                if (i >= m) {
+                    nlrow(i - m, f);
+                } else {
+                    absmax_bits(mxb, f.x);
+                    absmax_bits(mxb, f.y);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < q; ++k) nlrow(k, yrow(m + k));
+            cp_async_wait<0>();                                  // w_N rows z < q of a refilled lane
+            double M[nx > 0 ? nx : 1][nx + 1];
+#pragma unroll
+            for (int r = 0; r < nx; ++r)
+#pragma unroll
+                for (int cc = 0; cc <= nx; ++cc) M[r][cc] = 0.0;
+            double rvm[m];
+#pragma unroll
+            for (int j = c; j < m; ++j) rvm[j] = 1.0 / Vm[j];
+#pragma unroll
+            for (int i = 1; i < m; ++i) {
+                const double2 I1 = yrow(i);
+                const double2 s_i = cmul(V[i], cconj(I1));                   // V_i conj(I_i)
+                const double pl = sP[i * T + lane], ql = sQ[i * T + lane];
+                const double2 fs = make_double2(pl + s_i.x, ql + s_i.y);    // power mismatch (HG:372-380)
+                absmax_bits(mxb, fs.x);
+                if (i >= c) absmax_bits(mxb, fs.y);
+                const int rp = i - 1, rq = nth + (i - c);
+                double2 ri = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int j = 0; j < m; ++j) {
+                    const double2 pv = cmul(C.Yeff[i * m + j], V[j]);
+                    ri = cadd(ri, pv);
+                    if (j >= 1) {
+                        const double2 t = cmul(V[i], cconj(pv));             // t_ij = V_i conj(Yeff_ij V_j)
+                        const double2 d = (i == j) ? csub(s_i, t) : cneg(t);
+                        M[rp][j - 1] = -d.y;                                 // j ([i=j] s_i - t_ij)
+                        if (i >= c) M[rq][j - 1] = d.x;
+                        if (j >= c) {
+                            const double2 e = (i == j) ? cadd(s_i, t) : t;
+                            M[rp][nth + j - c] = e.x * rvm[j];
+                            if (i >= c) M[rq][nth + j - c] = e.y * rvm[j];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < q; ++k) {
+                    const double2 w = sW[k * T + lane];
+                    ri = cfma(ri, cneg(C.Y[i * n + m + k]), w);
+                }
+                const double2 vr = cmul(V[i], cconj(ri));
+                M[rp][nx] = -pl - vr.x;
+                if (i >= c) M[rq][nx] = -ql - vr.y;
+            }
+            int badp = 0;
+            if constexpr (nx > 0) badp = gauss_regs<nx>(M, xF);
+            if (badp) stat |= 0x200;
+            sTot[lane] = V[0];
+#pragma unroll
+            for (int i = 1; i < m; ++i) {
+                const double dth = xF[i - 1];
+                const double dvm = (i >= c) ? xF[nth + i - c] : 0.0;
+                const double ex = (i >= c) ? V[i].x * rvm[i] : 0.0, ey = (i >= c) ? V[i].y * rvm[i] : 0.0;
+                // V_i + u_F,i,  u_F = (j V_i) dtheta + E_i dV_m
+                sTot[i * T + lane] = make_double2(V[i].x - V[i].y * dth + ex * dvm, V[i].y + V[i].x * dth + ey * dvm);
+            }
+        }
+        atomicMax(&red[cur * T + lane], (unsigned long long)mxb);
+        __syncthreads();
+        // ================= C: decisions, finished lanes, update, refill =================
+        const double err = __longlong_as_double((long long)red[cur * T + lane]);
+        const bool active = sc >= 0;
+        const bool cont = active && (err > a.thresh_h) && (itc < a.max_h);
+        const bool done = active && !cont;
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;          // same lanes in every warp: uniform over the CTA
+        const unsigned donemask = __ballot_sync(0xffffffffu, done);
+        if (h == 0) {
+            red[(cur ^ 1) * T + lane] = 0ull;                         // next round's accumulator
+            if (a.hist_h && active) a.hist_h[(size_t)itc * B + sc] = err;
+        }
+        if (done) {
+            // post-processing (HG:547-549) + write-out of the thread's n rows
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                double vm = Vm[i], va = Va[i];
+                if (!(a.flags & HPF_SOLVE_RAW)) {
+                    if (vm < 0.0) va += CUDART_PI;
+                    va = mod_twopi(va);
+                    if (vm < 0.0) vm = -vm;
+                }
+                a.V_m[(size_t)(h * n + i) * B + sc] = vm;
+                a.V_a[(size_t)(h * n + i) * B + sc] = va;
+            }
+            if (a.I_inj) {
+#pragma unroll
+                for (int k = 0; k < q; ++k) a.I_inj[(size_t)(k * H + h) * B + sc] = inj[k];
+            }
+            if (h == 0) {
+                int st = stat & 0xff;
+                if ((stat & 0x200) && st == HPF_ST_CONVERGED) st = HPF_ST_SINGULAR;
+                if (itc >= a.max_h && st == HPF_ST_CONVERGED) st = HPF_ST_MAXITER;
+                if (!(err < CUDART_INF)) st = HPF_ST_NONFINITE;           // NaN or Inf mismatch
+                a.n_iter_h[sc] = itc;
+                a.err_h[sc] = err;
+                a.status[sc] = st;
+            }
+        }
+        if (h != 0) cp_async_wait<0>();                                // w_N rows of a refilled lane
+        if (cont) {
+            double2 tot[m];
+#pragma unroll
+            for (int i = 0; i < m; ++i) tot[i] = sTot[i * T + lane];
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const int z = h * n + i - m;                               // warp-uniform
+                if (z >= 0) {
+                    // u_z = -V_z - sum_i G[z][i] (V_i + u_F,i) - w_N,z ; polar conversion; update
+                    const double2 w = sW[z * T + lane];
+                    double2 acc = make_double2(V[i].x + w.x, V[i].y + w.y);
+#pragma unroll
+                    for (int j = 0; j < m; ++j) acc = cfma(acc, C.G[z * m + j], tot[j]);
+                    // conj(E) u with E = V / V_m:  dV_m = Re(conj(V) u) / V_m,  dtheta = Im(conj(V) u) / V_m^2
+                    const double2 cv = cmul(make_double2(V[i].x, -V[i].y), cneg(acc));
+                    const double rv = 1.0 / Vm[i];
+                    Va[i] += (cv.y * rv) * rv;
+                    Vm[i] += cv.x * rv;
+                } else if (i >= 1) {                                       // linear bus at the fundamental (h == 0)
+                    Va[i] += xF[i - 1];
+                    if (i >= c) Vm[i] += xF[nth + i - c];
+                }
+            }
+            ++itc;
+        }
+        isnew = false;
+        if (donemask) {
+            if (threadIdx.x == 0) sbase[0] = atomicAdd(a.work_counter, __popc(donemask));
+            __syncthreads();
+            if (done) {
+                const int idx = sbase[0] + __popc(donemask & lt);
+                sc = ((size_t)idx < B) ? idx : -1;
+                isnew = true;
+            }
+        }
+        cur ^= 1;
+    }
+}

@@ -585,6 +585,7 @@ mismatch_tile_kernel(const DevNet net, const MismatchArgs a, const int yn_elems)
 }
 
 #include "hpf_lane.cuh"
+#include "hpf_harmonic_warp.cuh"
 
 // Fallback for networks whose 32-scenario tile does not fit in shared memory (e.g. net1 with
 // 26 harmonics): one scenario per CTA, same arithmetic (VS = 1), strided HBM access.
@@ -826,6 +827,7 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
         double err;
         for (;;) {
             err = cta_harmonic_mismatch(net, s, rhs);          // phasors, I1, Iinj, f
+            if (a.hist_h && !a.step_only && tid == 0) a.hist_h[(size_t)it * B + b] = err;
             if (!a.step_only && !((err > a.thresh_h) && (it < a.max_h))) break;
             // u0 of the fundamental nonlinear rows (closed form)
             for (int k = tid; k < q; k += blockDim.x) {
@@ -1059,7 +1061,12 @@ struct hpf_handle {
     int force_variant = 0;        // $HPF_STRUCT_VARIANT=2|3: force a per-CTA variant of the harmonic stage
     // host mirror of the network constants for kernels that take them as parameters
     // (constant bank): fetched lazily from the device tables, see host_consts()
-    std::vector<double2> hY, hYN, hWNL;
+    std::vector<double2> hY, hYN, hWNL, hG;
+    std::vector<char> hw_consts;  // HwConsts<D, coupled> of the one-warp-per-harmonic kernel (hw_shape != 0)
+    int hw_shape = 0;             // 0 none, 1 = Dims<4,3,2,13,1>, 2 = Dims<4,2,1,10,2>
+    int harm_tile_only = 0;       // $HPF_HARM_KERNEL=tile: 32-scenario tile kernel instead (A/B measurements)
+    int hw_minb = 2;              // $HPF_HW_MINB: register budget of the one-warp-per-harmonic kernel (CTAs per SM)
+    int max_ctas = 0;             // $HPF_MAX_CTAS: cap on the grid of the persistent kernels (tests: forces queue refills on small batches)
     std::vector<int> hdev;
     bool host_consts_valid = false;
     double pivot_min = 0.0, pivot_max = 0.0;
@@ -1205,6 +1212,7 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     CK(cudaMemsetAsync(h->d_counter + h->cur_slot, 0, sizeof(int), st));
     long long grid = (long long)occ * h->sm_count;
     if (grid > B) grid = B;
+    if (h->max_ctas && grid > h->max_ctas) grid = h->max_ctas;
     a.workspace = nullptr;
     if (gm && !ws_smem) {
         rc = ensure_workspace(h, (size_t)grid * lub_ld(net.N) * (net.N + 1));
@@ -1243,6 +1251,41 @@ static StructNet structnet(const hpf_t* h) {
 }
 
 static int host_consts(hpf_t* h);
+
+// Constants of the one-warp-per-harmonic kernel (hpf_harmonic_warp.cuh) for a shape-specialised
+// network, from the host mirrors of Y(h), Y_N and G: kept in the handle, passed BY VALUE at launch.
+template <class D>
+static bool build_hw_consts(hpf_t* h, int shape_id) {
+    if (!(h->n == D::n && h->m == D::m && h->c == D::c && h->H == D::H && h->q == D::q)) return false;
+    constexpr int n = D::n, m = D::m, H = D::H, q = D::q;
+    auto fill = [&](auto* C) {
+        for (int t = 0; t < H * n * n; ++t) C->Y[t] = h->hY[(size_t)t];
+        const int per = h->coupled ? H * H : H;
+        for (int k = 0; k < q; ++k)
+            for (int t = 0; t < per; ++t) C->YNk[k * per + t] = h->hYN[(size_t)h->hdev[(size_t)k] * per + t];
+        for (size_t t = 0; t < h->hG.size(); ++t) C->G[t] = h->hG[t];
+        // Yeff_ij = Y1_ij - sum_k Y1_{i,m+k} G[k][j]   (row z = k of G: fundamental, nonlinear bus k)
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) {
+                double2 v = h->hY[(size_t)i * n + j];
+                for (int k = 0; k < q; ++k) {
+                    const double2 y = h->hY[(size_t)i * n + m + k], g = h->hG[(size_t)k * m + j];
+                    v.x -= y.x * g.x - y.y * g.y;
+                    v.y -= y.x * g.y + y.y * g.x;
+                }
+                C->Yeff[i * m + j] = v;
+            }
+    };
+    if (h->coupled) {
+        h->hw_consts.assign(sizeof(HwConsts<D, true>), 0);
+        fill(reinterpret_cast<HwConsts<D, true>*>(h->hw_consts.data()));
+    } else {
+        h->hw_consts.assign(sizeof(HwConsts<D, false>), 0);
+        fill(reinterpret_cast<HwConsts<D, false>*>(h->hw_consts.data()));
+    }
+    h->hw_shape = shape_id;
+    return true;
+}
 
 // Structured set-up, once per network.  Variants of the harmonic stage:
 //   1  32-scenario tile kernels (state of 32 scenarios in shared memory: the 4-bus networks)
@@ -1368,15 +1411,23 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(AZF); cudaFree(ipiv); cudaFree(pr); cudaFree(tmp);
     h->hWNL.clear();
+    h->hG.clear();
+    h->hw_shape = 0;
     if (variant == 1 && e == cudaSuccess && qH > 0 && (size_t)nZ * qH <= 1024) {   // small operators: host mirror
         h->hWNL.resize((size_t)nZ * qH);
         e = cudaMemcpy(h->hWNL.data(), h->d_WNL, h->hWNL.size() * sizeof(double2), cudaMemcpyDeviceToHost);
+        h->hG.resize((size_t)nZ * net.m);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(h->hG.data(), h->d_Gz, h->hG.size() * sizeof(double2), cudaMemcpyDeviceToHost);
     }
     if (variant == 3) { cudaFree(h->d_Ainv); h->d_Ainv = nullptr; }    // (GBs for the 1000-bus network)
     if (e != cudaSuccess) return fail(h, HPF_E_CUDA, std::string("structured setup: ") + cudaGetErrorString(e));
     h->pivot_min = prh[0]; h->pivot_max = prh[1];
     // usable when the inversion met no zero pivot and the pivots span < 1e12 (well conditioned)
     if (info == 0 && prh[0] > 0.0 && prh[1] / prh[0] < 1e12) h->struct_state = variant;
+    if (h->struct_state == 1 && !h->hG.empty() && !h->no_specialise) {
+        if (!build_hw_consts<Dims<4, 3, 2, 13, 1>>(h, 1)) build_hw_consts<Dims<4, 2, 1, 10, 2>>(h, 2);
+    }
     return HPF_OK;
 }
 
@@ -1437,10 +1488,38 @@ static int launch_harm_t(hpf_t* h, const DevNet& net, const StructNet& sn, const
     const long long tiles = ((long long)ha.B + HPF_T - 1) / HPF_T;
     long long grid = tiles;
     if (persistent && grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
+    if (persistent && h->max_ctas && grid > h->max_ctas) grid = h->max_ctas;
     harm_tile_kernel<NW, MINB, D><<<(unsigned)grid, NW * 32, smem, st>>>(net, sn, ha);
     h->launches++;
     CK(cudaGetLastError());
     return HPF_OK;
+}
+
+template <class D>
+static int launch_harm_hw(hpf_t* h, const HarmTileArgs& ha, cudaStream_t st) {
+    constexpr size_t smem = harm_hw_smem_bytes<D>();
+    constexpr int threads = D::H * 32;
+    auto go = [&](auto kernel, const auto* C) -> int {
+        static_assert(sizeof(*C) + sizeof(HarmTileArgs) <= 32000, "kernel parameter space");
+        int occ = 0;
+        int rc = prep_kernel(h, kernel, smem, "hpf_solve", &occ, threads);
+        if (rc) return rc;
+        const long long tiles = ((long long)ha.B + HPF_T - 1) / HPF_T;
+        long long grid = (long long)occ * h->sm_count;
+        if (grid > tiles) grid = tiles;
+        if (h->max_ctas && grid > h->max_ctas) grid = h->max_ctas;
+        kernel<<<(unsigned)grid, threads, smem, st>>>(*C, ha);
+        h->launches++;
+        CK(cudaGetLastError());
+        return HPF_OK;
+    };
+    // two register budgets are compiled: 2 CTAs per SM (default) and 1 CTA per SM ($HPF_HW_MINB=1)
+    if (h->coupled) {
+        const auto* C = reinterpret_cast<const HwConsts<D, true>*>(h->hw_consts.data());
+        return h->hw_minb == 1 ? go(harm_hw_kernel<D, true, 1>, C) : go(harm_hw_kernel<D, true, 2>, C);
+    }
+    const auto* C = reinterpret_cast<const HwConsts<D, false>*>(h->hw_consts.data());
+    return h->hw_minb == 1 ? go(harm_hw_kernel<D, false, 1>, C) : go(harm_hw_kernel<D, false, 2>, C);
 }
 
 // Shape-specialised instances exist for the BASELINE configurations' 4-bus networks
@@ -1462,6 +1541,7 @@ static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const H
         if (rc) return rc;
         long long grid = ha.B;
         if ((persistent || gst) && grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
+        if (persistent && h->max_ctas && grid > h->max_ctas) grid = h->max_ctas;
         HarmTileArgs ha2 = ha;
         ha2.gstate = nullptr; ha2.gstate_stride = 0; ha2.lub_doubles = (int)lubd;
         if (gst) {
@@ -1481,6 +1561,10 @@ static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const H
         CK(cudaGetLastError());
         return HPF_OK;
     }
+    if (h->hw_shape && !h->harm_tile_only && !ha.step_only && persistent) {
+        if (h->hw_shape == 1) return launch_harm_hw<Dims<4, 3, 2, 13, 1>>(h, ha, st);
+        return launch_harm_hw<Dims<4, 2, 1, 10, 2>>(h, ha, st);
+    }
     const bool two = 2 * harm_tile_smem_bytes(net.n, net.H, net.m, net.c, net.q, 8, sn.yn_elems) + 2048 <=
                      (size_t)h->smem_optin + 1024;
     if (!h->no_specialise) {
@@ -1496,15 +1580,18 @@ static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const H
 static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, const double* I_N,
                             double thresh_f, int max_f, double thresh_h, int max_h, int flags,
                             double* V_m, double* V_a, double* I_inj, int* n_iter_f, int* n_iter_h,
-                            double* err_h, int* status, cudaStream_t st) {
+                            double* err_h, int* status, double* hist_f, double* hist_h, cudaStream_t st) {
     const DevNet net = devnet(h);
     const StructNet sn = structnet(h);
+    // error histories: the unused tail is NaN (all-ones bytes are a quiet NaN)
+    if (hist_f) CK(cudaMemsetAsync(hist_f, 0xff, (size_t)(max_f + 1) * B * sizeof(double), st));
+    if (hist_h) CK(cudaMemsetAsync(hist_h, 0xff, (size_t)(max_h + 1) * B * sizeof(double), st));
     CK(cudaMemsetAsync(h->d_counter + h->cur_slot, 0, sizeof(int), st));
     if (h->profiling) { CK(cudaEventRecord(h->ev[0], st)); }
     // fundamental stage: one lane per scenario (variant 1) or the per-CTA kernel (variant 2)
     if (h->struct_state >= 2) {
         int rc = solve_common(h, 1, B, P, Q, nullptr, thresh_f, max_f, 0.0, 0, 0, V_m, V_a, nullptr, n_iter_f,
-                              nullptr, nullptr, nullptr, status, nullptr, nullptr, st);
+                              nullptr, nullptr, nullptr, status, hist_f, nullptr, st);
         if (rc) return rc;
         CK(cudaMemsetAsync(h->d_counter + h->cur_slot, 0, sizeof(int), st));     // solve_common used the counter
     } else {
@@ -1514,7 +1601,7 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
         const size_t smem = per_warp * warps;
         FundTileArgs fa;
         fa.B = B; fa.P = P; fa.Q = Q; fa.thresh_f = thresh_f; fa.max_f = max_f;
-        fa.V_m = V_m; fa.V_a = V_a; fa.n_iter_f = n_iter_f; fa.status = status;
+        fa.V_m = V_m; fa.V_a = V_a; fa.n_iter_f = n_iter_f; fa.status = status; fa.hist_f = hist_f;
         const long long tiles = ((long long)B + HPF_T - 1) / HPF_T;
         auto launch = [&](auto kernel) -> int {
             CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1544,7 +1631,7 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
         ha.wN = h->d_wN + (size_t)h->cur_slot * h->wN_slot_stride;
         ha.thresh_h = thresh_h; ha.max_h = max_h; ha.V_m = V_m; ha.V_a = V_a; ha.I_inj = (double2*)I_inj;
         ha.n_iter_h = n_iter_h; ha.status = status; ha.err_h = err_h; ha.work_counter = h->d_counter + h->cur_slot;
-        ha.dx_out = nullptr; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0;
+        ha.dx_out = nullptr; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0; ha.hist_h = hist_h;
         rc = launch_harm(h, net, sn, ha, true, st);
         if (rc) return rc;
     }
@@ -1622,6 +1709,9 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_MISMATCH_TILE")) h->mismatch_tile = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_STRUCT_VARIANT")) h->force_variant = atoi(ev);
     if (const char* ev = getenv("HPF_DENSE_BLOCKED")) h->dense_blocked = atoi(ev) ? 1 : 0;
+    if (const char* ev = getenv("HPF_HARM_KERNEL")) h->harm_tile_only = (strcmp(ev, "tile") == 0) ? 1 : 0;
+    if (const char* ev = getenv("HPF_HW_MINB")) h->hw_minb = (atoi(ev) == 1) ? 1 : 2;
+    if (const char* ev = getenv("HPF_MAX_CTAS")) h->max_ctas = atoi(ev) > 0 ? atoi(ev) : 0;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     e = cudaMalloc((void**)&h->d_counter, 8 * sizeof(int));
@@ -1833,9 +1923,9 @@ static int solve_dispatch(hpf_t* h, int B, const double* P, const double* Q, con
                           int max_iter_f, double thresh_h, int max_iter_h, int flags, double* V_m, double* V_a,
                           double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status,
                           double* err_hist_f, double* err_hist_h, void* stream) {
-    // default strategy: structured Newton step; dense LU when forced, when the per-iteration
-    // error history is wanted, or when the network does not admit the structured set-up
-    if (h && !(flags & HPF_SOLVE_DENSE) && !err_hist_f && !err_hist_h && B > 0) {
+    // default strategy: structured Newton step; dense LU when forced or when the network does
+    // not admit the structured set-up
+    if (h && !(flags & HPF_SOLVE_DENSE) && B > 0) {
         int rc = ready(h, "hpf_solve", true);
         if (rc) return rc;
         if (!P || !Q || !V_m || !V_a || !n_iter_f || !n_iter_h || !err_h || !status || (h->q > 0 && !I_N))
@@ -1845,7 +1935,8 @@ static int solve_dispatch(hpf_t* h, int B, const double* P, const double* Q, con
         if (rc) return rc;
         if (h->struct_state >= 1)
             return solve_structured(h, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags,
-                                    V_m, V_a, I_inj, n_iter_f, n_iter_h, err_h, status, (cudaStream_t)stream);
+                                    V_m, V_a, I_inj, n_iter_f, n_iter_h, err_h, status, err_hist_f, err_hist_h,
+                                    (cudaStream_t)stream);
     }
     return solve_common(h, 0, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a,
                         I_inj, n_iter_f, n_iter_h, err_h, nullptr, status, err_hist_f, err_hist_h, stream);
@@ -1896,7 +1987,7 @@ int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const
     ha.wN = h->d_wN;
     ha.thresh_h = 0.0; ha.max_h = 1; ha.V_m = const_cast<double*>(V_m); ha.V_a = const_cast<double*>(V_a);
     ha.I_inj = nullptr; ha.n_iter_h = nullptr; ha.status = nullptr; ha.err_h = nullptr;
-    ha.work_counter = nullptr; ha.dx_out = dx; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0;
+    ha.work_counter = nullptr; ha.dx_out = dx; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0; ha.hist_h = nullptr;
     return launch_harm(h, net, sn, ha, false, (cudaStream_t)stream);
 }
 

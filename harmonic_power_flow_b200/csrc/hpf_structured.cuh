@@ -381,6 +381,7 @@ struct FundTileArgs {
     int max_f;
     double *V_m, *V_a;
     int *n_iter_f, *status;
+    double* hist_f;          // [max_f + 1, B] mismatch norm before each step and after the last one, or NULL
 };
 
 __host__ __device__ inline size_t fund_tile_doubles_per_warp(int n, int Nf) {
@@ -443,6 +444,7 @@ fund_tile_kernel(const DevNet net, const FundTileArgs a) {
             }
             if (running) {
                 err = mx;
+                if (a.hist_f && ok) a.hist_f[(size_t)it * B + b] = err;
                 running = (err > a.thresh_f) && (it < a.max_f);
             }
             if (!__any_sync(0xffffffffu, running)) break;
@@ -630,6 +632,7 @@ struct HarmTileArgs {
     double* gstate;          // per-CTA kernel, large networks: scenario state in global memory
     size_t gstate_stride;    //   doubles per CTA (0: state in shared memory)
     int lub_doubles;         //   shared-memory work area of the blocked LU (doubles)
+    double* hist_h;          // [max_h + 1, B] mismatch norm before each step and after the last one, or NULL
 };
 
 
@@ -1076,6 +1079,7 @@ harm_tile_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
                     a.err_h[sc] = err;
                     a.status[sc] = st;
                 }
+                if (a.hist_h && active) a.hist_h[(size_t)itv * B + sc] = err;
                 if (step) itc[lane] = itv + 1;
                 fnew[lane] = 0;
                 pendF = step;

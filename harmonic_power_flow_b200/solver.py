@@ -240,7 +240,8 @@ class BatchSolver:
               out: BatchResult | None = None) -> BatchResult:
         """Fundamental + harmonic Newton-Raphson for the whole batch (hpf_solve).
         dense=True forces the dense-LU Newton step; the default picks the structured step when
-        the network admits it (``struct_info()``).  history=True implies the dense kernel."""
+        the network admits it (``struct_info()``).  history=True also returns the mismatch norm
+        before every step and after the last one (err_hist_f / err_hist_h, unused tail NaN)."""
         P, Q, I_N = self.prepare(P, Q, I_N)
         n = self.net
         B = P.shape[1]

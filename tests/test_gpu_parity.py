@@ -188,10 +188,16 @@ def test_lu_solve_random_batch_and_singular(solvers, case, B):
 
 
 # ---------------------------------------------------------------- fused solve
+@pytest.mark.parametrize("strategy", ["structured", "dense"])
 @pytest.mark.parametrize("case", SMALL_CASES)
-def test_fused_solve_nominal_cases(solvers, case):
+def test_fused_solve_nominal_cases(solvers, case, strategy):
+    """Every nominal fixture on BOTH Newton-step strategies - "structured" is the default kernel
+    the headline number runs on (harm_hw_kernel / harm_tile_kernel), with the per-iteration error
+    history: exact iteration counts, V within 1e-9, the reference's error path, THD."""
     sol, net, d = solvers(case)
-    r = sol.solve(net.P[:, None], net.Q[:, None], net.I_N[:, :, None], history=True)
+    if strategy == "structured":
+        assert sol.struct_info()["available"] == 1
+    r = sol.solve(net.P[:, None], net.Q[:, None], net.I_N[:, :, None], history=True, dense=(strategy == "dense"))
     assert int(r.n_iter_f.item()) == int(d["n_iter_f"])
     assert int(r.n_iter_h.item()) == int(d["n_iter_h"])           # identical iteration counts
     assert int(r.status.item()) == 0
@@ -203,6 +209,10 @@ def test_fused_solve_nominal_cases(solvers, case):
     assert (Va >= 0).all() and (Va <= 2 * np.pi).all() and (r.V_m.cpu().numpy() >= 0).all()
     hist = r.err_hist_h[:, 0].cpu().numpy()
     k = len(d["err_h_hist"])
+    assert np.isnan(hist[k:]).all() and np.isfinite(hist[:k]).all()
+    hf = r.err_hist_f[:, 0].cpu().numpy()
+    kf = len(d["err_f_hist"])
+    assert np.isnan(hf[kf:]).all() and np.allclose(hf[:kf], d["err_f_hist"], rtol=1e-6, atol=1e-15)
     # the error PATH, not only the end: tight at the start, then round-off is amplified by the
     # non-contractive early iterations (cond(J) up to 2e7)
     assert np.allclose(hist[:4], d["err_h_hist"][:4], rtol=1e-9)
@@ -293,7 +303,7 @@ def test_host_entry_point_keeps_device_copy(solvers):
     from harmonic_power_flow_b200 import scenarios
     sol, net, _ = solvers("net3_c_h25")
     B = 20000
-    P, Q, I_N = scenarios.make_batch(net, B, "tight", exact_prefix=16)
+    P, Q, I_N = scenarios.make_batch(net, B, "tight")
     r = sol.solve_host(P, Q, I_N, keep=True)
     dev = r["device"].to_host()
     for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status"):
@@ -307,7 +317,7 @@ def test_host_entry_point_chunked_pipeline(solvers, tmp_path):
     from harmonic_power_flow_b200 import scenarios
     sol, net, _ = solvers("net3_c_h25")
     B = 40001
-    P, Q, I_N = scenarios.make_batch(net, B, "tight", exact_prefix=16)
+    P, Q, I_N = scenarios.make_batch(net, B, "tight")
     a = sol.solve(P, Q, I_N).to_host()
     b = sol.solve_host(P, Q, I_N)
     for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status"):
@@ -408,6 +418,56 @@ def test_status_words_and_edge_batches(solvers, dense):
     assert (r["V_m"] == r["V_m"][:, :, :1]).all() and (r["V_a"] == r["V_a"][:, :, :1]).all()
 
 
+@pytest.mark.parametrize("kernel", ["warp", "tile", "dense"])
+@pytest.mark.parametrize("case", ["net3_c_h25", "net2ev_uc_h19"])
+def test_queue_refill_few_ctas_ragged_batch(solvers, case, kernel, tmp_path, monkeypatch):
+    """The persistent kernels pull scenarios from a global queue and refill lanes / CTAs as
+    scenarios finish.  With the grid capped at 2 CTAs ($HPF_MAX_CTAS) a ragged batch of 333
+    scenarios exercises every refill path; per-scenario arithmetic does not depend on the lane,
+    tile or CTA a scenario lands in, so the results must be BIT-identical to the uncapped run.
+    kernel: "warp" = one warp per harmonic (default for the BASELINE shapes), "tile" = 32-scenario
+    tile kernel ($HPF_HARM_KERNEL=tile), "dense" = fused dense-LU kernel."""
+    from harmonic_power_flow_b200 import BatchSolver, scenarios
+    sol, net, _ = solvers(case)
+    B = 333
+    P, Q, I_N = scenarios.make_batch(net, B, "wide")
+    if kernel == "tile":
+        monkeypatch.setenv("HPF_HARM_KERNEL", "tile")
+        sol = BatchSolver(net)
+    want = sol.solve(P, Q, I_N, dense=(kernel == "dense"), history=True).to_host()
+    monkeypatch.setenv("HPF_MAX_CTAS", "2")
+    capped = BatchSolver(net)
+    got = capped.solve(P, Q, I_N, dense=(kernel == "dense"), history=True).to_host()
+    capped.close()
+    if kernel == "tile":
+        sol.close()
+    assert (want["status"] == 0).all()
+    for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status", "err_hist_h", "err_hist_f"):
+        assert np.array_equal(got[k], want[k], equal_nan=True), k
+    assert len(np.unique(want["n_iter_h"])) > 3              # lanes really finish at different times
+
+
+def test_warp_kernel_agrees_with_tile_kernel(solvers, monkeypatch):
+    """The two structured kernels assemble the border system differently (reduced complex form vs
+    entry by entry) - same Newton step, different round-off: counts agree except for a few
+    round-off-decided scenarios, phasors agree to 1e-9 wherever the counts do."""
+    from harmonic_power_flow_b200 import BatchSolver, scenarios
+    sol, net, _ = solvers("net3_c_h25")
+    B = 4096
+    P, Q, I_N = scenarios.make_batch(net, B, "tight")
+    a = sol.solve(P, Q, I_N).to_host()
+    monkeypatch.setenv("HPF_HARM_KERNEL", "tile")
+    tile = BatchSolver(net)
+    b = tile.solve(P, Q, I_N).to_host()
+    tile.close()
+    same = a["n_iter_h"] == b["n_iter_h"]
+    Va, Vb = helpers.phasor(a["V_m"], a["V_a"]), helpers.phasor(b["V_m"], b["V_a"])
+    rel = (np.abs(Va - Vb) / np.abs(Vb)).reshape(-1, B).max(0)
+    print("\nwarp vs tile kernel: %d/%d iteration-count differences, median phasor diff %.2e" % (
+        (~same).sum(), B, np.median(rel)))
+    assert (~same).mean() < 0.03 and np.median(rel) < 1e-11
+
+
 @pytest.mark.parametrize("case", ["net1_c_h25", "net1_uc_h51", "net1_c_h51", "net2_c_h51", "net2_uc_h51"])
 def test_large_networks_structured_cta_path(solvers, case):
     """net1 (20 buses, N = 518 / 1038) and net2 with 26 harmonics through the structured step
@@ -419,12 +479,10 @@ def test_large_networks_structured_cta_path(solvers, case):
     print("\n%s: structured variant %d, n_iter_h GPU %d, reference %d" % (
         case, info["available"], int(r.n_iter_h.item()), int(d["n_iter_h"])))
     assert int(r.n_iter_f.item()) == int(d["n_iter_f"])
-    if case == "net1_c_h51":
-        # cond(J) reaches 4e9 and ||f|| wanders around 1e3 for ~20 steps: the count is decided by
-        # round-off (reference: 23 with its SuperLU step, 36 with a LAPACK step)
-        assert 15 <= int(r.n_iter_h.item()) < 50
-    else:
-        assert int(r.n_iter_h.item()) == int(d["n_iter_h"])
+    # (net1/H<=51: cond(J) reaches 4e9 and ||f|| wanders around 1e3 for ~20 steps - the reference
+    # itself needs 23 steps with its SuperLU step and 36 with a LAPACK step; the
+    # structured step reproduces the reference's 23)
+    assert int(r.n_iter_h.item()) == int(d["n_iter_h"])
     assert int(r.status.item()) == 0
     V = helpers.phasor(r.V_m[:, :, 0].cpu().numpy(), r.V_a[:, :, 0].cpu().numpy())
     Vg = helpers.phasor(d["V_m"], d["V_a"])
@@ -512,7 +570,7 @@ def test_full_size_batch_properties(solvers):
     from harmonic_power_flow_b200 import scenarios
     sol, net, _ = solvers("net3_c_h25")
     B = 65536
-    P, Q, I_N = scenarios.make_batch(net, B, "tight", exact_prefix=32)
+    P, Q, I_N = scenarios.make_batch(net, B, "tight")
     dP, dQ, dI = sol.prepare(P, Q, I_N)
     raw = sol.solve(dP, dQ, dI, raw=True)
     assert int((raw.status == 0).sum()) == B
@@ -540,6 +598,44 @@ def test_full_size_batch_properties(solvers):
     Vp = pp.V_m * torch.exp(1j * pp.V_a)
     assert float((Vr - Vp).abs().max()) < 1e-10          # torch.exp on un-reduced angles of tens of radians
     assert float(pp.V_m.min()) >= 0 and float(pp.V_a.min()) >= 0 and float(pp.V_a.max()) <= 2 * np.pi
+
+
+def test_parity_rates_at_scale_vs_oracle(solvers):
+    """BASELINE config 3, 2,048 seeded scenarios (the SAME generator the bench and the golden sets
+    use) solved by both GPU strategies and by the oracle with the reference's SuperLU step and
+    with a LAPACK step.  The reference's iteration is chaotic before it converges, so its own
+    iteration count depends on round-off: "identical counts" can only mean that the
+    GPU disagrees with the reference no more often than the reference disagrees with itself.
+    Asserted: both GPU disagreement counts <= the SuperLU-vs-LAPACK floor + 3 sigma of its
+    sampling error; the median phasor difference is < 1e-11 and its tail stays within 10x the reference's own."""
+    import oracle_pool
+    from harmonic_power_flow_b200 import scenarios
+    sol, net, _ = solvers("net3_c_h25")
+    S = 2048
+    P, Q, I_N = scenarios.make_batch(net, S, "tight")
+    pool = oracle_pool.OraclePool(O.net_from_golden(GOLDEN, "net3", 25, True))
+    try:
+        ref = pool.solve(P, Q, I_N, "superlu")
+        lap = pool.solve(P, Q, I_N, "lapack")
+    finally:
+        pool.close()
+    floor = oracle_pool.parity_rates(lap, ref)["vs_oracle"]
+    for strategy in ("structured", "dense"):
+        r = sol.solve(P, Q, I_N, dense=(strategy == "dense")).to_host()
+        assert (r["status"] == 0).all() and (ref["status"] == 0).all()
+        st = oracle_pool.parity_rates(r, ref)["vs_oracle"]
+        print("\nnet3 tight x%d [%s]: iteration mismatches %d (floor %d), phasor diff > 1e-9: %d (floor %d), "
+              "median %.2e, max where counts agree %.2e" % (S, strategy, st["iteration_mismatches"],
+              floor["iteration_mismatches"], st["phasor_diff_gt_1e9"], floor["phasor_diff_gt_1e9"],
+              st["phasor_diff_median"], st["phasor_diff_max_same_count"]))
+        assert st["n_iter_f_mismatches"] == 0
+        margin = lambda k: k + 3.0 * np.sqrt(k + 1.0)
+        assert st["iteration_mismatches"] <= margin(floor["iteration_mismatches"])
+        assert st["phasor_diff_gt_1e9"] <= margin(floor["phasor_diff_gt_1e9"])
+        assert st["phasor_diff_median"] < 1e-11
+        # (a last accepted step of ||f|| ~ 1e-4 leaves the iterate ~1e-5 from the converged one: the
+        # reference against itself reaches 2.6e-5 on the first 1,024 scenarios)
+        assert st["phasor_diff_max_same_count"] <= max(1e-6, 10 * floor["phasor_diff_max_same_count"])
 
 
 def test_config2_batch_1024_against_oracle(solvers):
@@ -620,11 +716,27 @@ def test_config4_radial_200_bus_against_oracle(tmp_path):
     info = sol.struct_info()
     assert info["available"] == 3 and info["nZ"] == 2480
     B = 300
-    P, Q, I_N = scenarios.make_batch(net, B, "tight", exact_prefix=8)
+    P, Q, I_N = scenarios.make_batch(net, B, "tight")
     r = sol.solve(P, Q, I_N)
     res = r.to_host()
     assert (res["status"] == 0).all() and (res["n_iter_f"] == 3).all()
-    _check_against_oracle(net, res, P, Q, I_N, [0, 1], 1e-9)
+    # 16 scenarios against the oracle (about 10 s of CPU each, fanned out over the host cores)
+    import oracle_pool
+    pool = oracle_pool.OraclePool(helpers.oracle_net(net))
+    try:
+        o = pool.solve(P[:, :16], Q[:, :16], I_N[:, :, :16], "superlu", chunk=1)
+    finally:
+        pool.close()
+    for b in range(16):
+        tag = "scenario %d: oracle it %d/%d err %.2e, gpu it %d/%d err %.2e" % (
+            b, o["n_iter_f"][b], o["n_iter_h"][b], o["err_h"][b], res["n_iter_f"][b], res["n_iter_h"][b], res["err_h"][b])
+        assert o["status"][b] == 0, tag
+        assert res["n_iter_f"][b] == o["n_iter_f"][b] and res["n_iter_h"][b] == o["n_iter_h"][b], tag
+        Vo = helpers.phasor(o["V_m"][:, :, b], o["V_a"][:, :, b])
+        Vg = helpers.phasor(res["V_m"][:, :, b], res["V_a"][:, :, b])
+        t = max(1e-9, 0.1 * max(o["err_h"][b], res["err_h"][b]))      # see _check_against_oracle
+        assert np.abs(Vo - Vg).max() <= t * np.abs(Vo).max(), tag
+        assert np.abs(o["I_inj"][:, :, b] - res["I_inj"][:, :, b]).max() <= 10 * t * np.abs(o["I_inj"][:, :, b]).max(), tag
     part = sol.solve(P[:, 100:190].copy(), Q[:, 100:190].copy(), I_N[:, :, 100:190].copy()).to_host()
     assert np.array_equal(part["V_m"], res["V_m"][:, :, 100:190]) and np.array_equal(part["n_iter_h"], res["n_iter_h"][100:190])
     sol.close()
