@@ -36,6 +36,7 @@
 //      finished lanes are refilled from the global queue                           | barrier (only if a lane finished)
 // Lanes are refilled individually because iteration counts differ (8..40).
 #pragma once
+#include <type_traits>
 #include "hpf_structured.cuh"
 // (needs absmax_bits of hpf_lane.cuh: include after it)
 
@@ -51,7 +52,39 @@ struct HwConsts {
 template <class D>
 __host__ __device__ constexpr size_t harm_hw_smem_bytes() {
     // sVnl [q][H][32] c128 | sW [nZ][32] c128 | sTot [m][32] c128 | sP, sQ [m][32] | red [2][32] | sbase
-    return ((size_t)(2 * D::q * D::H + 2 * (D::n * D::H - D::m) + 2 * D::m + 2 * D::m + 2) * 32) * sizeof(double) + 64;
+    return ((size_t)(2 * D::q * D::H + 2 * (D::n * D::H - D::m) + 2 * D::m + 2 * D::m + 2) * 32) * sizeof(double) + 64 +
+           sizeof(double2) * (D::H * D::n * D::n + D::q * D::H * D::H + (D::n * D::H - D::m) * D::m);
+}
+
+// 1 / x without the library's special-case path (a CALL, which also clobbers the uniform
+// registers that hold the constant-bank addresses): MUFU.RCP64H seed (2^-23) and two Newton steps,
+// <= 1 ulp for normal x; 0, Inf and denormals give NaN (such a state is reported as non-finite anyway).
+__device__ __forceinline__ double rcp_fast(const double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// numpy's a % (2 pi) (HG:548) without fmod: for |a| < 1e6 the quotient k = trunc(a / 2pi) is exact
+// up to one unit, a - k * fl(2pi) is exactly representable (it is fmod's result or off by one
+// period), so ONE fma reproduces fmod bit for bit after the off-by-one correction.
+__device__ __forceinline__ double mod_twopi_fast(const double va) {
+    const double twopi = 2.0 * CUDART_PI;
+    if (!(fabs(va) < 1.0e6)) return mod_twopi(va);        // huge, Inf, NaN: library path
+    const double k = trunc(va * 0.15915494309189535);
+    double r = fma(-k, twopi, va);
+    if (va >= 0.0) {                                       // fmod: sign of the dividend, |r| < 2 pi
+        if (r < 0.0) r += twopi;
+        else if (r >= twopi) r -= twopi;
+    } else {
+        if (r > 0.0) r -= twopi;
+        else if (r <= -twopi) r += twopi;
+    }
+    if (r != 0.0) { if (r < 0.0) r += twopi; } else r = 0.0;   // python %: the divisor's sign
+    return r;
 }
 
 // Gaussian elimination with partial pivoting on a register-resident augmented system (every index
@@ -73,7 +106,7 @@ __device__ __forceinline__ int gauss_regs(double (&A)[NX][NX + 1], double (&x)[N
         }
         const double pv = fabs(A[k][k]);
         if (!(pv > 0.0) || !(pv < CUDART_INF)) bad = 1;
-        const double r = 1.0 / A[k][k];
+        const double r = rcp_fast(A[k][k]);
 #pragma unroll
         for (int i = k + 1; i < NX; ++i) {
             const double l = A[i][k] * r;
@@ -97,13 +130,16 @@ __device__ __forceinline__ void hw_cp_async16(void* sdst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sa), "l"(gsrc) : "memory");
 }
 
-template <class D, bool COUPLED, int MINB>
-__global__ void __launch_bounds__(D::H * 32, MINB)
-harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArgs a) {
+// The Newton loop of one warp.  FUND = true: the fundamental warp (h = 0 is a compile-time constant:
+// its constants are immediate constant-bank operands); FUND = false: a harmonic warp, h >= 1 is
+// re-derived into a uniform register in every phase.  Both instances execute the same sequence
+// of CTA barriers (the third one depends on donemask, which every warp computes identically).
+template <class D, bool COUPLED, bool FUND>
+__device__ __forceinline__ void harm_hw_loop(const HwConsts<D, COUPLED>& C, const HarmTileArgs& a, double* smem,
+                                             const int hv) {
     constexpr int n = D::n, m = D::m, c = D::c, H = D::H, q = D::q, nH = n * H, nZ = nH - m;
     constexpr int nth = m - 1, nv = m - c, nx = nth + nv;
     constexpr int T = 32;
-    extern __shared__ __align__(16) double smem[];
     double2* sVnl = reinterpret_cast<double2*>(smem);             // [q][H][T] phasors of the nonlinear buses
     double2* sW = sVnl + q * H * T;                               // [nZ][T]   w_N (row z = s - m)
     double2* sTot = sW + nZ * T;                                  // [m][T]    V_F + u_F
@@ -111,16 +147,26 @@ harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArg
     double* sQ = sP + m * T;                                      // [m][T]
     unsigned long long* red = reinterpret_cast<unsigned long long*>(sQ + m * T);   // [2][T] ||f||_inf bit patterns
     int* sbase = reinterpret_cast<int*>(red + 2 * T);
+    // the harmonic warps read their constants from a shared-memory copy (one broadcast wavefront per
+    // LDS.128): with a run-time harmonic index ptxas turns constant-bank reads into register-indexed
+    // LDC, whose throughput (not the FP64 pipe) then bounds the kernel - measured
+    const double2* cY = reinterpret_cast<const double2*>(sbase + 16);
+    const double2* cYN = cY + H * n * n;
+    const double2* cG = cYN + (COUPLED ? q * H * H : q * H);
 
     const int lane = threadIdx.x & 31;
-    // warp-uniform harmonic index in a UNIFORM register: constants become c[0x0][UR + imm] operands
-    const int h = __reduce_min_sync(0xffffffffu, threadIdx.x >> 5);
+    // The harmonic index is warp-uniform.  It is re-derived with a warp reduction (CREDUX writes a
+    // UNIFORM register) at the start of every phase so that the constants are c[0x0][UR + imm]
+    // operands of the DFMAs themselves: a uniform register does not survive a CALL, and the
+    // phases below contain none (rcp_fast / mod_twopi_fast instead of the library routines).
     const size_t B = (size_t)a.B;
     const unsigned lt = (1u << lane) - 1u;
+    // loop-invariant row bases of this thread (rows s = h n + i, i = 0..n-1; consecutive rows are B
+    // elements apart): only the scenario offset is added at a refill / write-out
+    const size_t row0 = (size_t)hv * n * B;
+    const double2* const wN0 = a.wN + row0 - (size_t)m * B;       // row z = h n + i - m (never read for z < 0)
+    const double2* const IN0 = a.I_N + (size_t)hv * B;             // row k H + h
 
-    if (threadIdx.x == 0) sbase[0] = atomicAdd(a.work_counter, T);
-    if (threadIdx.x < 2 * T) red[threadIdx.x] = 0ull;
-    __syncthreads();
     int sc = sbase[0] + lane;
     if ((size_t)sc >= B) sc = -1;
     bool isnew = true;
@@ -134,36 +180,53 @@ harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArg
         // ================= A: refill, phasors =================
         if (isnew) {
             itc = 0;
-            if (h == 0) {
+            const bool live = sc >= 0;
+            const size_t so = live ? (size_t)sc : 0;
+            if (FUND) {
+                const double* pm = a.V_m + so;
+                const double* pa = a.V_a + so;
+                const double* pp = a.P + so;
+                const double* pq = a.Q + so;
 #pragma unroll
                 for (int i = 0; i < n; ++i) {
-                    Vm[i] = (sc >= 0) ? __ldcs(a.V_m + (size_t)i * B + sc) : 1.0;
-                    Va[i] = (sc >= 0) ? __ldcs(a.V_a + (size_t)i * B + sc) : 0.0;
+                    Vm[i] = live ? __ldcs(pm) : 1.0;
+                    Va[i] = live ? __ldcs(pa) : 0.0;
+                    pm += B; pa += B;
                 }
 #pragma unroll
                 for (int i = 0; i < m; ++i) {
-                    sP[i * T + lane] = (sc >= 0) ? __ldcs(a.P + (size_t)i * B + sc) : 0.0;
-                    sQ[i * T + lane] = (sc >= 0) ? __ldcs(a.Q + (size_t)i * B + sc) : 0.0;
+                    sP[i * T + lane] = live ? __ldcs(pp) : 0.0;
+                    sQ[i * T + lane] = live ? __ldcs(pq) : 0.0;
+                    pp += B; pq += B;
                 }
-                stat = (sc >= 0) ? a.status[sc] : 0;
+                stat = live ? a.status[so] : 0;
             } else {
 #pragma unroll
                 for (int i = 0; i < n; ++i) {
-                    Vm[i] = (sc >= 0) ? 0.1 : 1.0;                  // flat start of the harmonics (HG:183)
+                    Vm[i] = live ? 0.1 : 1.0;                       // flat start of the harmonics (HG:183)
                     Va[i] = 0.0;
                 }
             }
+            {
+                const double2* pin = IN0 + so;
 #pragma unroll
-            for (int k = 0; k < q; ++k)
-                IN[k] = (sc >= 0) ? __ldcs(a.I_N + (size_t)(k * H + h) * B + sc) : make_double2(0.0, 0.0);
+                for (int k = 0; k < q; ++k) {
+                    IN[k] = live ? __ldcs(pin) : make_double2(0.0, 0.0);
+                    pin += (size_t)H * B;
+                }
+            }
             // w_N rows of this thread: thread-private columns of sW, fetched asynchronously (consumed in
-            // phase C, warp 0's z < q rows in phase B)
+            // phase C; warp 0's rows z < q in phase B)
+            {
+                const double2* pw = wN0 + so;
+                double2* sw = sW + (hv * n - m) * T + lane;
 #pragma unroll
-            for (int i = 0; i < n; ++i) {
-                const int z = h * n + i - m;
-                if (z >= 0) {
-                    if (sc >= 0) hw_cp_async16(&sW[z * T + lane], a.wN + (size_t)z * B + sc);
-                    else sW[z * T + lane] = make_double2(0.0, 0.0);
+                for (int i = 0; i < n; ++i) {
+                    if (!FUND || i >= m) {
+                        if (live) hw_cp_async16(sw, pw);
+                        else *sw = make_double2(0.0, 0.0);
+                    }
+                    pw += B; sw += T;
                 }
             }
         }
@@ -176,26 +239,36 @@ harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArg
         }
         if (COUPLED) {
 #pragma unroll
-            for (int k = 0; k < q; ++k) sVnl[(k * H + h) * T + lane] = V[m + k];
+            for (int k = 0; k < q; ++k) sVnl[(k * H + hv) * T + lane] = V[m + k];
         }
         __syncthreads();
         // ================= B: mismatch rows (HG:360-388); border system =================
         long long mxb = 0;
-        auto yrow = [&](const int i) {
+        auto yrow = [&](const int h, const int i) {
             double2 f = make_double2(0.0, 0.0);
 #pragma unroll
-            for (int j = 0; j < n; ++j) f = cfma(f, C.Y[(h * n + i) * n + j], V[j]);
+            for (int j = 0; j < n; ++j) f = cfma(f, FUND ? C.Y[(h * n + i) * n + j] : cY[(h * n + i) * n + j], V[j]);
             return f;
         };
         // nonlinear bus k: (Y_h V_h)_i + I_N - sum_p Y_N[h][p] V_p,i   (HG:313-323,335-354)
-        auto nlrow = [&](const int k, double2 f) {
+        auto nlrow = [&](const int h, const int k, double2 f) {
             double2 acc;
             if (COUPLED) {
-                acc = make_double2(0.0, 0.0);
+                // two independent accumulators (even / odd p): the 2 H-deep dependent DFMA chain of a
+                // single accumulator is what the warp would otherwise wait on
+                double2 a0 = make_double2(0.0, 0.0), a1 = a0;
+                const double2* sv = sVnl + (k * H) * T + lane;
 #pragma unroll
-                for (int p = 0; p < H; ++p) acc = cfma(acc, C.YNk[(k * H + h) * H + p], sVnl[(k * H + p) * T + lane]);
+                const double2* yn = FUND ? C.YNk + (k * H + h) * H : cYN + (k * H + h) * H;
+#pragma unroll
+                for (int p = 0; p + 1 < H; p += 2) {
+                    a0 = cfma(a0, yn[p], sv[p * T]);
+                    a1 = cfma(a1, yn[p + 1], sv[(p + 1) * T]);
+                }
+                if (H & 1) a0 = cfma(a0, yn[H - 1], sv[(H - 1) * T]);
+                acc = cadd(a0, a1);
             } else {
-                acc = cmul(C.YNk[k * H + h], V[m + k]);
+                acc = cmul(FUND ? C.YNk[k * H + h] : cYN[k * H + h], V[m + k]);
             }
             inj[k] = make_double2(IN[k].x - acc.x, IN[k].y - acc.y);
             f = cadd(f, inj[k]);
@@ -203,20 +276,24 @@ harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArg
             absmax_bits(mxb, f.y);
         };
         double xF[nx > 0 ? nx : 1];
-        if (h != 0) {
+        if constexpr (!FUND) {
+            // (a per-harmonic compile-time copy of this block - immediate constant operands, no loads -
+            // was measured 2.3x SLOWER: 13 code paths per CTA thrash the instruction cache)
+            const int hh = hv;
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-                const double2 f = yrow(i);
+                const double2 f = yrow(hh, i);
                 if (i >= m) {
-                    nlrow(i - m, f);
+                    nlrow(hh, i - m, f);
                 } else {
                     absmax_bits(mxb, f.x);
                     absmax_bits(mxb, f.y);
                 }
             }
         } else {
+            constexpr int hh = 0;
 #pragma unroll
-            for (int k = 0; k < q; ++k) nlrow(k, yrow(m + k));
+            for (int k = 0; k < q; ++k) nlrow(hh, k, yrow(hh, m + k));
             cp_async_wait<0>();                                  // w_N rows z < q of a refilled lane
             double M[nx > 0 ? nx : 1][nx + 1];
 #pragma unroll
@@ -225,10 +302,10 @@ harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArg
                 for (int cc = 0; cc <= nx; ++cc) M[r][cc] = 0.0;
             double rvm[m];
 #pragma unroll
-            for (int j = c; j < m; ++j) rvm[j] = 1.0 / Vm[j];
+            for (int j = c; j < m; ++j) rvm[j] = rcp_fast(Vm[j]);
 #pragma unroll
             for (int i = 1; i < m; ++i) {
-                const double2 I1 = yrow(i);
+                const double2 I1 = yrow(hh, i);
                 const double2 s_i = cmul(V[i], cconj(I1));                   // V_i conj(I_i)
                 const double pl = sP[i * T + lane], ql = sQ[i * T + lane];
                 const double2 fs = make_double2(pl + s_i.x, ql + s_i.y);    // power mismatch (HG:372-380)
@@ -283,28 +360,38 @@ harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArg
         const bool done = active && !cont;
         if (__ballot_sync(0xffffffffu, active) == 0u) break;          // same lanes in every warp: uniform over the CTA
         const unsigned donemask = __ballot_sync(0xffffffffu, done);
-        if (h == 0) {
+        // the queue position of the refills is requested first: its latency hides behind the update
+        int claimed = 0;
+        if (donemask && threadIdx.x == 0) claimed = atomicAdd(a.work_counter, __popc(donemask));
+        if (FUND) {
             red[(cur ^ 1) * T + lane] = 0ull;                         // next round's accumulator
             if (a.hist_h && active) a.hist_h[(size_t)itc * B + sc] = err;
         }
         if (done) {
             // post-processing (HG:547-549) + write-out of the thread's n rows
+            double* om = a.V_m + row0 + sc;
+            double* oa = a.V_a + row0 + sc;
 #pragma unroll
             for (int i = 0; i < n; ++i) {
                 double vm = Vm[i], va = Va[i];
                 if (!(a.flags & HPF_SOLVE_RAW)) {
                     if (vm < 0.0) va += CUDART_PI;
-                    va = mod_twopi(va);
+                    va = mod_twopi_fast(va);
                     if (vm < 0.0) vm = -vm;
                 }
-                a.V_m[(size_t)(h * n + i) * B + sc] = vm;
-                a.V_a[(size_t)(h * n + i) * B + sc] = va;
+                *om = vm;
+                *oa = va;
+                om += B; oa += B;
             }
             if (a.I_inj) {
+                double2* oj = a.I_inj + (size_t)hv * B + sc;
 #pragma unroll
-                for (int k = 0; k < q; ++k) a.I_inj[(size_t)(k * H + h) * B + sc] = inj[k];
+                for (int k = 0; k < q; ++k) {
+                    *oj = inj[k];
+                    oj += (size_t)H * B;
+                }
             }
-            if (h == 0) {
+            if (FUND) {
                 int st = stat & 0xff;
                 if ((stat & 0x200) && st == HPF_ST_CONVERGED) st = HPF_ST_SINGULAR;
                 if (itc >= a.max_h && st == HPF_ST_CONVERGED) st = HPF_ST_MAXITER;
@@ -314,35 +401,44 @@ harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArg
                 a.status[sc] = st;
             }
         }
-        if (h != 0) cp_async_wait<0>();                                // w_N rows of a refilled lane
-        if (cont) {
+        if (!FUND) cp_async_wait<0>();                               // w_N rows of a refilled lane
+        {
             double2 tot[m];
 #pragma unroll
             for (int i = 0; i < m; ++i) tot[i] = sTot[i * T + lane];
+            auto update = [&](const int hc) {
 #pragma unroll
-            for (int i = 0; i < n; ++i) {
-                const int z = h * n + i - m;                               // warp-uniform
-                if (z >= 0) {
-                    // u_z = -V_z - sum_i G[z][i] (V_i + u_F,i) - w_N,z ; polar conversion; update
-                    const double2 w = sW[z * T + lane];
-                    double2 acc = make_double2(V[i].x + w.x, V[i].y + w.y);
+                for (int i = 0; i < n; ++i) {
+                    const int z0 = hc * n - m;
+                    if (!FUND || i >= m) {
+                        const int z = z0 + i;
+                        // u_z = -V_z - sum_i G[z][i] (V_i + u_F,i) - w_N,z ; polar conversion; update
+                        const double2 w = sW[z * T + lane];
+                        double2 acc = make_double2(V[i].x + w.x, V[i].y + w.y);
 #pragma unroll
-                    for (int j = 0; j < m; ++j) acc = cfma(acc, C.G[z * m + j], tot[j]);
-                    // conj(E) u with E = V / V_m:  dV_m = Re(conj(V) u) / V_m,  dtheta = Im(conj(V) u) / V_m^2
-                    const double2 cv = cmul(make_double2(V[i].x, -V[i].y), cneg(acc));
-                    const double rv = 1.0 / Vm[i];
-                    Va[i] += (cv.y * rv) * rv;
-                    Vm[i] += cv.x * rv;
-                } else if (i >= 1) {                                       // linear bus at the fundamental (h == 0)
-                    Va[i] += xF[i - 1];
-                    if (i >= c) Vm[i] += xF[nth + i - c];
+                        for (int j = 0; j < m; ++j) acc = cfma(acc, FUND ? C.G[z * m + j] : cG[z * m + j], tot[j]);
+                        // conj(E) u with E = V / V_m:  dV_m = Re(conj(V) u) / V_m,  dtheta = Im(conj(V) u) / V_m^2
+                        const double2 cv = cmul(make_double2(V[i].x, -V[i].y), cneg(acc));
+                        const double rv = rcp_fast(Vm[i]);
+                        if (cont) {
+                            Va[i] += (cv.y * rv) * rv;
+                            Vm[i] += cv.x * rv;
+                        }
+                    } else if (i >= 1) {                                   // linear bus at the fundamental
+                        if (cont) {
+                            Va[i] += xF[i - 1];
+                            if (i >= c) Vm[i] += xF[nth + i - c];
+                        }
+                    }
                 }
-            }
-            ++itc;
+            };
+            if constexpr (FUND) update(0);
+            else update(hv);
+            if (cont) ++itc;
         }
         isnew = false;
         if (donemask) {
-            if (threadIdx.x == 0) sbase[0] = atomicAdd(a.work_counter, __popc(donemask));
+            if (threadIdx.x == 0) sbase[0] = claimed;
             __syncthreads();
             if (done) {
                 const int idx = sbase[0] + __popc(donemask & lt);
@@ -352,4 +448,28 @@ harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArg
         }
         cur ^= 1;
     }
+}
+
+template <class D, bool COUPLED, int MINB>
+__global__ void __launch_bounds__(D::H * 32, MINB)
+harm_hw_kernel(const __grid_constant__ HwConsts<D, COUPLED> C, const HarmTileArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int T = 32;
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(
+        smem + (2 * D::q * D::H + 2 * (D::n * D::H - D::m) + 2 * D::m + 2 * D::m) * T);
+    int* sbase = reinterpret_cast<int*>(red + 2 * T);
+    if (threadIdx.x == 0) sbase[0] = atomicAdd(a.work_counter, T);
+    if (threadIdx.x < 2 * T) red[threadIdx.x] = 0ull;
+    {
+        double2* cc = reinterpret_cast<double2*>(sbase + 16);
+        constexpr int nY = D::H * D::n * D::n, nYN = COUPLED ? D::q * D::H * D::H : D::q * D::H;
+        constexpr int nG = (D::n * D::H - D::m) * D::m;
+        for (int t = threadIdx.x; t < nY; t += D::H * 32) cc[t] = C.Y[t];
+        for (int t = threadIdx.x; t < nYN; t += D::H * 32) cc[nY + t] = C.YNk[t];
+        for (int t = threadIdx.x; t < nG; t += D::H * 32) cc[nY + nYN + t] = C.G[t];
+    }
+    __syncthreads();
+    const int hv = threadIdx.x >> 5;
+    if (hv == 0) harm_hw_loop<D, COUPLED, true>(C, a, smem, hv);
+    else harm_hw_loop<D, COUPLED, false>(C, a, smem, hv);
 }

@@ -1074,6 +1074,9 @@ struct hpf_handle {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     int ev_valid = 0;             // 0 none, 1 structured (3 events), 2 dense (ev[1], ev[2])
     long long launches = 0;
+    cudaEvent_t ev_last = nullptr;     // recorded after the last kernel sequence of this handle
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false;
     std::string err;
 };
 
@@ -1089,6 +1092,49 @@ static int fail(hpf_t* h, int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                           \
             return fail(h, HPF_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
+
+// Makes the handle's device current for the duration of an entry point and restores the caller's
+// current device on exit: a process may hold handles on several GPUs, and torch reads the
+// current device with cudaGetDevice.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ENTER_DEVICE(h) DeviceGuard dg_((h)->device); CK(dg_.err)
+
+// One kernel sequence in flight per handle.  The work-queue counter, the w_N scratch, the LU
+// workspaces and Y(h) itself live in the handle, so a call that arrives on a DIFFERENT stream than
+// the previous one is ordered after it (event wait on the device, the host does not block);
+// calls on the same stream are ordered by the stream.
+static int order_after_previous(hpf_t* h, cudaStream_t st) {
+    if (h->last_valid && st != h->last_stream) CK(cudaStreamWaitEvent(st, h->ev_last, 0));
+    return HPF_OK;
+}
+static int mark_last(hpf_t* h, cudaStream_t st) {
+    CK(cudaEventRecord(h->ev_last, st));
+    h->last_stream = st;
+    h->last_valid = true;
+    return HPF_OK;
+}
+
+// Runs one entry point's launches ordered after the handle's previous kernel sequence and
+// records the event the next one will wait on.
+template <class F>
+static int ordered(hpf_t* h, void* stream, F body) {
+    if (!h) return body();
+    ENTER_DEVICE(h);
+    int rc = order_after_previous(h, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = body();
+    if (rc) return rc;
+    return mark_last(h, (cudaStream_t)stream);
+}
 
 static DevNet devnet(const hpf_t* h) {
     DevNet d;
@@ -1175,7 +1221,7 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     if (!P || !Q || !V_m || !V_a || !n_iter_f ||
         (mode == 0 && (!n_iter_h || !err_h || !status || (h->q > 0 && !I_N))))
         return fail(h, HPF_E_INVALID, std::string(who) + ": NULL buffer");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     DevNet net = devnet(h);
     if (mode == 1) net.N = net.Nf;      // fundamental only: size the matrix for Nf
@@ -1693,7 +1739,8 @@ int hpf_create(hpf_t** out, int device) {
     if (!h) return fail(nullptr, HPF_E_NOMEM, "hpf_create: out of host memory");
     h->device = device;
     cudaDeviceProp prop;
-    e = cudaSetDevice(device);
+    DeviceGuard dg_(device);
+    e = dg_.err;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) {
         delete h;
@@ -1715,7 +1762,9 @@ int hpf_create(hpf_t** out, int device) {
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     e = cudaMalloc((void**)&h->d_counter, 8 * sizeof(int));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming);
     if (e != cudaSuccess) {
+        cudaFree(h->d_counter);
         delete h;
         return fail(nullptr, HPF_E_CUDA, std::string("hpf_create: ") + cudaGetErrorString(e));
     }
@@ -1725,8 +1774,9 @@ int hpf_create(hpf_t** out, int device) {
 
 int hpf_destroy(hpf_t* h) {
     if (!h) return HPF_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard dg_(h->device);
     cudaDeviceSynchronize();
+    if (h->ev_last) cudaEventDestroy(h->ev_last);
     cudaFree(h->d_harm); cudaFree(h->d_from); cudaFree(h->d_to); cudaFree(h->d_devof);
     cudaFree(h->d_R); cudaFree(h->d_X); cudaFree(h->d_G); cudaFree(h->d_B); cudaFree(h->d_Xsh);
     cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work); cudaFree(h->d_io); cudaFree(h->d_Ainv); cudaFree(h->d_Gz);
@@ -1751,7 +1801,7 @@ int hpf_set_network(hpf_t* h, int n, int m, int c, int H, const int* harmonics, 
     for (int l = 0; l < L; ++l)
         if (from_id[l] < 1 || from_id[l] > n || to_id[l] < 1 || to_id[l] > n)
             return fail(h, HPF_E_INVALID, "hpf_set_network: line endpoint outside 1..n");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     h->n = n; h->m = m; h->c = c; h->H = H; h->q = n - m; h->L = L;
     CK(upload(&h->d_harm, harmonics, (size_t)H));
     CK(upload(&h->d_from, from_id, (size_t)L));
@@ -1780,7 +1830,7 @@ int hpf_set_devices(hpf_t* h, int n_dev, int coupled, const double* Y_N, const i
     for (int k = 0; k < h->q; ++k)
         if (dev_of_nl_bus[k] < 0 || dev_of_nl_bus[k] >= n_dev)
             return fail(h, HPF_E_INVALID, "hpf_set_devices: dev_of_nl_bus entry outside 0..n_dev-1");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     h->n_dev = n_dev;
     h->coupled = coupled ? 1 : 0;
     const size_t per = coupled ? (size_t)h->H * h->H : (size_t)h->H;
@@ -1797,7 +1847,7 @@ int hpf_set_transformers(hpf_t* h, const double* tau, const double* phase_shift_
     if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_set_transformers: call hpf_set_network first");
     if ((tau == nullptr) != (phase_shift_deg == nullptr))
         return fail(h, HPF_E_INVALID, "hpf_set_transformers: give both arrays or neither");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     cudaFree(h->d_tau); cudaFree(h->d_phase); h->d_tau = nullptr; h->d_phase = nullptr;
     if (tau) {
         for (int l = 0; l < h->L; ++l)
@@ -1822,10 +1872,10 @@ int hpf_set_y_options(hpf_t* h, int flags) {
     return HPF_OK;
 }
 
-int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
+static int build_Y_impl(hpf_t* h, double* Y_out, void* stream) {
     if (!h) return HPF_E_INVALID;
     if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_build_Y: call hpf_set_network first");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     const int total = h->n * h->H;
     ybus_kernel<<<(total + 127) / 128, 128, 0, st>>>(h->n, h->H, h->L, h->d_harm, h->d_from, h->d_to,
@@ -1842,11 +1892,15 @@ int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
     return HPF_OK;
 }
 
+int hpf_build_Y(hpf_t* h, double* Y_out, void* stream) {
+    return ordered(h, stream, [&] { return build_Y_impl(h, Y_out, stream); });
+}
+
 int hpf_set_Y(hpf_t* h, const double* Y) {
     if (!h) return HPF_E_INVALID;
     if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_set_Y: call hpf_set_network first");
     if (!Y) return fail(h, HPF_E_INVALID, "hpf_set_Y: Y is NULL");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     CK(cudaMemcpy(h->d_Y, Y, (size_t)h->H * h->n * h->n * sizeof(double2), cudaMemcpyHostToDevice));
     h->have_Y = true;
     h->struct_state = 0;
@@ -1860,7 +1914,7 @@ int hpf_thd(hpf_t* h, int B, const double* V_m, double* thd, void* stream) {
     if (!h->have_net) return fail(h, HPF_E_INVALID, "hpf_thd: call hpf_set_network first");
     if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_thd: B < 0");
     if (!V_m || !thd) return fail(h, HPF_E_INVALID, "hpf_thd: NULL buffer");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     const size_t total = (size_t)h->n * B;
     thd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->n, h->H, h->d_harm, B,
                                                                                     V_m, thd);
@@ -1874,7 +1928,7 @@ int hpf_bus_currents(hpf_t* h, int B, const double* V_m, const double* V_a, doub
     if (rc) return rc;
     if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_bus_currents: B < 0");
     if (!V_m || !V_a || !I_bus) return fail(h, HPF_E_INVALID, "hpf_bus_currents: NULL buffer");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     const DevNet net = devnet(h);
     const size_t total = (size_t)net.nH * B;
     bus_currents_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
@@ -1886,7 +1940,7 @@ int hpf_bus_currents(hpf_t* h, int B, const double* V_m, const double* V_a, doub
 
 int hpf_set_profiling(hpf_t* h, int enabled) {
     if (!h) return HPF_E_INVALID;
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     if (enabled)
         for (int i = 0; i < 3; ++i)
             if (!h->ev[i]) CK(cudaEventCreate(&h->ev[i]));
@@ -1930,7 +1984,7 @@ static int solve_dispatch(hpf_t* h, int B, const double* P, const double* Q, con
         if (rc) return rc;
         if (!P || !Q || !V_m || !V_a || !n_iter_f || !n_iter_h || !err_h || !status || (h->q > 0 && !I_N))
             return fail(h, HPF_E_INVALID, "hpf_solve: NULL buffer");
-        CK(cudaSetDevice(h->device));
+        ENTER_DEVICE(h);
         rc = ensure_struct(h, (cudaStream_t)stream);
         if (rc) return rc;
         if (h->struct_state >= 1)
@@ -1949,14 +2003,16 @@ int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I
               double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status,
               double* err_hist_f, double* err_hist_h, void* stream) {
     if (h) { h->cur_slot = 0; h->wN_slot_stride = 0; }      // (a failed hpf_solve_host may have left them set)
-    return solve_dispatch(h, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a, I_inj,
-                          n_iter_f, n_iter_h, err_h, status, err_hist_f, err_hist_h, stream);
+    return ordered(h, stream, [&] {
+        return solve_dispatch(h, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a, I_inj,
+                              n_iter_f, n_iter_h, err_h, status, err_hist_f, err_hist_h, stream);
+    });
 }
 
 int hpf_struct_info(hpf_t* h, int* available, int* nZ, double* pivot_min, double* pivot_max) {
     int rc = ready(h, "hpf_struct_info", true);
     if (rc) return rc;
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     rc = ensure_struct(h, nullptr);
     if (rc) return rc;
     if (available) *available = h->struct_state >= 1 ? h->struct_state : 0;
@@ -1966,14 +2022,14 @@ int hpf_struct_info(hpf_t* h, int* available, int* nZ, double* pivot_min, double
     return HPF_OK;
 }
 
-int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const double* P,
-                    const double* Q, const double* I_N, double* dx, void* stream) {
+static int newton_step_impl(hpf_t* h, int B, const double* V_m, const double* V_a, const double* P,
+                            const double* Q, const double* I_N, double* dx, void* stream) {
     int rc = ready(h, "hpf_newton_step", true);
     if (rc) return rc;
     if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_newton_step: B < 0");
     if (!V_m || !V_a || !P || !Q || !dx || (h->q > 0 && !I_N))
         return fail(h, HPF_E_INVALID, "hpf_newton_step: NULL buffer");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     rc = ensure_struct(h, (cudaStream_t)stream);
     if (rc) return rc;
     if (h->struct_state < 1)
@@ -1991,6 +2047,11 @@ int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const
     return launch_harm(h, net, sn, ha, false, (cudaStream_t)stream);
 }
 
+int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const double* P,
+                    const double* Q, const double* I_N, double* dx, void* stream) {
+    return ordered(h, stream, [&] { return newton_step_impl(h, B, V_m, V_a, P, Q, I_N, dx, stream); });
+}
+
 int hpf_ne_extract(hpf_t* h, int D, int N, const double* Vf, const double* Vh, const double* I_f,
                    const double* I_h, double* Y_N_c, double* I_N_c, double* Y_N_uc, double* I_N_uc,
                    int* info, void* stream) {
@@ -1999,7 +2060,7 @@ int hpf_ne_extract(hpf_t* h, int D, int N, const double* Vf, const double* Vh, c
     if (N < 2) return fail(h, HPF_E_INVALID, "hpf_ne_extract: at least 2 frequencies needed");
     if (!Vf || !Vh || !I_f || !I_h || !Y_N_c || !I_N_c || !Y_N_uc || !I_N_uc || !info)
         return fail(h, HPF_E_INVALID, "hpf_ne_extract: NULL buffer");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     const size_t smem = ne_extract_smem_bytes(N);
     int occ = 0;
     int rc = prep_kernel(h, ne_extract_kernel, smem, "hpf_ne_extract", &occ, 256);
@@ -2020,8 +2081,10 @@ int hpf_ne_extract(hpf_t* h, int D, int N, const double* Vf, const double* Vh, c
 int hpf_fund_solve(hpf_t* h, int B, const double* P, const double* Q, double thresh_f, int max_iter_f,
                    double* V_m, double* V_a, int* n_iter_f, double* err_f, double* err_hist_f,
                    void* stream) {
-    return solve_common(h, 1, B, P, Q, nullptr, thresh_f, max_iter_f, 0.0, 0, 0, V_m, V_a, nullptr,
-                        n_iter_f, nullptr, nullptr, err_f, nullptr, err_hist_f, nullptr, stream);
+    return ordered(h, stream, [&] {
+        return solve_common(h, 1, B, P, Q, nullptr, thresh_f, max_iter_f, 0.0, 0, 0, V_m, V_a, nullptr,
+                            n_iter_f, nullptr, nullptr, err_f, nullptr, err_hist_f, nullptr, stream);
+    });
 }
 
 } // extern "C"
@@ -2041,7 +2104,7 @@ static int solve_host_impl(hpf_t* h, int B, const double* P, const double* Q, co
     if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_solve_host: B < 0");
     if (!P || !Q || !V_m || !V_a || !n_iter_f || !n_iter_h || !err_h || !status || (h->q > 0 && !I_N))
         return fail(h, HPF_E_INVALID, "hpf_solve_host: NULL buffer");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     // Pipelined in chunks of scenarios: while chunk k is being solved, chunk k+1 is copied in and
     // the results of chunk k-1 are copied out (PCIe is full duplex); consecutive chunks alternate
     // between two compute streams so that the long-iteration tail of one chunk overlaps the start
@@ -2164,14 +2227,14 @@ int hpf_solve_host_keep(hpf_t* h, int B, const double* P, const double* Q, const
                            n_iter_f, n_iter_h, err_h, status, &k);
 }
 
-int hpf_mismatch(hpf_t* h, int B, const double* V_m, const double* V_a, const double* P, const double* Q,
+static int mismatch_impl(hpf_t* h, int B, const double* V_m, const double* V_a, const double* P, const double* Q,
                  const double* I_N, double* f, double* err, double* I_inj, void* stream) {
     int rc = ready(h, "hpf_mismatch", true);
     if (rc) return rc;
     if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_mismatch: B < 0");
     if (!V_m || !V_a || !P || !Q || !f || !err || (h->q > 0 && !I_N))
         return fail(h, HPF_E_INVALID, "hpf_mismatch: NULL buffer");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     const DevNet net = devnet(h);
     MismatchArgs a;
     a.B = B; a.V_m = V_m; a.V_a = V_a; a.P = P; a.Q = Q; a.I_N = (const double2*)I_N;
@@ -2218,14 +2281,19 @@ int hpf_mismatch(hpf_t* h, int B, const double* V_m, const double* V_a, const do
     return HPF_OK;
 }
 
-int hpf_jacobian(hpf_t* h, int B, const double* V_m, const double* V_a, double* J, void* stream) {
+int hpf_mismatch(hpf_t* h, int B, const double* V_m, const double* V_a, const double* P, const double* Q,
+                 const double* I_N, double* f, double* err, double* I_inj, void* stream) {
+    return ordered(h, stream, [&] { return mismatch_impl(h, B, V_m, V_a, P, Q, I_N, f, err, I_inj, stream); });
+}
+
+static int jacobian_impl(hpf_t* h, int B, const double* V_m, const double* V_a, double* J, void* stream) {
     int rc = ready(h, "hpf_jacobian", true);
     if (rc) return rc;
     if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_jacobian: B < 0");
     if (!V_m || !V_a || !J) return fail(h, HPF_E_INVALID, "hpf_jacobian: NULL buffer");
     if ((reinterpret_cast<uintptr_t>(J) & 15) != 0)
         return fail(h, HPF_E_INVALID, "hpf_jacobian: J must be 16-byte aligned");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     const DevNet net = devnet(h);
     JacobianArgs a;
     a.B = B; a.V_m = V_m; a.V_a = V_a; a.J = J; a.stride = hpf_jacobian_stride(h);
@@ -2250,12 +2318,16 @@ int hpf_jacobian(hpf_t* h, int B, const double* V_m, const double* V_a, double* 
     return HPF_OK;
 }
 
-int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, int* info, void* stream) {
+int hpf_jacobian(hpf_t* h, int B, const double* V_m, const double* V_a, double* J, void* stream) {
+    return ordered(h, stream, [&] { return jacobian_impl(h, B, V_m, V_a, J, stream); });
+}
+
+static int lu_solve_impl(hpf_t* h, int B, const double* J, const double* f, double* dx, int* info, void* stream) {
     int rc = ready(h, "hpf_lu_solve", false);
     if (rc) return rc;
     if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_lu_solve: B < 0");
     if (!J || !f || !dx || !info) return fail(h, HPF_E_INVALID, "hpf_lu_solve: NULL buffer");
-    CK(cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     const DevNet net = devnet(h);
     LuArgs a;
     a.B = B; a.J = J; a.f = f; a.dx = dx; a.info = info; a.stride = hpf_jacobian_stride(h);
@@ -2291,6 +2363,10 @@ int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, 
     h->launches++;
     CK(cudaGetLastError());
     return HPF_OK;
+}
+
+int hpf_lu_solve(hpf_t* h, int B, const double* J, const double* f, double* dx, int* info, void* stream) {
+    return ordered(h, stream, [&] { return lu_solve_impl(h, B, J, f, dx, info, stream); });
 }
 
 }  // extern "C"

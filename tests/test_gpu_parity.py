@@ -212,7 +212,7 @@ def test_fused_solve_nominal_cases(solvers, case, strategy):
     assert np.isnan(hist[k:]).all() and np.isfinite(hist[:k]).all()
     hf = r.err_hist_f[:, 0].cpu().numpy()
     kf = len(d["err_f_hist"])
-    assert np.isnan(hf[kf:]).all() and np.allclose(hf[:kf], d["err_f_hist"], rtol=1e-6, atol=1e-15)
+    assert np.isnan(hf[kf:]).all() and np.allclose(hf[:kf], d["err_f_hist"], rtol=1e-6, atol=1e-11)
     # the error PATH, not only the end: tight at the start, then round-off is amplified by the
     # non-contractive early iterations (cond(J) up to 2e7)
     assert np.allclose(hist[:4], d["err_h_hist"][:4], rtol=1e-9)
