@@ -170,7 +170,7 @@ __device__ __forceinline__ void harm_hw_loop(const HwConsts<D, COUPLED>& C, cons
     int sc = sbase[0] + lane;
     if ((size_t)sc >= B) sc = -1;
     bool isnew = true;
-    int itc = 0, stat = 0, cur = 0;
+    int itc = 0, stat = 0, cur = 0, rc = 0;
     double Vm[n], Va[n];
     double2 V[n], IN[q], inj[q];
 #pragma unroll
@@ -357,9 +357,18 @@ __device__ __forceinline__ void harm_hw_loop(const HwConsts<D, COUPLED>& C, cons
         const double err = __longlong_as_double((long long)red[cur * T + lane]);
         const bool active = sc >= 0;
         const bool cont = active && (err > a.thresh_h) && (itc < a.max_h);
-        const bool done = active && !cont;
-        if (__ballot_sync(0xffffffffu, active) == 0u) break;          // same lanes in every warp: uniform over the CTA
-        const unsigned donemask = __ballot_sync(0xffffffffu, done);
+        const unsigned actmask = __ballot_sync(0xffffffffu, active);
+        if (actmask == 0u) break;                                     // same lanes in every warp: uniform over the CTA
+        // Finished lanes are written out and refilled in BATCHES: every warp executes the write-out /
+        // refill code (and the CTA the queue atomic and a third barrier) whenever ANY lane is serviced,
+        // which would be 4 rounds out of 5 with lanes serviced one by one.  A finished lane keeps its
+        // state frozen (cont stays false, its mismatch is recomputed bit-identically) until the next
+        // service round: every `epoch`-th round, or at once when 8 lanes wait or nothing else is left.
+        unsigned donemask = __ballot_sync(0xffffffffu, active && !cont);
+        ++rc;
+        if (!(rc >= a.epoch || donemask == actmask || __popc(donemask) >= 8)) donemask = 0u;
+        if (donemask) rc = 0;
+        const bool done = (donemask >> lane) & 1u;
         // the queue position of the refills is requested first: its latency hides behind the update
         int claimed = 0;
         if (donemask && threadIdx.x == 0) claimed = atomicAdd(a.work_counter, __popc(donemask));

@@ -1065,6 +1065,7 @@ struct hpf_handle {
     std::vector<char> hw_consts;  // HwConsts<D, coupled> of the one-warp-per-harmonic kernel (hw_shape != 0)
     int hw_shape = 0;             // 0 none, 1 = Dims<4,3,2,13,1>, 2 = Dims<4,2,1,10,2>
     int harm_tile_only = 0;       // $HPF_HARM_KERNEL=tile: 32-scenario tile kernel instead (A/B measurements)
+    int hw_epoch = 3;             // $HPF_HW_EPOCH: service interval of finished lanes in the one-warp-per-harmonic kernel
     int hw_minb = 2;              // $HPF_HW_MINB: register budget of the one-warp-per-harmonic kernel (CTAs per SM)
     int max_ctas = 0;             // $HPF_MAX_CTAS: cap on the grid of the persistent kernels (tests: forces queue refills on small batches)
     std::vector<int> hdev;
@@ -1677,7 +1678,7 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
         ha.wN = h->d_wN + (size_t)h->cur_slot * h->wN_slot_stride;
         ha.thresh_h = thresh_h; ha.max_h = max_h; ha.V_m = V_m; ha.V_a = V_a; ha.I_inj = (double2*)I_inj;
         ha.n_iter_h = n_iter_h; ha.status = status; ha.err_h = err_h; ha.work_counter = h->d_counter + h->cur_slot;
-        ha.dx_out = nullptr; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0; ha.hist_h = hist_h;
+        ha.dx_out = nullptr; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0; ha.hist_h = hist_h; ha.epoch = h->hw_epoch;
         rc = launch_harm(h, net, sn, ha, true, st);
         if (rc) return rc;
     }
@@ -1757,6 +1758,7 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_STRUCT_VARIANT")) h->force_variant = atoi(ev);
     if (const char* ev = getenv("HPF_DENSE_BLOCKED")) h->dense_blocked = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_HARM_KERNEL")) h->harm_tile_only = (strcmp(ev, "tile") == 0) ? 1 : 0;
+    if (const char* ev = getenv("HPF_HW_EPOCH")) h->hw_epoch = atoi(ev) >= 1 ? atoi(ev) : 1;
     if (const char* ev = getenv("HPF_HW_MINB")) h->hw_minb = (atoi(ev) == 1) ? 1 : 2;
     if (const char* ev = getenv("HPF_MAX_CTAS")) h->max_ctas = atoi(ev) > 0 ? atoi(ev) : 0;
     h->sm_count = prop.multiProcessorCount;
@@ -2043,7 +2045,7 @@ static int newton_step_impl(hpf_t* h, int B, const double* V_m, const double* V_
     ha.wN = h->d_wN;
     ha.thresh_h = 0.0; ha.max_h = 1; ha.V_m = const_cast<double*>(V_m); ha.V_a = const_cast<double*>(V_a);
     ha.I_inj = nullptr; ha.n_iter_h = nullptr; ha.status = nullptr; ha.err_h = nullptr;
-    ha.work_counter = nullptr; ha.dx_out = dx; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0; ha.hist_h = nullptr;
+    ha.work_counter = nullptr; ha.dx_out = dx; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0; ha.hist_h = nullptr; ha.epoch = 1;
     return launch_harm(h, net, sn, ha, false, (cudaStream_t)stream);
 }
 

@@ -633,6 +633,7 @@ struct HarmTileArgs {
     size_t gstate_stride;    //   doubles per CTA (0: state in shared memory)
     int lub_doubles;         //   shared-memory work area of the blocked LU (doubles)
     double* hist_h;          // [max_h + 1, B] mismatch norm before each step and after the last one, or NULL
+    int epoch;               // harm_hw_kernel: finished lanes are serviced every `epoch` rounds (>= 1)
 };
 
 
