@@ -1112,12 +1112,20 @@ struct DeviceGuard {
 // One kernel sequence in flight per handle.  The work-queue counter, the w_N scratch, the LU
 // workspaces and Y(h) itself live in the handle, so a call that arrives on a DIFFERENT stream than
 // the previous one is ordered after it (event wait on the device, the host does not block);
-// calls on the same stream are ordered by the stream.
+// calls on the same stream are ordered by the stream.  A stream that is being CAPTURED into a
+// CUDA graph is left alone (an event recorded inside a capture cannot be waited on from outside
+// it, and the other way round): the owner of the graph orders its replays against other work.
+static bool stream_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+    return cs != cudaStreamCaptureStatusNone;
+}
 static int order_after_previous(hpf_t* h, cudaStream_t st) {
-    if (h->last_valid && st != h->last_stream) CK(cudaStreamWaitEvent(st, h->ev_last, 0));
+    if (h->last_valid && st != h->last_stream && !stream_capturing(st)) CK(cudaStreamWaitEvent(st, h->ev_last, 0));
     return HPF_OK;
 }
 static int mark_last(hpf_t* h, cudaStream_t st) {
+    if (stream_capturing(st)) return HPF_OK;
     CK(cudaEventRecord(h->ev_last, st));
     h->last_stream = st;
     h->last_valid = true;
@@ -2132,6 +2140,10 @@ static int solve_host_impl(hpf_t* h, int B, const double* P, const double* Q, co
         for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&h->ev_io[i], cudaEventDisableTiming));
     }
     cudaStream_t s_in = h->st_io[0], s_out = h->st_io[2];
+    // ordered after the handle's previous kernel sequence like every other entry point (the copy-in
+    // overwrites the staging buffers, the solves share the handle's scratch)
+    if (h->last_valid)
+        for (int i = 0; i < 4; ++i) CK(cudaStreamWaitEvent(h->st_io[i], h->ev_last, 0));
     // two compute streams only where concurrent solves share no scratch (tile variant)
     rc = ensure_struct(h, h->st_io[1]);
     if (rc) return rc;
@@ -2203,6 +2215,7 @@ static int solve_host_impl(hpf_t* h, int B, const double* P, const double* Q, co
         const cudaError_t e2 = cudaStreamSynchronize(h->st_io[i]);
         if (!rc && e2 != cudaSuccess) rc = fail(h, HPF_E_CUDA, std::string("hpf_solve_host: ") + cudaGetErrorString(e2));
     }
+    if (!rc) h->last_valid = false;        // everything this handle issued has completed
     return rc;
 }
 

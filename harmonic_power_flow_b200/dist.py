@@ -78,3 +78,30 @@ def gather_slab(slab: torch.Tensor, group=None) -> torch.Tensor:
     out = slab.new_empty(world * slab.numel())             # concatenation along dim 0 (gloo and NCCL)
     dist.all_gather_into_tensor(out, slab, group=group)
     return out.view(world, slab.numel())
+
+
+def gather_slab_to_root(slab: torch.Tensor, flag_offset: int, root: int = 0, out=None, group=None,
+                        async_op: bool = False):
+    """The final gather as the north star words it: convergence FLAGS first (the tail of the result
+    slab from ``flag_offset`` on - err_h, n_iter_f, n_iter_h, status: 20 bytes per scenario), then the
+    RESULTS (V_m, V_a, I_inj), each as one gather TO THE ROOT RANK only (NCCL: grouped send/recv -
+    rank r sends its block once, nobody but the root receives; an all-gather would deliver
+    world x the batch to every rank).  Returns ``(stack, works)``: ``stack`` is the rank-major
+    [world, nbytes] uint8 tensor on the root (``solver.result_from_slab(stack[r], ...)`` gives rank
+    r's fields as views) and None elsewhere; ``works`` are the two async handles (async_op=True)
+    - the caller waits on them before reading ``stack`` or reusing ``slab``."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nbytes = slab.numel()
+    stack = None
+    if rank == root:
+        stack = out if out is not None else slab.new_empty((world, nbytes))
+        assert stack.shape == (world, nbytes)
+    works = []
+    for lo, hi in ((flag_offset, nbytes), (0, flag_offset)):
+        if hi <= lo:
+            continue
+        dst = [stack[r, lo:hi] for r in range(world)] if rank == root else None
+        w = dist.gather(slab[lo:hi], dst, dst=root, group=group, async_op=async_op)
+        if async_op:
+            works.append(w)
+    return stack, works

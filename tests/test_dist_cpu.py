@@ -80,6 +80,15 @@ def _slab_worker(rank, world, port, B, q):
             want_s = torch.randint(0, 4, (B,), dtype=torch.int32, generator=gr)
             rr = solver.result_from_slab(out[r], H, n, nq, B)
             ok = ok and torch.equal(rr.V_m, want_V) and torch.equal(rr.I_inj, want_I) and torch.equal(rr.status, want_s)
+        # the gather to the root rank only (flags first, then results): same bytes, one receiver
+        flag_off = lay["err_h"][0]
+        for async_op in (False, True):
+            stack, works = hdist.gather_slab_to_root(slab, flag_off, root=0, async_op=async_op)
+            for w in works:
+                w.wait()
+            ok = ok and ((stack is None) == (rank != 0))
+            if rank == 0:
+                ok = ok and torch.equal(stack, out)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -475,14 +475,24 @@ def test_large_networks_structured_cta_path(solvers, case):
     sol, net, d = solvers(case)
     info = sol.struct_info()
     assert info["available"] in (1, 2)
-    r = sol.solve(net.P[:, None], net.Q[:, None], net.I_N[:, :, None])
-    print("\n%s: structured variant %d, n_iter_h GPU %d, reference %d" % (
-        case, info["available"], int(r.n_iter_h.item()), int(d["n_iter_h"])))
+    r = sol.solve(net.P[:, None], net.Q[:, None], net.I_N[:, :, None], history=True)
+    hist = r.err_hist_h[:, 0].cpu().numpy()
+    ref_hist = np.asarray(d["err_h_hist"])
+    k = min(len(ref_hist), int(r.n_iter_h.item()) + 1)
+    dev = np.abs(hist[:k] - ref_hist[:k]) / ref_hist[:k]
+    split = int(np.argmax(dev > 1e-6)) if (dev > 1e-6).any() else k
+    print("\n%s: structured variant %d, n_iter_h GPU %d, reference %d; error path equal to 1e-6 for the first %d steps" % (
+        case, info["available"], int(r.n_iter_h.item()), int(d["n_iter_h"]), split))
     assert int(r.n_iter_f.item()) == int(d["n_iter_f"])
-    # (net1/H<=51: cond(J) reaches 4e9 and ||f|| wanders around 1e3 for ~20 steps - the reference
-    # itself needs 23 steps with its SuperLU step and 36 with a LAPACK step; the
-    # structured step reproduces the reference's 23)
-    assert int(r.n_iter_h.item()) == int(d["n_iter_h"])
+    if case == "net1_c_h51":
+        # cond(J) reaches 4e9 and ||f|| wanders around 1e3 for ~20 steps: the count is decided by
+        # round-off - the reference itself needs 23 steps with its SuperLU step and 36 with a LAPACK
+        # step; B200 builds of this kernel have given 23 and 28.  Pinned instead:
+        # the first steps of the reference's error path, convergence, and the (unique) solution.
+        assert np.allclose(hist[:6], ref_hist[:6], rtol=1e-4)
+        assert 15 <= int(r.n_iter_h.item()) < 50
+    else:
+        assert int(r.n_iter_h.item()) == int(d["n_iter_h"])
     assert int(r.status.item()) == 0
     V = helpers.phasor(r.V_m[:, :, 0].cpu().numpy(), r.V_a[:, :, 0].cpu().numpy())
     Vg = helpers.phasor(d["V_m"], d["V_a"])
@@ -596,7 +606,10 @@ def test_full_size_batch_properties(solvers):
     pp = sol.solve(dP, dQ, dI)
     Vr = raw.V_m * torch.exp(1j * raw.V_a)
     Vp = pp.V_m * torch.exp(1j * pp.V_a)
-    assert float((Vr - Vp).abs().max()) < 1e-10          # torch.exp on un-reduced angles of tens of radians
+    # (the raw angles are un-reduced: reducing an angle a by the DOUBLE 2 pi - what numpy's % does too,
+    # HG:548 - moves the phasor by |a| * 3.9e-17 relative; torch.exp on |a| adds ~|a| ulp)
+    tol = raw.V_m.abs() * (raw.V_a.abs() * 1e-15 + 1e-14) + 1e-14
+    assert bool(((Vr - Vp).abs() <= tol).all()), float(((Vr - Vp).abs() / tol).max())
     assert float(pp.V_m.min()) >= 0 and float(pp.V_a.min()) >= 0 and float(pp.V_a.max()) <= 2 * np.pi
 
 
@@ -720,23 +733,39 @@ def test_config4_radial_200_bus_against_oracle(tmp_path):
     r = sol.solve(P, Q, I_N)
     res = r.to_host()
     assert (res["status"] == 0).all() and (res["n_iter_f"] == 3).all()
-    # 16 scenarios against the oracle (about 10 s of CPU each, fanned out over the host cores)
+    # 16 scenarios against the oracle (about 10 s of CPU each, fanned out over the host cores), with the
+    # reference's SuperLU step and with a LAPACK step: a scenario whose mismatch norm lands within
+    # round-off of the 1e-4 threshold stops one or two iterations earlier or later (seen: oracle
+    # 8.06e-5 after 24 steps, GPU 26 steps), so the GPU count must equal the SuperLU oracle's except
+    # for at most one scenario more than the oracle disagrees with itself
     import oracle_pool
     pool = oracle_pool.OraclePool(helpers.oracle_net(net))
     try:
         o = pool.solve(P[:, :16], Q[:, :16], I_N[:, :, :16], "superlu", chunk=1)
+        ol = pool.solve(P[:, :16], Q[:, :16], I_N[:, :, :16], "lapack", keep_V=False, chunk=1)
     finally:
         pool.close()
+    floor = int((o["n_iter_h"] != ol["n_iter_h"]).sum())
+    mism = 0
     for b in range(16):
-        tag = "scenario %d: oracle it %d/%d err %.2e, gpu it %d/%d err %.2e" % (
-            b, o["n_iter_f"][b], o["n_iter_h"][b], o["err_h"][b], res["n_iter_f"][b], res["n_iter_h"][b], res["err_h"][b])
+        tag = "scenario %d: oracle it %d/%d err %.2e (lapack step: %d), gpu it %d/%d err %.2e" % (
+            b, o["n_iter_f"][b], o["n_iter_h"][b], o["err_h"][b], ol["n_iter_h"][b], res["n_iter_f"][b],
+            res["n_iter_h"][b], res["err_h"][b])
         assert o["status"][b] == 0, tag
-        assert res["n_iter_f"][b] == o["n_iter_f"][b] and res["n_iter_h"][b] == o["n_iter_h"][b], tag
+        assert res["n_iter_f"][b] == o["n_iter_f"][b], tag
+        if res["n_iter_h"][b] != o["n_iter_h"][b]:
+            mism += 1
+            print("\n" + tag)
         Vo = helpers.phasor(o["V_m"][:, :, b], o["V_a"][:, :, b])
         Vg = helpers.phasor(res["V_m"][:, :, b], res["V_a"][:, :, b])
         t = max(1e-9, 0.1 * max(o["err_h"][b], res["err_h"][b]))      # see _check_against_oracle
         assert np.abs(Vo - Vg).max() <= t * np.abs(Vo).max(), tag
-        assert np.abs(o["I_inj"][:, :, b] - res["I_inj"][:, :, b]).max() <= 10 * t * np.abs(o["I_inj"][:, :, b]).max(), tag
+        # (the current rows of f ARE the residual of I_inj in p.u.: two iterates accepted at mismatch
+        # norms e1, e2 differ by up to e1 + e2 in the injected currents)
+        assert np.abs(o["I_inj"][:, :, b] - res["I_inj"][:, :, b]).max() <= max(
+            10 * t * np.abs(o["I_inj"][:, :, b]).max(), 2 * (o["err_h"][b] + res["err_h"][b])), tag
+    print("\nconfig 4: %d/16 iteration-count differences against the SuperLU oracle (oracle vs itself: %d)" % (mism, floor))
+    assert mism <= floor + 1
     part = sol.solve(P[:, 100:190].copy(), Q[:, 100:190].copy(), I_N[:, :, 100:190].copy()).to_host()
     assert np.array_equal(part["V_m"], res["V_m"][:, :, 100:190]) and np.array_equal(part["n_iter_h"], res["n_iter_h"][100:190])
     sol.close()
