@@ -258,7 +258,6 @@ __device__ __forceinline__ void harm_hw_loop(const HwConsts<D, COUPLED>& C, cons
                 // single accumulator is what the warp would otherwise wait on
                 double2 a0 = make_double2(0.0, 0.0), a1 = a0;
                 const double2* sv = sVnl + (k * H) * T + lane;
-#pragma unroll
                 const double2* yn = FUND ? C.YNk + (k * H + h) * H : cYN + (k * H + h) * H;
 #pragma unroll
                 for (int p = 0; p + 1 < H; p += 2) {

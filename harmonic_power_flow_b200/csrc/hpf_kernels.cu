@@ -18,6 +18,7 @@
 
 #include "../../include/hpf_b200.h"
 #include "hpf_device.cuh"
+#include "hpf_lu_panel.cuh"
 #include "hpf_structured.cuh"
 #include "hpf_lu_blocked.cuh"
 #include "hpf_ne_extract.cuh"
@@ -123,6 +124,7 @@ __global__ void ybus_kernel(int n, int H, int L, const int* __restrict__ harmoni
 // Shared-memory carve-up of one scenario (fused and per-CTA kernels).
 struct ScnSmem {
     double* A;                                 // ld * (N + 1), column-major, odd ld
+    double* lup;                               // work area of the panel LU (hpf_lu_panel.cuh), with the matrix only
     double *Vm, *Va, *Vre, *Vim, *Ere, *Eim;   // nH each
     double2 *I1, *Iinj, *IN;                   // n, q*H, q*H
     double *P, *Q;                             // n each
@@ -136,7 +138,7 @@ __host__ __device__ inline int odd_ld(int N) { return N | 1; }
 __host__ __device__ inline size_t scn_smem_bytes(int n, int H, int q, int N, bool with_matrix) {
     const size_t nH = (size_t)n * H;
     size_t d = 0;
-    if (with_matrix) d += (size_t)odd_ld(N) * (N + 1);
+    if (with_matrix) d += (size_t)odd_ld(N) * (N + 1) + lup_extra_doubles(N);
     d += 6 * nH + 2 * n + 4 * (size_t)q * H + 2 * n + N + 64 + 4;
     return d * sizeof(double) + 16;
 }
@@ -146,7 +148,13 @@ __device__ __forceinline__ ScnSmem carve(double* base, const DevNet& net, bool w
     double* p = base;
     const int nH = net.nH, qH = net.q * net.H;
     s.A = p;
-    if (with_matrix) p += (size_t)odd_ld(net.N) * (net.N + 1);
+    s.lup = nullptr;
+    if (with_matrix) {
+        p += (size_t)odd_ld(net.N) * (net.N + 1);
+        if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) p += 1;
+        s.lup = p;
+        p += lup_extra_doubles(net.N);
+    }
     if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) p += 1;   // double2 alignment
     s.I1 = reinterpret_cast<double2*>(p);   p += 2 * net.n;
     s.Iinj = reinterpret_cast<double2*>(p); p += 2 * qH;
@@ -278,6 +286,7 @@ struct SolveArgs {
     int* work_counter;
     double* workspace;     // GMEM variant: gridDim.x * ld * (N + 1) doubles
     int lub_doubles;       // GMEM variant: shared-memory work area of the blocked LU (doubles)
+    int lu_classic;        // shared-memory LU: 1 = rank-1 updates (lu_solve_smem), 0 = panel-blocked (default)
 };
 
 #define HPF_THREADS_GMEM 512
@@ -297,7 +306,7 @@ static inline size_t gmem_kernel_lub_doubles(int n, int H, int q, int N, size_t 
 // LU: 0 = shared-memory LU (matrix in smem), 1 = blocked LU (matrix in the global workspace or
 // behind the work area), 2 = blocked LU for systems whose panels do not fit the staging buffer
 template <int LU>
-__global__ void __launch_bounds__(LU ? HPF_THREADS_GMEM : HPF_THREADS)
+__global__ void __launch_bounds__(LU ? HPF_THREADS_GMEM : HPF_THREADS, LU ? 1 : 2)
 solve_kernel(const DevNet net, const SolveArgs a) {
     constexpr bool GMEM = LU != 0;
     extern __shared__ __align__(16) double smem[];
@@ -342,7 +351,8 @@ solve_kernel(const DevNet net, const SolveArgs a) {
             __syncthreads();
             cta_fund_jacobian(net, s, s.A, 1, ld);
             const int info = GMEM ? lu_solve_blocked_t<LU == 2>(s.A, Nf, ld, lub, a.lub_doubles, s.flag)
-                                  : lu_solve_smem(s.A, Nf, ld, s.rinv, s.flag);
+                                  : (a.lu_classic ? lu_solve_smem(s.A, Nf, ld, s.rinv, s.flag)
+                                                  : lu_solve_smem_panel(s.A, Nf, ld, s.rinv, s.flag, s.lup));
             if (info) status = HPF_ST_SINGULAR;
             for (int t = tid; t < Nf; t += blockDim.x) {       // HG:226-235
                 const double dx = rhs_f[t];
@@ -382,7 +392,8 @@ solve_kernel(const DevNet net, const SolveArgs a) {
             __syncthreads();
             cta_harmonic_jacobian(net, s, s.A, 1, ld);
             const int info = GMEM ? lu_solve_blocked_t<LU == 2>(s.A, N, ld, lub, a.lub_doubles, s.flag)
-                                  : lu_solve_smem(s.A, N, ld, s.rinv, s.flag);
+                                  : (a.lu_classic ? lu_solve_smem(s.A, N, ld, s.rinv, s.flag)
+                                                  : lu_solve_smem_panel(s.A, N, ld, s.rinv, s.flag, s.lup));
             if (info && status == HPF_ST_CONVERGED) status = HPF_ST_SINGULAR;
             for (int t = tid; t < N; t += blockDim.x) {        // HG:476-485
                 const double dx = rhs[t];
@@ -724,10 +735,11 @@ struct LuArgs {
     long long stride;
     double* workspace;
     int lub_doubles;
+    int lu_classic;
 };
 
 template <int LU>
-__global__ void __launch_bounds__(LU ? HPF_THREADS_GMEM : HPF_THREADS)
+__global__ void __launch_bounds__(LU ? HPF_THREADS_GMEM : HPF_THREADS, LU ? 1 : 2)
 lu_solve_kernel(const DevNet net, const LuArgs a) {
     constexpr bool GMEM = LU != 0;
     extern __shared__ __align__(16) double smem[];
@@ -746,7 +758,8 @@ lu_solve_kernel(const DevNet net, const LuArgs a) {
         double* rhs = s.A + (size_t)N * ld;
         for (int t = threadIdx.x; t < N; t += blockDim.x) rhs[t] = a.f[t * B + b];
         const int info = GMEM ? lu_solve_blocked_t<LU == 2>(s.A, N, ld, lub, a.lub_doubles, s.flag)
-                              : lu_solve_smem(s.A, N, ld, s.rinv, s.flag);
+                              : (a.lu_classic ? lu_solve_smem(s.A, N, ld, s.rinv, s.flag)
+                                              : lu_solve_smem_panel(s.A, N, ld, s.rinv, s.flag, s.lup));
         for (int t = threadIdx.x; t < N; t += blockDim.x) a.dx[t * B + b] = rhs[t];
         if (threadIdx.x == 0) a.info[b] = info;
     }
@@ -1057,6 +1070,7 @@ struct hpf_handle {
     int harm_minb = 1;
     int no_specialise = 0;        // $HPF_NO_SPECIALISE=1: always use the runtime-dimension kernels
     int mismatch_tile = 0;        // $HPF_MISMATCH_TILE=1: standalone mismatch through the tile kernel
+    int lu_classic = 0;           // $HPF_LU_CLASSIC=1: shared-memory LU with rank-1 updates (lu_solve_smem) instead of the panel LU
     int dense_blocked = 0;        // $HPF_DENSE_BLOCKED=1: blocked tensor-core LU also for smem-sized systems
     int force_variant = 0;        // $HPF_STRUCT_VARIANT=2|3: force a per-CTA variant of the harmonic stage
     // host mirror of the network constants for kernels that take them as parameters
@@ -1264,6 +1278,7 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     a.n_iter_f = n_iter_f; a.n_iter_h = n_iter_h; a.status = status; a.err_h = err_h; a.err_f = err_f;
     a.work_counter = h->d_counter + h->cur_slot;
     a.lub_doubles = (int)lubd;
+    a.lu_classic = h->lu_classic;
     CK(cudaMemsetAsync(h->d_counter + h->cur_slot, 0, sizeof(int), st));
     long long grid = (long long)occ * h->sm_count;
     if (grid > B) grid = B;
@@ -1765,6 +1780,7 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_MISMATCH_TILE")) h->mismatch_tile = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_STRUCT_VARIANT")) h->force_variant = atoi(ev);
     if (const char* ev = getenv("HPF_DENSE_BLOCKED")) h->dense_blocked = atoi(ev) ? 1 : 0;
+    if (const char* ev = getenv("HPF_LU_CLASSIC")) h->lu_classic = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_HARM_KERNEL")) h->harm_tile_only = (strcmp(ev, "tile") == 0) ? 1 : 0;
     if (const char* ev = getenv("HPF_HW_EPOCH")) h->hw_epoch = atoi(ev) >= 1 ? atoi(ev) : 1;
     if (const char* ev = getenv("HPF_HW_MINB")) h->hw_minb = (atoi(ev) == 1) ? 1 : 2;
@@ -2355,6 +2371,7 @@ static int lu_solve_impl(hpf_t* h, int B, const double* J, const double* f, doub
                               (ws_smem ? (size_t)lub_ld(net.N) * (net.N + 1) : 0)) * sizeof(double) + 16
                            : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
     a.lub_doubles = (int)lubd;
+    a.lu_classic = h->lu_classic;
     int occ = 0;
     const bool big = gm && lub_needs_big(net.N, lubd);
     rc = !gm ? prep_kernel(h, lu_solve_kernel<0>, smem, "hpf_lu_solve", &occ)
