@@ -22,6 +22,7 @@
 #include "hpf_structured.cuh"
 #include "hpf_lu_blocked.cuh"
 #include "hpf_ne_extract.cuh"
+#include "hpf_zgemm.cuh"
 
 #define HPF_THREADS 256
 #define HPF_TILE 32          // scenarios per CTA in the tile kernels
@@ -1070,6 +1071,7 @@ struct hpf_handle {
     int harm_minb = 1;
     int no_specialise = 0;        // $HPF_NO_SPECIALISE=1: always use the runtime-dimension kernels
     int mismatch_tile = 0;        // $HPF_MISMATCH_TILE=1: standalone mismatch through the tile kernel
+    int wn_kernel = 0;            // $HPF_WN_KERNEL=fma|dmma: generic w_N = W_NL I_N product on the CUDA-core pipe (wn_tile_kernel) or on the FP64 tensor cores (zgemm_dmma_kernel); 0 = default
     int lu_classic = 0;           // $HPF_LU_CLASSIC=1: shared-memory LU with rank-1 updates (lu_solve_smem) instead of the panel LU
     int dense_blocked = 0;        // $HPF_DENSE_BLOCKED=1: blocked tensor-core LU also for smem-sized systems
     int force_variant = 0;        // $HPF_STRUCT_VARIANT=2|3: force a per-CTA variant of the harmonic stage
@@ -1501,6 +1503,27 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     return HPF_OK;
 }
 
+// C [M x N] = A [M x K] B [K x N] (complex, row-major) on the FP64 tensor cores (hpf_zgemm.cuh)
+static int launch_zgemm(hpf_t* h, int M, int N, int K, const double2* A, size_t lda, const double2* B, size_t ldb,
+                        double2* C, size_t ldc, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return HPF_OK;
+    CK(cudaFuncSetAttribute(zgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZG_SMEM_BYTES));
+    const dim3 grid((unsigned)((N + ZG_BN - 1) / ZG_BN), (unsigned)((M + ZG_BM - 1) / ZG_BM));
+    zgemm_dmma_kernel<<<grid, 256, ZG_SMEM_BYTES, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+// The generic Norton contraction w_N = W_NL I_N runs on the tensor cores when the product is large
+// enough to fill the machine with 64 x 64 tiles (measured A/B: profiles/r2_wn_dmma_ab.txt);
+// $HPF_WN_KERNEL=fma|dmma forces either.
+static bool wn_use_dmma(const hpf_t* h, int nZ, int qH, int B) {
+    if (h->wn_kernel) return h->wn_kernel == 2;
+    // (full 64-scenario column tiles only: a single scenario would waste 63 / 64 of every DMMA)
+    return B >= ZG_BN && (long long)((nZ + ZG_BM - 1) / ZG_BM) * ((B + ZG_BN - 1) / ZG_BN) >= h->sm_count && qH >= 64;
+}
+
 static int launch_wn(hpf_t* h, const DevNet& net, const StructNet& sn, int B, const double* I_N,
                      cudaStream_t st) {
     const size_t off = (size_t)h->cur_slot * h->wN_slot_stride;
@@ -1529,6 +1552,10 @@ static int launch_wn(hpf_t* h, const DevNet& net, const StructNet& sn, int B, co
             CK(cudaGetLastError());
             return HPF_OK;
         }
+    }
+    if (wn_use_dmma(h, sn.nZ, qH, B)) {
+        int rcz = launch_zgemm(h, sn.nZ, B, qH, sn.WNL, (size_t)qH, (const double2*)I_N, (size_t)B, wa.wN, (size_t)B, st);
+        return rcz;
     }
     const size_t smem = (size_t)(qH < HPF_WN_UCH ? qH : HPF_WN_UCH) * HPF_T * sizeof(double2) + 16;
     int occ = 0;
@@ -1781,6 +1808,7 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_STRUCT_VARIANT")) h->force_variant = atoi(ev);
     if (const char* ev = getenv("HPF_DENSE_BLOCKED")) h->dense_blocked = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_LU_CLASSIC")) h->lu_classic = atoi(ev) ? 1 : 0;
+    if (const char* ev = getenv("HPF_WN_KERNEL")) h->wn_kernel = (strcmp(ev, "dmma") == 0) ? 2 : (strcmp(ev, "fma") == 0) ? 1 : 0;
     if (const char* ev = getenv("HPF_HARM_KERNEL")) h->harm_tile_only = (strcmp(ev, "tile") == 0) ? 1 : 0;
     if (const char* ev = getenv("HPF_HW_EPOCH")) h->hw_epoch = atoi(ev) >= 1 ? atoi(ev) : 1;
     if (const char* ev = getenv("HPF_HW_MINB")) h->hw_minb = (atoi(ev) == 1) ? 1 : 2;
@@ -2076,6 +2104,27 @@ static int newton_step_impl(hpf_t* h, int B, const double* V_m, const double* V_
 int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a, const double* P,
                     const double* Q, const double* I_N, double* dx, void* stream) {
     return ordered(h, stream, [&] { return newton_step_impl(h, B, V_m, V_a, P, Q, I_N, dx, stream); });
+}
+
+int hpf_norton_wn(hpf_t* h, int B, const double* I_N, double* wN, void* stream) {
+    return ordered(h, stream, [&] {
+        int rc = ready(h, "hpf_norton_wn", true);
+        if (rc) return rc;
+        if (B <= 0) return B == 0 ? HPF_OK : fail(h, HPF_E_INVALID, "hpf_norton_wn: B < 0");
+        if (!wN || (h->q > 0 && !I_N)) return fail(h, HPF_E_INVALID, "hpf_norton_wn: NULL buffer");
+        ENTER_DEVICE(h);
+        rc = ensure_struct(h, (cudaStream_t)stream);
+        if (rc) return rc;
+        if (h->struct_state < 1)
+            return fail(h, HPF_E_UNSUPPORTED, "hpf_norton_wn: structured strategy not available for this network");
+        const DevNet net = devnet(h);
+        const StructNet sn = structnet(h);
+        h->cur_slot = 0; h->wN_slot_stride = 0;
+        rc = launch_wn(h, net, sn, B, I_N, (cudaStream_t)stream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(wN, h->d_wN, (size_t)sn.nZ * B * sizeof(double2), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return HPF_OK;
+    });
 }
 
 int hpf_ne_extract(hpf_t* h, int D, int N, const double* Vf, const double* Vh, const double* I_f,

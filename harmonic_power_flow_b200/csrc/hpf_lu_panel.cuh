@@ -339,7 +339,7 @@ __device__ __forceinline__ int lu_solve_smem_panel(double* A, const int N, const
                                                    int* sflag, double* X) {
     constexpr int NB = HPF_LUP_NB;
     if (N > 128 || blockDim.x < 64) return lu_solve_smem(A, N, ld, rinv, sflag);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, nw = blockDim.x >> 5;
     const size_t half = (size_t)NB * N + 2 * NB;
     if (tid == 0) *sflag = 0;
     __syncthreads();

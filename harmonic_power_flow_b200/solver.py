@@ -340,6 +340,15 @@ class BatchSolver:
                                                      _ptr(I_N), _ptr(dx), self._stream()))
         return dx
 
+    def norton_wn(self, I_N):
+        """w_N = A_ZZ^-1 I_N,Z = W_NL I_N for the batch, complex [nZ, B] (hpf_norton_wn): the Norton
+        contraction of the structured step as one complex GEMM."""
+        I_N = self._dev(I_N, torch.complex128)
+        B = I_N.shape[2]
+        out = self._c128(self.struct_info()["nZ"], B)
+        _lib.check(self._h, self.lib.hpf_norton_wn(self._h, B, _ptr(I_N), _ptr(out), self._stream()))
+        return out
+
     # -- standalone kernels --------------------------------------------------------------
     def mismatch(self, V_m, V_a, P, Q, I_N=None, want_I_inj=False, out=None):
         n = self.net

@@ -55,7 +55,7 @@ typedef struct hpf_handle hpf_t;
 #define HPF_ST_NONFINITE    3   /* NaN/Inf in the mismatch or the state            */
 
 /* ABI version of this header: bumped on any signature change. */
-#define HPF_ABI_VERSION 9
+#define HPF_ABI_VERSION 10
 int hpf_abi_version(void);
 
 /* Lifetime.  `device` is the CUDA ordinal the handle is bound to. */
@@ -224,6 +224,17 @@ int hpf_struct_info(hpf_t* h, int* available, int* nZ, double* pivot_min, double
 int hpf_newton_step(hpf_t* h, int B, const double* V_m, const double* V_a,
                     const double* P, const double* Q, const double* I_N,
                     double* dx, void* stream);
+
+/*
+ * The Norton contraction of the structured step for a whole batch: w_N = A_ZZ^{-1} I_N,Z = W_NL I_N,
+ * complex [nZ, B] (nZ from hpf_struct_info; row z = stacked index s - m).  I_N enters the current
+ * balance additively (current_injections / current_balance, HG:313-323,351-354), so this product is
+ * the per-scenario constant of the harmonic Newton loop.  One complex GEMM [nZ x qH] [qH x B]: on the
+ * FP64 tensor cores (DMMA) when it fills the machine, else on the CUDA-core FP64 pipe
+ * ($HPF_WN_KERNEL=fma|dmma forces either; both kernels are kept for the A/B of the north star).
+ *   in : I_N complex [q, H, B];  out: wN complex [nZ, B]
+ */
+int hpf_norton_wn(hpf_t* h, int B, const double* I_N, double* wN, void* stream);
 
 /*
  * Post-processing after the path - get_THD() (HG:563-572): for every bus and scenario

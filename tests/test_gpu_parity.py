@@ -596,10 +596,17 @@ def test_reference_shaped_api(tmp_path):
     assert list(V.columns) == ["V_m", "V_a"] and V.index.names == ["harmonic", "bus"]
     assert V.loc[(5, 3), "V_m"] == pytest.approx(2.823989096210703e-01, rel=1e-9)
     assert V.loc[(5, 3), "V_a"] == pytest.approx(1.899824023109353, rel=1e-9)
+    assert isinstance(J, hg.LastJacobian) and J._J is None       # assembled on first use only
     assert J.shape == (101, 101) and J.nnz == 1221
     assert _rel(J.toarray(), d["J_last"]) < 1e-6
+    # a second call on the same network reuses the cached GPU handle and gives the same answer
+    n_handles = len(hg._SOLVERS)
+    V2, err_h2, n_iter_h2, _ = hg.hpf(buses, lines, coupled=True)
+    assert len(hg._SOLVERS) == n_handles and n_iter_h2 == n_iter_h and V2.equals(V)
     THD = hg.get_THD(V)
     assert np.abs(THD.to_numpy() - d["THD"]).max() < 1e-8
+    hg.release_solvers()
+    assert not hg._SOLVERS
     hg.configure(H_MAX=51)
 
 
@@ -1100,3 +1107,43 @@ def test_guard_bands_large_network_variant(tmp_path, monkeypatch):
     assert torch.equal(runs[0], runs[1])
     assert (res.to_host()["status"] == 0).all()
     sol.close()
+
+
+@pytest.mark.parametrize("kind,n,variant,B", [("meshed", 70, 3, 200), ("radial", 40, 3, 67), ("net1", 0, 2, 130)])
+def test_norton_contraction_dmma_matches_fma_and_definition(kind, n, variant, B, tmp_path, monkeypatch):
+    """hpf_norton_wn: w_N = W_NL I_N of a whole batch on the FP64 tensor cores (zgemm_dmma_kernel,
+    $HPF_WN_KERNEL=dmma) against the CUDA-core kernel ($HPF_WN_KERNEL=fma) and against the definition
+    A_ZZ w_N = I_N,Z with A = blockdiag Y(h) - scatter(Y_N) built on the host (HG:313-357); ragged
+    sizes (nZ, qH and B are not multiples of the 64 x 64 x 8 tiles)."""
+    from harmonic_power_flow_b200 import BatchSolver, scenarios
+    if kind == "net1":
+        net, _, _ = helpers.packed_from_files("net1", 25, True, tmp_path, julia_schema=True)
+    else:
+        monkeypatch.setenv("HPF_STRUCT_VARIANT", str(variant))
+        net, _ = helpers.synthetic_packed(kind, tmp_path, h_max=25, n=n, load_scale=0.02)
+    _, _, I_N = scenarios.make_batch(net, B, "wide")
+    out = {}
+    for kern in ("fma", "dmma"):
+        monkeypatch.setenv("HPF_WN_KERNEL", kern)
+        sol = BatchSolver(net)
+        assert sol.struct_info()["available"] == variant
+        out[kern] = sol.norton_wn(I_N).cpu().numpy()
+        Y = sol.Y.cpu().numpy()
+        sol.close()
+    scale = np.abs(out["fma"]).max()
+    assert np.abs(out["dmma"] - out["fma"]).max() <= 1e-13 * scale
+    # definition: A_ZZ w = I_N,Z
+    nn, m, H, q = net.n, net.m, net.H, net.q
+    A = np.zeros((nn * H, nn * H), dtype=complex)
+    for h in range(H):
+        A[h * nn:(h + 1) * nn, h * nn:(h + 1) * nn] = Y[h]
+    YN = net.Y_N[net.dev_of_nl_bus]                              # [q, H, H]
+    for k in range(q):
+        idx = np.arange(H) * nn + m + k
+        A[np.ix_(idx, idx)] -= YN[k]
+    Azz = A[m:, m:]
+    rhs = np.zeros((nn * H - m, B), dtype=complex)
+    for k in range(q):
+        rhs[np.arange(H) * nn + k, :] = I_N[k]                    # row z = s - m = h n + k
+    res = Azz @ out["dmma"] - rhs
+    assert np.abs(res).max() <= 1e-9 * np.abs(rhs).max()
