@@ -1071,6 +1071,7 @@ struct hpf_handle {
     int harm_minb = 1;
     int no_specialise = 0;        // $HPF_NO_SPECIALISE=1: always use the runtime-dimension kernels
     int mismatch_tile = 0;        // $HPF_MISMATCH_TILE=1: standalone mismatch through the tile kernel
+    int setup_gj = 0;             // $HPF_SETUP=gj: variant 3 set-up by Gauss-Jordan inversion of the whole A_ZZ (round-1 path) instead of the Woodbury form
     int wn_kernel = 0;            // $HPF_WN_KERNEL=fma|dmma: generic w_N = W_NL I_N product on the CUDA-core pipe (wn_tile_kernel) or on the FP64 tensor cores (zgemm_dmma_kernel); 0 = default
     int lu_classic = 0;           // $HPF_LU_CLASSIC=1: shared-memory LU with rank-1 updates (lu_solve_smem) instead of the panel LU
     int dense_blocked = 0;        // $HPF_DENSE_BLOCKED=1: blocked tensor-core LU also for smem-sized systems
@@ -1323,6 +1324,110 @@ static StructNet structnet(const hpf_t* h) {
 }
 
 static int host_consts(hpf_t* h);
+static int launch_zgemm(hpf_t* h, int M, int N, int K, const double2* A, size_t lda, const double2* B, size_t ldb,
+                        double2* C, size_t ldc, cudaStream_t st);
+
+// In-place complex Gauss-Jordan inverse with partial pivoting of one matrix of order nn (row-major):
+// one CTA for nn <= 768, else four small launches per pivot over the whole GPU.  info[0] = 0 or
+// k + 1 (zero pivot), pr[0..1] = min / max pivot modulus.  ipiv: nn ints, tmp: 2 nn + 1 double2.
+static int gj_invert(hpf_t* h, double2* A, int nn, int* ipiv, int* info, double* pr, double2* tmp, cudaStream_t st) {
+    if (nn <= 768) {
+        cinv_gj_kernel<<<1, 1024, 0, st>>>(nn, A, ipiv, info, pr);
+        h->launches++;
+    } else {
+        double2 *rowk = tmp, *colk = tmp + nn, *pinv = tmp + 2 * (size_t)nn;
+        const int g1 = (nn + 255) / 256;
+        int gy = (h->sm_count * 8 + g1 - 1) / g1;
+        if (gy > nn) gy = nn;
+        for (int k = 0; k < nn; ++k) {
+            gjm_pivot_kernel<<<1, 1024, 0, st>>>(nn, k, A, ipiv, info, pr, pinv);
+            gjm_row_kernel<<<g1, 256, 0, st>>>(nn, k, A, ipiv, pinv, rowk);
+            gjm_col_kernel<<<g1, 256, 0, st>>>(nn, k, A, colk);
+            gjm_elim_kernel<<<dim3(g1, gy), 256, 0, st>>>(nn, k, A, rowk, colk);
+        }
+        gjm_unpermute_kernel<<<g1, 256, 0, st>>>(nn, A, ipiv);
+        h->launches += 4LL * nn + 1;
+    }
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+// Structured set-up of the large networks through the block structure of A_ZZ (Woodbury identity,
+// see hpf_structured.cuh): fills d_WNL, d_Gz, d_GzT; *info_out = 0 or a zero-pivot indicator,
+// prh = min / max pivot modulus over all inversions.
+static int setup_woodbury(hpf_t* h, const DevNet& net, cudaStream_t st, int* info_out, double* prh) {
+    const int n = net.n, m = net.m, q = net.q, H = net.H, qH = q * H, nZ = net.nH - m;
+    const size_t nblk = (size_t)q * q + (size_t)(H - 1) * n * n;
+    const int nmax = n > qH ? n : qH;
+    double2 *Dinv = nullptr, *Mx = nullptr, *T = nullptr, *U = nullptr, *tmp = nullptr;
+    int *ipiv = nullptr, *info = nullptr;
+    double* pr = nullptr;
+    auto cleanup = [&] { cudaFree(Dinv); cudaFree(Mx); cudaFree(T); cudaFree(U); cudaFree(tmp); cudaFree(ipiv); cudaFree(info); cudaFree(pr); };
+#define WB(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            cleanup();                                                                            \
+            return fail(h, HPF_E_CUDA, std::string("structured setup: " #call ": ") + cudaGetErrorString(e_)); \
+        }                                                                                         \
+    } while (0)
+    WB(cudaMalloc((void**)&Dinv, (nblk + 1) * sizeof(double2)));
+    WB(cudaMalloc((void**)&Mx, ((size_t)qH * qH + 1) * sizeof(double2)));
+    WB(cudaMalloc((void**)&T, ((size_t)q * m + 1) * sizeof(double2)));
+    WB(cudaMalloc((void**)&U, ((size_t)qH * m + 1) * sizeof(double2)));
+    WB(cudaMalloc((void**)&tmp, ((size_t)2 * nmax + 1) * sizeof(double2)));
+    WB(cudaMalloc((void**)&ipiv, (size_t)(nmax + 2) * sizeof(int)));
+    WB(cudaMalloc((void**)&info, (size_t)(H + 1) * sizeof(int)));
+    WB(cudaMalloc((void**)&pr, (size_t)2 * (H + 1) * sizeof(double)));
+    wb_blocks_kernel<<<h->sm_count * 8, 256, 0, st>>>(net, Dinv);
+    h->launches++;
+    int rc = HPF_OK;
+    for (int hh = 0; hh < H && !rc; ++hh) {
+        double2* blk = hh == 0 ? Dinv : Dinv + (size_t)q * q + (size_t)(hh - 1) * n * n;
+        rc = gj_invert(h, blk, hh == 0 ? q : n, ipiv, info + hh, pr + 2 * hh, tmp, st);
+    }
+    if (!rc) {
+        wb_capacitance_kernel<<<h->sm_count * 8, 256, 0, st>>>(net, Dinv, Mx);
+        h->launches++;
+        rc = gj_invert(h, Mx, qH, ipiv, info + H, pr + 2 * H, tmp, st);
+    }
+    // W_NL = (D^-1 E) M^-1, one GEMM per harmonic block: rows of block h x the rows (k, h) of M^-1
+    for (int hh = 0; hh < H && !rc; ++hh) {
+        const double2* blk = hh == 0 ? Dinv : Dinv + (size_t)q * q + (size_t)(hh - 1) * n * n;
+        const int rows = hh == 0 ? q : n;
+        const double2* Ablk = hh == 0 ? blk : blk + m;               // columns of the nonlinear buses
+        const size_t z0 = hh == 0 ? 0 : (size_t)hh * n - m;
+        rc = launch_zgemm(h, rows, qH, q, Ablk, (size_t)rows, Mx + (size_t)hh * qH, (size_t)H * qH,
+                          h->d_WNL + z0 * qH, (size_t)qH, st);
+    }
+    // T = D_0^-1 Y_0[nl, lin];  U = YN E^T D^-1 A_ZF;  G = W_NL U + [T; 0]
+    if (!rc) rc = launch_zgemm(h, q, m, q, Dinv, (size_t)q, net.Y + (size_t)m * n, (size_t)n, T, (size_t)m, st);
+    if (!rc) {
+        wb_coupling_rhs_kernel<<<h->sm_count * 4, 256, 0, st>>>(net, T, U);
+        h->launches++;
+        rc = launch_zgemm(h, nZ, m, qH, h->d_WNL, (size_t)qH, U, (size_t)m, h->d_Gz, (size_t)m, st);
+    }
+    if (!rc) {
+        wb_finish_G_kernel<<<h->sm_count * 8, 256, 0, st>>>(nZ, m, q, T, h->d_Gz, h->d_GzT);
+        h->launches++;
+    }
+    if (rc) { cleanup(); return rc; }
+    std::vector<int> hinfo((size_t)H + 1);
+    std::vector<double> hpr((size_t)2 * (H + 1));
+    WB(cudaMemcpyAsync(hinfo.data(), info, hinfo.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    WB(cudaMemcpyAsync(hpr.data(), pr, hpr.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    WB(cudaStreamSynchronize(st));
+#undef WB
+    cleanup();
+    *info_out = 0;
+    prh[0] = 1.0e308; prh[1] = 0.0;
+    for (int t = 0; t <= H; ++t) {
+        if (hinfo[(size_t)t] != 0 && *info_out == 0) *info_out = hinfo[(size_t)t];
+        prh[0] = hpr[(size_t)2 * t] < prh[0] ? hpr[(size_t)2 * t] : prh[0];
+        prh[1] = hpr[(size_t)2 * t + 1] > prh[1] ? hpr[(size_t)2 * t + 1] : prh[1];
+    }
+    return HPF_OK;
+}
 
 // Constants of the one-warp-per-harmonic kernel (hpf_harmonic_warp.cuh) for a shape-specialised
 // network, from the host mirrors of Y(h), Y_N and G: kept in the handle, passed BY VALUE at launch.
@@ -1439,9 +1544,20 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
         }
     }
     CK(cudaMalloc((void**)&h->d_WNL, ((size_t)nZ * qH + 1) * sizeof(double2)));
-    CK(cudaMalloc((void**)&h->d_Ainv, (size_t)nZ * nZ * sizeof(double2)));
     CK(cudaMalloc((void**)&h->d_Gz, (size_t)nZ * net.m * sizeof(double2)));
     CK(cudaMalloc((void**)&h->d_GzT, (size_t)nZ * net.m * sizeof(double2)));
+    if (variant == 3 && qH > 0 && !h->setup_gj) {
+        // large networks: the operator inverse through its block structure (Woodbury) - no nZ x nZ inverse
+        int winfo = -1;
+        double wpr[2] = {0.0, 0.0};
+        int rcw = setup_woodbury(h, net, st, &winfo, wpr);
+        if (rcw) return rcw;
+        h->hWNL.clear(); h->hG.clear(); h->hw_shape = 0;
+        h->pivot_min = wpr[0]; h->pivot_max = wpr[1];
+        if (winfo == 0 && wpr[0] > 0.0 && wpr[1] / wpr[0] < 1e12) h->struct_state = variant;
+        return HPF_OK;
+    }
+    CK(cudaMalloc((void**)&h->d_Ainv, (size_t)nZ * nZ * sizeof(double2)));
     CK(cudaMalloc((void**)&AZF, (size_t)nZ * net.m * sizeof(double2)));
     CK(cudaMalloc((void**)&ipiv, (size_t)(nZ + 2) * sizeof(int)));
     CK(cudaMalloc((void**)&pr, 2 * sizeof(double)));
@@ -1515,13 +1631,15 @@ static int launch_zgemm(hpf_t* h, int M, int N, int K, const double2* A, size_t 
     return HPF_OK;
 }
 
-// The generic Norton contraction w_N = W_NL I_N runs on the tensor cores when the product is large
-// enough to fill the machine with 64 x 64 tiles (measured A/B: profiles/r2_wn_dmma_ab.txt);
-// $HPF_WN_KERNEL=fma|dmma forces either.
+// The generic Norton contraction w_N = W_NL I_N runs on the tensor cores for batches of at least one
+// full 64-scenario column tile (measured A/B: profiles/r2_wn_dmma_ab.txt: 5-10x the CUDA-core kernel);
+// smaller batches - a single scenario would waste 63 / 64 of every DMMA - keep the CUDA-core kernel.
+// The choice depends on nothing but B >= 64, and neither kernel's arithmetic depends on the position
+// of a scenario in the batch: results are bit-identical for every split of a batch into parts of at
+// least 64 scenarios (e.g. over GPUs).  $HPF_WN_KERNEL=fma|dmma forces either.
 static bool wn_use_dmma(const hpf_t* h, int nZ, int qH, int B) {
     if (h->wn_kernel) return h->wn_kernel == 2;
-    // (full 64-scenario column tiles only: a single scenario would waste 63 / 64 of every DMMA)
-    return B >= ZG_BN && (long long)((nZ + ZG_BM - 1) / ZG_BM) * ((B + ZG_BN - 1) / ZG_BN) >= h->sm_count && qH >= 64;
+    return B >= ZG_BN && nZ >= ZG_BM && qH >= 64;
 }
 
 static int launch_wn(hpf_t* h, const DevNet& net, const StructNet& sn, int B, const double* I_N,
@@ -1808,6 +1926,7 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_STRUCT_VARIANT")) h->force_variant = atoi(ev);
     if (const char* ev = getenv("HPF_DENSE_BLOCKED")) h->dense_blocked = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_LU_CLASSIC")) h->lu_classic = atoi(ev) ? 1 : 0;
+    if (const char* ev = getenv("HPF_SETUP")) h->setup_gj = (strcmp(ev, "gj") == 0) ? 1 : 0;
     if (const char* ev = getenv("HPF_WN_KERNEL")) h->wn_kernel = (strcmp(ev, "dmma") == 0) ? 2 : (strcmp(ev, "fma") == 0) ? 1 : 0;
     if (const char* ev = getenv("HPF_HARM_KERNEL")) h->harm_tile_only = (strcmp(ev, "tile") == 0) ? 1 : 0;
     if (const char* ev = getenv("HPF_HW_EPOCH")) h->hw_epoch = atoi(ev) >= 1 ? atoi(ev) : 1;

@@ -279,6 +279,90 @@ __global__ void struct_G_kernel(int nZ, int m, int kmax, const double2* __restri
 }
 
 // ---------------------------------------------------------------------------------------
+// setup for large networks (variant 3): the operator inverse through its STRUCTURE instead of a
+// Gauss-Jordan inversion of the whole A_ZZ (order nZ = 12,400 for the 1000-bus configuration:
+// 8 nZ^3 = 1.5e13 flop and one HBM pass over 2.5 GB per pivot - 13 s).  With
+//     A_ZZ = D - E YN E^T,   D = blockdiag(Y_0[nl, nl], Y_1, ..., Y_{H-1}),
+//     E = the nZ x qH selection of the (harmonic, nonlinear bus) rows,  YN = the Norton admittances
+//     (block diagonal per bus, HG:313-323),
+// the Woodbury identity gives, with S = E^T D^-1 E (block diagonal per harmonic) and the
+// qH x qH "capacitance" matrix M = I - YN S:
+//     W_NL = A_ZZ^-1 E    = (D^-1 E) M^-1
+//     G    = A_ZZ^-1 A_ZF = D^-1 A_ZF + W_NL (YN E^T D^-1 A_ZF),
+// i.e. H block inversions of order <= n, ONE inversion of order qH and three families of complex
+// GEMMs on the FP64 tensor cores (hpf_zgemm.cuh): ~1.7e12 flop instead of 1.5e13.
+// Column index u = k H + h of W_NL / M  <->  nonlinear bus m + k at harmonic h.
+
+// block h of D into its slot of Dinv (to be inverted in place): block 0 = Y_0[nl, nl] (q x q), else Y_h
+__global__ void wb_blocks_kernel(const DevNet net, double2* __restrict__ Dinv) {
+    const int n = net.n, m = net.m, q = net.q, H = net.H;
+    const size_t total = (size_t)q * q + (size_t)(H - 1) * n * n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        double2 v;
+        int h, i, j;
+        if (t < (size_t)q * q) {
+            h = 0; i = m + (int)(t / q); j = m + (int)(t % q);
+        } else {
+            const size_t r = t - (size_t)q * q;
+            h = 1 + (int)(r / ((size_t)n * n));
+            const size_t e = r % ((size_t)n * n);
+            i = (int)(e / n); j = (int)(e % n);
+        }
+        v = net.Y[((size_t)h * n + i) * n + j];
+        // uncoupled Norton equivalents sit on the diagonal of their own harmonic block
+        if (!net.coupled && i >= m && i == j) v = csub(v, net.YN[(size_t)net.dev_of_nl[i - m] * H + h]);
+        Dinv[t] = v;
+    }
+}
+
+__device__ __forceinline__ const double2* wb_block(const double2* Dinv, int h, int n, int q) {
+    return h == 0 ? Dinv : Dinv + (size_t)q * q + (size_t)(h - 1) * n * n;
+}
+
+// M = I - YN S :  M[(k,h)][(k',p)] = delta - YN_k[h][p] * (D_p^-1)[nl k][nl k']   (coupled; uncoupled: M = I)
+__global__ void wb_capacitance_kernel(const DevNet net, const double2* __restrict__ Dinv, double2* __restrict__ Mx) {
+    const int n = net.n, m = net.m, q = net.q, H = net.H, qH = q * H;
+    const size_t total = (size_t)qH * qH;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int u = (int)(t / qH), v = (int)(t % qH);
+        const int k = u / H, h = u % H, k2 = v / H, p = v % H;
+        double2 val = make_double2(u == v ? 1.0 : 0.0, 0.0);
+        if (net.coupled) {
+            const double2 yn = net.YN[((size_t)net.dev_of_nl[k] * H + h) * H + p];
+            const double2* Dp = wb_block(Dinv, p, n, q);
+            const double2 sp = (p == 0) ? Dp[(size_t)k * q + k2] : Dp[(size_t)(m + k) * n + m + k2];
+            val = csub(val, cmul(yn, sp));
+        }
+        Mx[t] = val;
+    }
+}
+
+// U [qH x m] = YN E^T D^-1 A_ZF :  U[(k,h)][j] = YN_k[h][0] T[k][j],  T = D_0^-1 Y_0[nl, lin]
+__global__ void wb_coupling_rhs_kernel(const DevNet net, const double2* __restrict__ T, double2* __restrict__ U) {
+    const int m = net.m, q = net.q, H = net.H;
+    const size_t total = (size_t)q * H * m;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int u = (int)(t / m), j = (int)(t % m), k = u / H, h = u % H;
+        double2 v = make_double2(0.0, 0.0);
+        if (net.coupled) v = cmul(net.YN[((size_t)net.dev_of_nl[k] * H + h) * H + 0], T[(size_t)k * m + j]);
+        U[t] = v;
+    }
+}
+
+// G += [T; 0] (the D^-1 A_ZF term lives in the first q rows) and GT = G^T
+__global__ void wb_finish_G_kernel(int nZ, int m, int q, const double2* __restrict__ T, double2* __restrict__ G,
+                                   double2* __restrict__ GT) {
+    const size_t total = (size_t)nZ * m;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t / m), j = (int)(t % m);
+        double2 g = G[t];
+        if (r < q) g = cadd(g, T[(size_t)r * m + j]);
+        G[t] = g;
+        GT[(size_t)j * nZ + r] = g;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Per-lane dense solve of a small augmented real system M [nx][nx+1] stored with stride
 // HPF_T (element (r, c) of lane l at M[(r*(nx+1)+c)*HPF_T + l] -> bank = lane, conflict
 // free).  Gaussian elimination with partial pivoting, each lane pivots on its own data.

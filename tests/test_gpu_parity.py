@@ -1147,3 +1147,37 @@ def test_norton_contraction_dmma_matches_fma_and_definition(kind, n, variant, B,
         rhs[np.arange(H) * nn + k, :] = I_N[k]                    # row z = s - m = h n + k
     res = Azz @ out["dmma"] - rhs
     assert np.abs(res).max() <= 1e-9 * np.abs(rhs).max()
+
+
+@pytest.mark.parametrize("kind,n,coupled", [("meshed", 70, True), ("radial", 40, True), ("meshed", 30, False)])
+def test_woodbury_setup_matches_gauss_jordan_setup(kind, n, coupled, tmp_path, monkeypatch):
+    """Large-network set-up (variant 3): the operators W_NL = A_ZZ^-1 E and G = A_ZZ^-1 A_ZF built
+    through the block structure of A_ZZ (Woodbury identity: H block inversions, one inversion of
+    order qH, complex GEMMs on the tensor cores) against the round-1 path (Gauss-Jordan inversion
+    of the whole A_ZZ, $HPF_SETUP=gj): same w_N, same Newton step, same solve."""
+    from harmonic_power_flow_b200 import BatchSolver, scenarios
+    monkeypatch.setenv("HPF_STRUCT_VARIANT", "3")
+    net, _ = helpers.synthetic_packed(kind, tmp_path, h_max=25, coupled=coupled, n=n, load_scale=0.02)
+    B = 24
+    P, Q, I_N = scenarios.make_batch(net, B, "tight")
+    out = {}
+    for setup in ("gj", "woodbury"):
+        monkeypatch.setenv("HPF_SETUP", setup)
+        sol = BatchSolver(net)
+        info = sol.struct_info()
+        assert info["available"] == 3 and info["pivot_min"] > 0
+        if setup == "gj":                                      # ONE iterate for both (early iterations amplify round-off)
+            raw = sol.solve(P, Q, I_N, raw=True, max_iter_h=2)
+            Vm0, Va0 = raw.V_m.cpu().numpy(), raw.V_a.cpu().numpy()
+        out[setup] = dict(wn=sol.norton_wn(I_N).cpu().numpy(),
+                          dx=sol.newton_step(Vm0, Va0, P, Q, I_N).cpu().numpy(),
+                          res=sol.solve(P, Q, I_N).to_host())
+        sol.close()
+    a, b = out["gj"], out["woodbury"]
+    assert np.abs(a["wn"] - b["wn"]).max() <= 1e-11 * np.abs(a["wn"]).max()
+    assert np.abs(a["dx"] - b["dx"]).max() <= 1e-9 * np.abs(a["dx"]).max()
+    assert (b["res"]["status"] == 0).all()
+    same = a["res"]["n_iter_h"] == b["res"]["n_iter_h"]
+    assert same.mean() >= 0.75                                 # (round-off-decided counts, DESIGN.md section 4)
+    Va, Vb = helpers.phasor(a["res"]["V_m"], a["res"]["V_a"]), helpers.phasor(b["res"]["V_m"], b["res"]["V_a"])
+    assert np.abs(Va - Vb)[..., same].max() <= 1e-7
