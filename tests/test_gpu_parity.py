@@ -1180,4 +1180,6 @@ def test_woodbury_setup_matches_gauss_jordan_setup(kind, n, coupled, tmp_path, m
     same = a["res"]["n_iter_h"] == b["res"]["n_iter_h"]
     assert same.mean() >= 0.75                                 # (round-off-decided counts)
     Va, Vb = helpers.phasor(a["res"]["V_m"], a["res"]["V_a"]), helpers.phasor(b["res"]["V_m"], b["res"]["V_a"])
-    assert np.abs(Va - Vb)[..., same].max() <= 1e-7
+    # (an iterate accepted at mismatch norm e is ~e away from the solution)
+    tol = np.maximum(a["res"]["err_h"], b["res"]["err_h"])[same]
+    assert (np.abs(Va - Vb)[..., same].reshape(-1, same.sum()).max(0) <= np.maximum(1e-9, tol)).all()
