@@ -482,7 +482,19 @@ def run_ours(a):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = None
     if world > 1:
+        # one process per GPU: run on the CPUs next to this GPU, so that the pinned host buffers (first
+        # touch) and the copy threads live on the GPU's own NUMA node / PCIe root
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+            pynvml.nvmlDeviceSetCpuAffinity(hnd)
+            affinity = sorted(os.sched_getaffinity(0))
+            affinity = "%d CPUs: %d..%d" % (len(affinity), affinity[0], affinity[-1])
+        except Exception as e:                                   # not fatal: the numbers just stand as they are
+            affinity = "not set (%s)" % type(e).__name__
         dist.init_process_group("nccl", device_id=dev)
     if a.gpus != world:
         a.gpus = world
@@ -757,6 +769,7 @@ def run_ours(a):
                 "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_max / a.steps * 1e3,
                         "host_buffers": "pinned (torch pin_memory); pageable numpy buffers through the same call: see pageable",
+                        "cpu_affinity_rank0": affinity,
                         "path": ("BatchSolver.solve_host -> hpf_solve_host (C ABI, host buffers)" if world == 1 else
                                  "per rank: BatchSolver.solve_host(keep=slab) -> hpf_solve_host_keep (C ABI, host buffers: "
                                  "chunk-pipelined H2D / solve / D2H of the rank's own results to its own host buffers, "

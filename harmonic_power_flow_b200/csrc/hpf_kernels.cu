@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -1071,6 +1072,8 @@ struct hpf_handle {
     int harm_minb = 1;
     int no_specialise = 0;        // $HPF_NO_SPECIALISE=1: always use the runtime-dimension kernels
     int mismatch_tile = 0;        // $HPF_MISMATCH_TILE=1: standalone mismatch through the tile kernel
+    int gj_single_max = 768;      // $HPF_GJ_SINGLE_MAX: largest order inverted by the one-CTA Gauss-Jordan kernel (tests: 0 forces the multi-CTA paths)
+    int gj_unblocked = 0;         // $HPF_GJ_UNBLOCKED=1: multi-CTA Gauss-Jordan with one rank-1 update of the whole matrix per pivot (round-1 kernel) instead of the blocked one
     int setup_gj = 0;             // $HPF_SETUP=gj: variant 3 set-up by Gauss-Jordan inversion of the whole A_ZZ (round-1 path) instead of the Woodbury form
     int wn_kernel = 0;            // $HPF_WN_KERNEL=fma|dmma: generic w_N = W_NL I_N product on the CUDA-core pipe (wn_tile_kernel) or on the FP64 tensor cores (zgemm_dmma_kernel); 0 = default
     int lu_classic = 0;           // $HPF_LU_CLASSIC=1: shared-memory LU with rank-1 updates (lu_solve_smem) instead of the panel LU
@@ -1325,14 +1328,35 @@ static StructNet structnet(const hpf_t* h) {
 
 static int host_consts(hpf_t* h);
 static int launch_zgemm(hpf_t* h, int M, int N, int K, const double2* A, size_t lda, const double2* B, size_t ldb,
-                        double2* C, size_t ldc, cudaStream_t st);
+                        double2* C, size_t ldc, cudaStream_t st, bool subtract = false);
 
 // In-place complex Gauss-Jordan inverse with partial pivoting of one matrix of order nn (row-major):
 // one CTA for nn <= 768, else four small launches per pivot over the whole GPU.  info[0] = 0 or
 // k + 1 (zero pivot), pr[0..1] = min / max pivot modulus.  ipiv: nn ints, tmp: 2 nn + 1 double2.
-static int gj_invert(hpf_t* h, double2* A, int nn, int* ipiv, int* info, double* pr, double2* tmp, cudaStream_t st) {
-    if (nn <= 768) {
+static int gj_invert(hpf_t* h, double2* A, int nn, int* ipiv, int* info, double* pr, double2* tmp, cudaStream_t st,
+                     double2* FR = nullptr) {
+    if (nn <= h->gj_single_max) {
         cinv_gj_kernel<<<1, 1024, 0, st>>>(nn, A, ipiv, info, pr);
+        h->launches++;
+    } else if (FR && !h->gj_unblocked) {
+        // blocked: panels of GJB_NB pivots, the rest of the matrix updated by one tensor-core GEMM per panel
+        double2 *rowk = tmp, *pinv = tmp + 2 * (size_t)nn;
+        double2 *F = FR, *R = FR + (size_t)nn * GJB_NB, *pinv_all = R + (size_t)GJB_NB * nn;
+        const int g1 = (nn + 255) / 256;
+        for (int j0 = 0; j0 < nn; j0 += GJB_NB) {
+            const int nb = nn - j0 < GJB_NB ? nn - j0 : GJB_NB, j1 = j0 + nb;
+            int ge = (nn + 3) / 4;
+            if (ge > h->sm_count * 8) ge = h->sm_count * 8;
+            for (int k = j0; k < j1; ++k) {
+                gjb_pivot_row_kernel<<<1, 1024, 0, st>>>(nn, k, j0, j1, A, ipiv, info, pr, pinv, rowk, F, pinv_all);
+                gjb_col_elim_kernel<<<ge, dim3(GJB_NB, 4), 0, st>>>(nn, k, j0, j1, A, rowk, pinv, F);
+            }
+            gjb_rows_kernel<<<g1, 256, 0, st>>>(nn, j0, nb, A, ipiv, F, pinv_all, R);
+            h->launches += 2LL * nb + 1;
+            int rc = launch_zgemm(h, nn, nn, nb, F, (size_t)GJB_NB, R, (size_t)nn, A, (size_t)nn, st, true);
+            if (rc) return rc;
+        }
+        gjm_unpermute_kernel<<<g1, 256, 0, st>>>(nn, A, ipiv);
         h->launches++;
     } else {
         double2 *rowk = tmp, *colk = tmp + nn, *pinv = tmp + 2 * (size_t)nn;
@@ -1359,10 +1383,14 @@ static int setup_woodbury(hpf_t* h, const DevNet& net, cudaStream_t st, int* inf
     const int n = net.n, m = net.m, q = net.q, H = net.H, qH = q * H, nZ = net.nH - m;
     const size_t nblk = (size_t)q * q + (size_t)(H - 1) * n * n;
     const int nmax = n > qH ? n : qH;
-    double2 *Dinv = nullptr, *Mx = nullptr, *T = nullptr, *U = nullptr, *tmp = nullptr;
+    double2 *Dinv = nullptr, *Mx = nullptr, *T = nullptr, *U = nullptr, *tmp = nullptr, *FR = nullptr;
     int *ipiv = nullptr, *info = nullptr;
     double* pr = nullptr;
-    auto cleanup = [&] { cudaFree(Dinv); cudaFree(Mx); cudaFree(T); cudaFree(U); cudaFree(tmp); cudaFree(ipiv); cudaFree(info); cudaFree(pr); };
+    // (stream-ordered allocations: a plain cudaFree of these ~1.7 GB of temporaries costs 160 ms)
+    auto cleanup = [&] {
+        cudaFreeAsync(Dinv, st); cudaFreeAsync(Mx, st); cudaFreeAsync(T, st); cudaFreeAsync(U, st); cudaFreeAsync(tmp, st);
+        cudaFreeAsync(FR, st); cudaFreeAsync(ipiv, st); cudaFreeAsync(info, st); cudaFreeAsync(pr, st);
+    };
 #define WB(call)                                                                                  \
     do {                                                                                          \
         cudaError_t e_ = (call);                                                                  \
@@ -1371,26 +1399,40 @@ static int setup_woodbury(hpf_t* h, const DevNet& net, cudaStream_t st, int* inf
             return fail(h, HPF_E_CUDA, std::string("structured setup: " #call ": ") + cudaGetErrorString(e_)); \
         }                                                                                         \
     } while (0)
-    WB(cudaMalloc((void**)&Dinv, (nblk + 1) * sizeof(double2)));
-    WB(cudaMalloc((void**)&Mx, ((size_t)qH * qH + 1) * sizeof(double2)));
-    WB(cudaMalloc((void**)&T, ((size_t)q * m + 1) * sizeof(double2)));
-    WB(cudaMalloc((void**)&U, ((size_t)qH * m + 1) * sizeof(double2)));
-    WB(cudaMalloc((void**)&tmp, ((size_t)2 * nmax + 1) * sizeof(double2)));
-    WB(cudaMalloc((void**)&ipiv, (size_t)(nmax + 2) * sizeof(int)));
-    WB(cudaMalloc((void**)&info, (size_t)(H + 1) * sizeof(int)));
-    WB(cudaMalloc((void**)&pr, (size_t)2 * (H + 1) * sizeof(double)));
+    const bool timing = getenv("HPF_SETUP_TIMING") != nullptr;       // phase times on stderr (synchronises)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto tprev = now();
+    auto tick = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        const auto t = now();
+        fprintf(stderr, "[hpf setup] %-34s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - tprev).count());
+        tprev = t;
+    };
+    WB(cudaMallocAsync((void**)&Dinv, (nblk + 1) * sizeof(double2), st));
+    WB(cudaMallocAsync((void**)&Mx, ((size_t)qH * qH + 1) * sizeof(double2), st));
+    WB(cudaMallocAsync((void**)&T, ((size_t)q * m + 1) * sizeof(double2), st));
+    WB(cudaMallocAsync((void**)&U, ((size_t)qH * m + 1) * sizeof(double2), st));
+    WB(cudaMallocAsync((void**)&tmp, ((size_t)2 * nmax + 1) * sizeof(double2), st));
+    WB(cudaMallocAsync((void**)&FR, ((size_t)2 * nmax * GJB_NB + GJB_NB + 1) * sizeof(double2), st));      // F, R, 1 / pivots
+    WB(cudaMallocAsync((void**)&ipiv, (size_t)(nmax + 2) * sizeof(int), st));
+    WB(cudaMallocAsync((void**)&info, (size_t)(H + 1) * sizeof(int), st));
+    WB(cudaMallocAsync((void**)&pr, (size_t)2 * (H + 1) * sizeof(double), st));
+    tick("allocations");
     wb_blocks_kernel<<<h->sm_count * 8, 256, 0, st>>>(net, Dinv);
     h->launches++;
     int rc = HPF_OK;
     for (int hh = 0; hh < H && !rc; ++hh) {
         double2* blk = hh == 0 ? Dinv : Dinv + (size_t)q * q + (size_t)(hh - 1) * n * n;
-        rc = gj_invert(h, blk, hh == 0 ? q : n, ipiv, info + hh, pr + 2 * hh, tmp, st);
+        rc = gj_invert(h, blk, hh == 0 ? q : n, ipiv, info + hh, pr + 2 * hh, tmp, st, FR);
     }
+    tick("block inversions D_h");
     if (!rc) {
         wb_capacitance_kernel<<<h->sm_count * 8, 256, 0, st>>>(net, Dinv, Mx);
         h->launches++;
-        rc = gj_invert(h, Mx, qH, ipiv, info + H, pr + 2 * H, tmp, st);
+        rc = gj_invert(h, Mx, qH, ipiv, info + H, pr + 2 * H, tmp, st, FR);
     }
+    tick("capacitance matrix M: build + invert");
     // W_NL = (D^-1 E) M^-1, one GEMM per harmonic block: rows of block h x the rows (k, h) of M^-1
     for (int hh = 0; hh < H && !rc; ++hh) {
         const double2* blk = hh == 0 ? Dinv : Dinv + (size_t)q * q + (size_t)(hh - 1) * n * n;
@@ -1411,6 +1453,7 @@ static int setup_woodbury(hpf_t* h, const DevNet& net, cudaStream_t st, int* inf
         wb_finish_G_kernel<<<h->sm_count * 8, 256, 0, st>>>(nZ, m, q, T, h->d_Gz, h->d_GzT);
         h->launches++;
     }
+    tick("W_NL, G (tensor-core GEMMs)");
     if (rc) { cleanup(); return rc; }
     std::vector<int> hinfo((size_t)H + 1);
     std::vector<double> hpr((size_t)2 * (H + 1));
@@ -1419,6 +1462,7 @@ static int setup_woodbury(hpf_t* h, const DevNet& net, cudaStream_t st, int* inf
     WB(cudaStreamSynchronize(st));
 #undef WB
     cleanup();
+    tick("read-back + frees");
     *info_out = 0;
     prh[0] = 1.0e308; prh[1] = 0.0;
     for (int t = 0; t <= H; ++t) {
@@ -1621,11 +1665,13 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
 
 // C [M x N] = A [M x K] B [K x N] (complex, row-major) on the FP64 tensor cores (hpf_zgemm.cuh)
 static int launch_zgemm(hpf_t* h, int M, int N, int K, const double2* A, size_t lda, const double2* B, size_t ldb,
-                        double2* C, size_t ldc, cudaStream_t st) {
+                        double2* C, size_t ldc, cudaStream_t st, bool subtract) {
     if (M <= 0 || N <= 0) return HPF_OK;
-    CK(cudaFuncSetAttribute(zgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZG_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(zgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZG_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(zgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZG_SMEM_BYTES));
     const dim3 grid((unsigned)((N + ZG_BN - 1) / ZG_BN), (unsigned)((M + ZG_BM - 1) / ZG_BM));
-    zgemm_dmma_kernel<<<grid, 256, ZG_SMEM_BYTES, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
+    if (subtract) zgemm_dmma_kernel<true><<<grid, 256, ZG_SMEM_BYTES, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
+    else zgemm_dmma_kernel<false><<<grid, 256, ZG_SMEM_BYTES, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
     h->launches++;
     CK(cudaGetLastError());
     return HPF_OK;
@@ -1926,6 +1972,8 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_STRUCT_VARIANT")) h->force_variant = atoi(ev);
     if (const char* ev = getenv("HPF_DENSE_BLOCKED")) h->dense_blocked = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_LU_CLASSIC")) h->lu_classic = atoi(ev) ? 1 : 0;
+    if (const char* ev = getenv("HPF_GJ_SINGLE_MAX")) h->gj_single_max = atoi(ev);
+    if (const char* ev = getenv("HPF_GJ_UNBLOCKED")) h->gj_unblocked = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_SETUP")) h->setup_gj = (strcmp(ev, "gj") == 0) ? 1 : 0;
     if (const char* ev = getenv("HPF_WN_KERNEL")) h->wn_kernel = (strcmp(ev, "dmma") == 0) ? 2 : (strcmp(ev, "fma") == 0) ? 1 : 0;
     if (const char* ev = getenv("HPF_HARM_KERNEL")) h->harm_tile_only = (strcmp(ev, "tile") == 0) ? 1 : 0;

@@ -249,6 +249,199 @@ __global__ void gjm_elim_kernel(int n, int k, double2* __restrict__ A, const dou
     }
 }
 
+// ---- blocked variant (panels of GJB_NB pivots): the pivot steps of a panel touch only the panel's
+// columns [j0, j1) (the three kernels below); every other column receives the panel's GJB_NB rank-1
+// updates at once, A -= F R, as one complex GEMM on the tensor cores (hpf_zgemm.cuh).  With column k
+// of the pivot step reset to e_k, a Gauss-Jordan step IS a rank-1 update A -= f r^T over all rows when
+// f_k = a_kk - 1 (a_kk the pivot), f_i = a_ik otherwise, r = (row k) / a_kk:
+//   F [n x NB]  f of every step of the panel (rows interchanged along with the matrix rows),
+//   R [NB x n]  the scaled pivot rows on the other columns: R_t = (a_{k_t,:} - sum_{s<t} F[k_t][s] R_s) / a_kk.
+#define GJB_NB 64
+
+// pivot row of step t = k - j0 on the panel's columns; earlier columns of F follow the interchange
+__global__ void gjb_row_kernel(int n, int k, int j0, int j1, double2* __restrict__ A, const int* __restrict__ ipiv,
+                               const double2* __restrict__ pinv_in, double2* __restrict__ rowk,
+                               double2* __restrict__ F, double2* __restrict__ pinv_all) {
+    const int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= j1) return;
+    const int p = ipiv[k], t = k - j0;
+    const double2 pinv = pinv_in[0];
+    const double2 tk = A[(size_t)k * n + j], tp = A[(size_t)p * n + j];
+    const double2 a = (j == k) ? make_double2(1.0, 0.0) : tp;
+    const double2 v = cmul(a, pinv);
+    A[(size_t)k * n + j] = v;
+    if (p != k) A[(size_t)p * n + j] = tk;
+    rowk[j - j0] = v;
+    const int s = j - j0;
+    if (s < t && p != k) {                                   // F rows k <-> p of the panel's earlier steps
+        const double2 fk = F[(size_t)k * GJB_NB + s], fp = F[(size_t)p * GJB_NB + s];
+        F[(size_t)k * GJB_NB + s] = fp;
+        F[(size_t)p * GJB_NB + s] = fk;
+    }
+    if (j == k) pinv_all[t] = pinv;
+}
+
+// column k after the interchange: multipliers of the panel's own elimination + column t of F
+__global__ void gjb_col_kernel(int n, int k, int j0, const double2* __restrict__ A, const int* __restrict__ ipiv,
+                               const double2* __restrict__ pinv_in, double2* __restrict__ colk,
+                               double2* __restrict__ F) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 a = A[(size_t)i * n + k];
+    colk[i] = (i == k) ? make_double2(0.0, 0.0) : a;
+    double2 f = a;
+    if (i == k) {                                            // a_kk - 1 (row k already holds 1 / a_kk at column k)
+        const double2 piv = crecip(pinv_in[0]);
+        f = make_double2(piv.x - 1.0, piv.y);
+    }
+    F[(size_t)i * GJB_NB + (k - j0)] = f;
+}
+
+__global__ void gjb_elim_kernel(int n, int k, int j0, int j1, double2* __restrict__ A, const double2* __restrict__ rowk,
+                                const double2* __restrict__ colk) {
+    const int j = j0 + threadIdx.x;                          // blockDim.x = GJB_NB
+    if (j >= j1) return;
+    const double2 r = rowk[j - j0];
+    for (int i = blockIdx.x * blockDim.y + threadIdx.y; i < n; i += gridDim.x * blockDim.y) {
+        if (i == k) continue;
+        const double2 f = colk[i];
+        double2* a = A + (size_t)i * n + j;
+        *a = (j == k) ? cneg(cmul(f, r)) : csub(*a, cmul(f, r));
+    }
+}
+
+// The two kernels of a blocked pivot step (the set-up is bound by the NUMBER of launches - ~6 us each,
+// 12,400 pivots for the 1000-bus configuration - so pivot search + pivot row are one launch, multiplier
+// column + elimination of the panel's columns the other).
+__global__ void __launch_bounds__(1024)
+gjb_pivot_row_kernel(int n, int k, int j0, int j1, double2* __restrict__ A, int* __restrict__ ipiv,
+                     int* __restrict__ info, double* __restrict__ pivrange, double2* __restrict__ pinv_out,
+                     double2* __restrict__ rowk, double2* __restrict__ F, double2* __restrict__ pinv_all) {
+    __shared__ double redv[33];
+    __shared__ int redi[33];
+    __shared__ double2 spinv;
+    __shared__ int sp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + tid; i < n; i += blockDim.x) {
+        const double2 a = A[(size_t)i * n + k];
+        const double v = hypot(a.x, a.y);
+        if (v > best) { best = v; bi = i; }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        best = (lane < nw) ? redv[lane] : -1.0;
+        bi = (lane < nw) ? redi[lane] : 0x7fffffff;
+        for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            ipiv[k] = bi;
+            if (k == 0) { info[0] = 0; pivrange[0] = CUDART_INF; pivrange[1] = 0.0; }
+            if (!(best > 0.0) || !(best < CUDART_INF)) { if (info[0] == 0) info[0] = k + 1; }
+            pivrange[0] = fmin(pivrange[0], best);
+            pivrange[1] = fmax(pivrange[1], best);
+            const double2 pi = crecip(A[(size_t)bi * n + k]);
+            pinv_out[0] = pi;
+            spinv = pi;
+            sp = bi;
+        }
+    }
+    __syncthreads();
+    // pivot row on the panel's columns (see gjb_row_kernel)
+    const int j = j0 + tid;
+    if (j < j1) {
+        const int p = sp, t = k - j0;
+        const double2 pinv = spinv;
+        const double2 tk = A[(size_t)k * n + j], tp = A[(size_t)p * n + j];
+        const double2 a = (j == k) ? make_double2(1.0, 0.0) : tp;
+        const double2 v = cmul(a, pinv);
+        A[(size_t)k * n + j] = v;
+        if (p != k) A[(size_t)p * n + j] = tk;
+        rowk[tid] = v;
+        if (tid < t && p != k) {
+            const double2 fk = F[(size_t)k * GJB_NB + tid], fp = F[(size_t)p * GJB_NB + tid];
+            F[(size_t)k * GJB_NB + tid] = fp;
+            F[(size_t)p * GJB_NB + tid] = fk;
+        }
+        if (j == k) pinv_all[t] = pinv;
+    }
+}
+
+// blockDim = (GJB_NB, 4): thread (x, y) = column j0 + x of one of the block's 4 rows per pass
+__global__ void __launch_bounds__(GJB_NB * 4)
+gjb_col_elim_kernel(int n, int k, int j0, int j1, double2* __restrict__ A, const double2* __restrict__ rowk,
+                    const double2* __restrict__ pinv_in, double2* __restrict__ F) {
+    const int j = j0 + threadIdx.x;
+    const bool jok = j < j1;
+    const double2 r = jok ? rowk[threadIdx.x] : make_double2(0.0, 0.0);
+    const int rows_per_pass = gridDim.x * blockDim.y;
+    for (int base = 0; base < n; base += rows_per_pass) {            // (uniform trip count: barrier inside)
+        const int i = base + blockIdx.x * blockDim.y + threadIdx.y;
+        const bool iok = i < n;
+        const double2 f = iok ? A[(size_t)i * n + k] : make_double2(0.0, 0.0);     // multiplier, read by the whole row
+        __syncthreads();                                             // ... before thread j == k overwrites it
+        if (iok && jok) {
+            if (i != k) {
+                double2* a = A + (size_t)i * n + j;
+                *a = (j == k) ? cneg(cmul(f, r)) : csub(*a, cmul(f, r));
+            }
+            if (j == k) {
+                double2 fr = f;
+                if (i == k) {                                        // a_kk - 1 (row k holds 1 / a_kk at column k)
+                    const double2 piv = crecip(pinv_in[0]);
+                    fr = make_double2(piv.x - 1.0, piv.y);
+                }
+                F[(size_t)i * GJB_NB + (k - j0)] = fr;
+            }
+        }
+    }
+}
+
+// the other columns: the panel's interchanges, then R (forward substitution over the pivot rows);
+// R = 0 on the panel's own columns so that the GEMM leaves them alone
+__global__ void gjb_rows_kernel(int n, int j0, int nb, double2* __restrict__ A, const int* __restrict__ ipiv,
+                                const double2* __restrict__ F, const double2* __restrict__ pinv_all,
+                                double2* __restrict__ R) {
+    __shared__ double2 sF[GJB_NB * GJB_NB / 2 + GJB_NB];     // strictly lower triangle of F on the pivot rows
+    __shared__ double2 sP[GJB_NB];
+    __shared__ int sPiv[GJB_NB];
+    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+        const int t = e / nb, s2 = e % nb;
+        if (s2 < t) sF[t * (t - 1) / 2 + s2] = F[(size_t)(j0 + t) * GJB_NB + s2];
+    }
+    for (int t = threadIdx.x; t < nb; t += blockDim.x) { sP[t] = pinv_all[t]; sPiv[t] = ipiv[j0 + t]; }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (j >= j0 && j < j0 + nb) {
+        for (int t = 0; t < nb; ++t) R[(size_t)t * n + j] = make_double2(0.0, 0.0);
+        return;
+    }
+    for (int t = 0; t < nb; ++t) {                           // the interchanges, in order
+        const int k = j0 + t, p = sPiv[t];
+        if (p != k) {
+            const double2 a = A[(size_t)k * n + j], b = A[(size_t)p * n + j];
+            A[(size_t)k * n + j] = b;
+            A[(size_t)p * n + j] = a;
+        }
+    }
+    for (int t = 0; t < nb; ++t) {
+        double2 x = A[(size_t)(j0 + t) * n + j];
+        for (int s2 = 0; s2 < t; ++s2) x = csub(x, cmul(sF[t * (t - 1) / 2 + s2], R[(size_t)s2 * n + j]));
+        R[(size_t)t * n + j] = cmul(x, sP[t]);
+    }
+}
+
 __global__ void gjm_unpermute_kernel(int n, double2* __restrict__ A, const int* __restrict__ ipiv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -38,6 +38,8 @@ __device__ __forceinline__ void zg_cp16(double2* sdst, const double2* gsrc, cons
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(sa), "l"(gsrc), "r"(sz) : "memory");
 }
 
+// SUB = false: C = A B;  SUB = true: C -= A B (the deferred rank-64 update of the blocked Gauss-Jordan)
+template <bool SUB>
 __global__ void __launch_bounds__(256, 2)
 zgemm_dmma_kernel(const int M, const int N, const int K, const double2* __restrict__ A, const size_t lda,
                   const double2* __restrict__ B, const size_t ldb, double2* __restrict__ C, const size_t ldc) {
@@ -114,8 +116,13 @@ zgemm_dmma_kernel(const int M, const int N, const int K, const double2* __restri
         for (int j = 0; j < 4; ++j) {
             const int c = n0 + wn * 32 + j * 8 + 2 * (lane & 3);
             double2* dst = C + (size_t)r * ldc + c;
-            if (c < N) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
-            if (c + 1 < N) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
+            if (SUB) {
+                if (c < N) { const double2 o = dst[0]; dst[0] = make_double2(o.x - cr[i][j][0], o.y - ci[i][j][0]); }
+                if (c + 1 < N) { const double2 o = dst[1]; dst[1] = make_double2(o.x - cr[i][j][1], o.y - ci[i][j][1]); }
+            } else {
+                if (c < N) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
+                if (c + 1 < N) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
+            }
         }
     }
 }

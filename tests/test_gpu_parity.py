@@ -1149,8 +1149,9 @@ def test_norton_contraction_dmma_matches_fma_and_definition(kind, n, variant, B,
     assert np.abs(res).max() <= 1e-9 * np.abs(rhs).max()
 
 
+@pytest.mark.parametrize("gj", ["default", "blocked", "unblocked"])
 @pytest.mark.parametrize("kind,n,coupled", [("meshed", 70, True), ("radial", 40, True), ("meshed", 30, False)])
-def test_woodbury_setup_matches_gauss_jordan_setup(kind, n, coupled, tmp_path, monkeypatch):
+def test_woodbury_setup_matches_gauss_jordan_setup(kind, n, coupled, gj, tmp_path, monkeypatch):
     """Large-network set-up (variant 3): the operators W_NL = A_ZZ^-1 E and G = A_ZZ^-1 A_ZF built
     through the block structure of A_ZZ (Woodbury identity: H block inversions, one inversion of
     order qH, complex GEMMs on the tensor cores) against the round-1 path (Gauss-Jordan inversion
@@ -1161,8 +1162,15 @@ def test_woodbury_setup_matches_gauss_jordan_setup(kind, n, coupled, tmp_path, m
     B = 24
     P, Q, I_N = scenarios.make_batch(net, B, "tight")
     out = {}
+    # gj: which inversion kernels the Woodbury path uses - "default" (one-CTA kernel for these small
+    # blocks), "blocked" (multi-CTA, panels of 64 pivots + tensor-core GEMM update: what the 1000-bus
+    # configuration runs; partial panels and panels narrower than 64 included), "unblocked" (multi-CTA,
+    # one rank-1 update per pivot)
     for setup in ("gj", "woodbury"):
         monkeypatch.setenv("HPF_SETUP", setup)
+        if setup == "woodbury" and gj != "default":
+            monkeypatch.setenv("HPF_GJ_SINGLE_MAX", "0")
+            monkeypatch.setenv("HPF_GJ_UNBLOCKED", "1" if gj == "unblocked" else "0")
         sol = BatchSolver(net)
         info = sol.struct_info()
         assert info["available"] == 3 and info["pivot_min"] > 0
