@@ -1,7 +1,8 @@
 """Summarise an .ncu-rep into the CSV kept under profiles/: one row per kernel launch with the
-metrics the roofline discussion uses.  usage: ncu_summary.py report.ncu-rep out.csv [git-sha]
-The first line of the CSV is a comment with the git SHA of the binary the capture was taken from
-(bench.py compares it with the SHA it runs at and marks the traffic figure stale otherwise)."""
+metrics the roofline discussion uses.  usage: ncu_summary.py report.ncu-rep out.csv [git-sha] [src-hash]
+The first line of the CSV is a comment with the git SHA and the hash of the CUDA sources
+(bench.source_hash) of the binary the capture was taken from: bench.py recomputes the hash where it
+runs and marks the traffic figure stale when the sources have changed since."""
 import csv
 import subprocess
 import sys
@@ -30,13 +31,16 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 rep, out = sys.argv[1], sys.argv[2]
 sha = sys.argv[3] if len(sys.argv) > 3 else "unknown"
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
+import bench
+src_hash = sys.argv[4] if len(sys.argv) > 4 else bench.source_hash()
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 ki = hdr.index("Kernel Name")
 cols = [(w, hdr.index(w)) for w in WANT if w in hdr]
 with open(out, "w", newline="") as f:
-    f.write("# git_sha=%s source=%s\n" % (sha, rep.split("/")[-1]))
+    f.write("# git_sha=%s src_hash=%s source=%s\n" % (sha, src_hash, rep.split("/")[-1]))
     w = csv.writer(f)
     w.writerow(["Kernel Name"] + [c for c, _ in cols])
     w.writerow([""] + [units[i] for _, i in cols])
