@@ -16,7 +16,7 @@ HPF_OK, HPF_E_INVALID, HPF_E_CUDA, HPF_E_UNSUPPORTED, HPF_E_NOMEM = 0, -1, -2, -
 ST_CONVERGED, ST_MAXITER, ST_SINGULAR, ST_NONFINITE = 0, 1, 2, 3
 SOLVE_RAW = 1
 SOLVE_DENSE = 2
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
 _ip, _dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -37,6 +37,7 @@ SIGNATURES = {
     "hpf_struct_info": (_i, [_vp, _ip, _ip, _dp, _dp]),
     "hpf_newton_step": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hpf_norton_wn": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "hpf_prepare": (_i, [_vp, _i, _vp]),
     "hpf_set_profiling": (_i, [_vp, _i]),
     "hpf_last_kernel_ms": (_i, [_vp, _dp]),
     "hpf_thd": (_i, [_vp, _i, _vp, _vp, _vp]),

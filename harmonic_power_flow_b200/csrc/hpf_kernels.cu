@@ -1513,9 +1513,35 @@ static bool build_hw_consts(hpf_t* h, int shape_id) {
 //   2  one scenario per CTA, state in shared memory (net1: 20 buses x 26 harmonics)
 //   3  one scenario per CTA, state in a global-memory slab, blocked tensor-core LU for the
 //      border system (200- / 1000-bus configurations)
+// frees the temporaries of a set-up on every exit path
+struct TmpFree {
+    std::vector<void*> p;
+    ~TmpFree() { for (void* x : p) cudaFree(x); }
+};
+
+static void free_struct_buffers(hpf_t* h) {
+    cudaFree(h->d_Ainv); cudaFree(h->d_Gz); cudaFree(h->d_GzT); cudaFree(h->d_WNL);
+    h->d_Ainv = nullptr; h->d_Gz = nullptr; h->d_GzT = nullptr; h->d_WNL = nullptr;
+}
+
 static int ensure_struct(hpf_t* h, cudaStream_t st) {
     if (h->struct_state != 0) return HPF_OK;
     h->struct_state = -1;
+    TmpFree guard;
+    // allocation inside the set-up: out of device memory is not an error of the solve - the structured
+    // buffers are released, the reason is left in hpf_last_error() and hpf_solve uses the dense strategy
+#define SK(ptr, bytes, temp)                                                                          \
+    do {                                                                                              \
+        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                         \
+        if (e_ == cudaErrorMemoryAllocation) {                                                        \
+            cudaGetLastError();                                                                       \
+            free_struct_buffers(h);                                                                   \
+            h->err = "structured set-up skipped (out of device memory for " #ptr "): dense strategy"; \
+            return HPF_OK;                                                                            \
+        }                                                                                             \
+        if (e_ != cudaSuccess) return fail(h, HPF_E_CUDA, std::string("structured setup: cudaMalloc " #ptr ": ") + cudaGetErrorString(e_)); \
+        if (temp) guard.p.push_back((void*)(ptr));                                                    \
+    } while (0)
     const DevNet net = devnet(h);
     const int nZ = net.nH - net.m;
     if (nZ < 1) return HPF_OK;
@@ -1542,9 +1568,8 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     double2* tmp = nullptr;
     int* ipiv = nullptr;
     double* pr = nullptr;
-    cudaFree(h->d_Ainv); cudaFree(h->d_Gz); cudaFree(h->d_GzT); cudaFree(h->d_WNL);
+    free_struct_buffers(h);
     cudaFree(h->d_nbr_ptr); cudaFree(h->d_nbr_idx);
-    h->d_Ainv = nullptr; h->d_Gz = nullptr; h->d_GzT = nullptr; h->d_WNL = nullptr;
     h->d_nbr_ptr = nullptr; h->d_nbr_idx = nullptr;
     const int qH = net.q * net.H;
     // nonlinear neighbours of the linear buses (structure of Y1), from the host mirror of Y
@@ -1587,9 +1612,9 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
             }
         }
     }
-    CK(cudaMalloc((void**)&h->d_WNL, ((size_t)nZ * qH + 1) * sizeof(double2)));
-    CK(cudaMalloc((void**)&h->d_Gz, (size_t)nZ * net.m * sizeof(double2)));
-    CK(cudaMalloc((void**)&h->d_GzT, (size_t)nZ * net.m * sizeof(double2)));
+    SK(h->d_WNL, ((size_t)nZ * qH + 1) * sizeof(double2), false);
+    SK(h->d_Gz, (size_t)nZ * net.m * sizeof(double2), false);
+    SK(h->d_GzT, (size_t)nZ * net.m * sizeof(double2), false);
     if (variant == 3 && qH > 0 && !h->setup_gj) {
         // large networks: the operator inverse through its block structure (Woodbury) - no nZ x nZ inverse
         int winfo = -1;
@@ -1601,17 +1626,17 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
         if (winfo == 0 && wpr[0] > 0.0 && wpr[1] / wpr[0] < 1e12) h->struct_state = variant;
         return HPF_OK;
     }
-    CK(cudaMalloc((void**)&h->d_Ainv, (size_t)nZ * nZ * sizeof(double2)));
-    CK(cudaMalloc((void**)&AZF, (size_t)nZ * net.m * sizeof(double2)));
-    CK(cudaMalloc((void**)&ipiv, (size_t)(nZ + 2) * sizeof(int)));
-    CK(cudaMalloc((void**)&pr, 2 * sizeof(double)));
+    SK(h->d_Ainv, (size_t)nZ * nZ * sizeof(double2), false);
+    SK(AZF, (size_t)nZ * net.m * sizeof(double2), true);
+    SK(ipiv, (size_t)(nZ + 2) * sizeof(int), true);
+    SK(pr, 2 * sizeof(double), true);
     struct_assemble_kernel<<<h->sm_count * 8, 256, 0, st>>>(net, h->d_Ainv, AZF);
     h->launches++;
     if (nZ <= 768) {
         cinv_gj_kernel<<<1, 1024, 0, st>>>(nZ, h->d_Ainv, ipiv, ipiv + nZ, pr);
         h->launches++;
     } else {
-        CK(cudaMalloc((void**)&tmp, ((size_t)2 * nZ + 1) * sizeof(double2)));
+        SK(tmp, ((size_t)2 * nZ + 1) * sizeof(double2), true);
         double2 *rowk = tmp, *colk = tmp + nZ, *pinv = tmp + 2 * (size_t)nZ;
         const int g1 = (nZ + 255) / 256;
         int gy = (h->sm_count * 8 + g1 - 1) / g1;
@@ -1641,7 +1666,6 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
     cudaError_t e = cudaMemcpyAsync(&info, ipiv + nZ, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(prh, pr, sizeof(prh), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(AZF); cudaFree(ipiv); cudaFree(pr); cudaFree(tmp);
     h->hWNL.clear();
     h->hG.clear();
     h->hw_shape = 0;
@@ -1661,6 +1685,7 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
         if (!build_hw_consts<Dims<4, 3, 2, 13, 1>>(h, 1)) build_hw_consts<Dims<4, 2, 1, 10, 2>>(h, 2);
     }
     return HPF_OK;
+#undef SK
 }
 
 // C [M x N] = A [M x K] B [K x N] (complex, row-major) on the FP64 tensor cores (hpf_zgemm.cuh)
@@ -2228,6 +2253,35 @@ int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I
         return solve_dispatch(h, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a, I_inj,
                               n_iter_f, n_iter_h, err_h, status, err_hist_f, err_hist_h, stream);
     });
+}
+
+int hpf_prepare(hpf_t* h, int B_max, void* stream) {
+    int rc = ready(h, "hpf_prepare", true);
+    if (rc) return rc;
+    if (B_max <= 0) return fail(h, HPF_E_INVALID, "hpf_prepare: B_max <= 0");
+    ENTER_DEVICE(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    // a zero-iteration solve of B_max all-zero scenarios (thresholds above every mismatch) walks exactly
+    // the allocation paths of hpf_solve: structured set-up, w_N scratch, LU workspaces, state slabs
+    const size_t B = (size_t)B_max, n = h->n, H = h->H, q = h->q;
+    const size_t nd = 2 * n * B + 2 * q * H * B + 2 * n * H * B + 2 * q * H * B + B + 2 * B + 8;
+    double* buf = nullptr;
+    cudaError_t e = cudaMalloc((void**)&buf, nd * sizeof(double));
+    if (e != cudaSuccess) return fail(h, e == cudaErrorMemoryAllocation ? HPF_E_NOMEM : HPF_E_CUDA,
+                                      std::string("hpf_prepare: ") + cudaGetErrorString(e));
+    e = cudaMemsetAsync(buf, 0, nd * sizeof(double), st);
+    double *P = buf, *Q = P + n * B, *IN = Q + n * B, *Vm = IN + 2 * q * H * B, *Va = Vm + n * H * B,
+           *Inj = Va + n * H * B, *err = Inj + 2 * q * H * B;
+    int* iw = reinterpret_cast<int*>(err + B);
+    if (e == cudaSuccess)
+        rc = hpf_solve(h, B_max, P, Q, q ? IN : nullptr, 1e300, 1, 1e300, 1, 0, Vm, Va, q ? Inj : nullptr, iw, iw + B, err,
+                       iw + 2 * B, nullptr, nullptr, stream);
+    const cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(buf);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return fail(h, HPF_E_CUDA, std::string("hpf_prepare: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return HPF_OK;
 }
 
 int hpf_struct_info(hpf_t* h, int* available, int* nZ, double* pivot_min, double* pivot_max) {

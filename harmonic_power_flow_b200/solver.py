@@ -340,6 +340,10 @@ class BatchSolver:
                                                      _ptr(I_N), _ptr(dx), self._stream()))
         return dx
 
+    def prepare_batch(self, B_max):
+        """hpf_prepare: all lazy set-up and scratch allocation for batches of up to B_max scenarios now."""
+        _lib.check(self._h, self.lib.hpf_prepare(self._h, int(B_max), self._stream()))
+
     def norton_wn(self, I_N):
         """w_N = A_ZZ^-1 I_N,Z = W_NL I_N for the batch, complex [nZ, B] (hpf_norton_wn): the Norton
         contraction of the structured step as one complex GEMM."""

@@ -16,9 +16,21 @@
  *  - "host" pointers are read during the call and copied.  "device" pointers are
  *    caller-owned CUDA device memory on the handle's device; the handle owns only
  *    the network, Norton-equivalent tables, Y(h) and small scratch.
- *  - Every kernel entry point is asynchronous on `stream` (a cudaStream_t passed
- *    as void*, NULL = legacy default stream); no hidden synchronisation except
- *    in hpf_destroy() and the *_host convenience call.
+ *  - Every kernel entry point enqueues its work on `stream` (a cudaStream_t passed
+ *    as void*, NULL = legacy default stream) and returns without waiting for it.
+ *    LAZY SET-UP does synchronise, once: the first hpf_solve / hpf_newton_step /
+ *    hpf_norton_wn / hpf_struct_info after a network, device-table or Y(h) change
+ *    builds the structured-step operators (device allocations, a stream
+ *    synchronisation and a small read-back); the first use of the one-thread-per-
+ *    scenario mismatch kernel mirrors Y(h) to the host; a batch larger than any
+ *    before it grows the handle's scratch (device synchronisation + reallocation).
+ *    hpf_prepare() does all of that up front, after which solves of up to B_max
+ *    scenarios neither allocate nor synchronise (and may be captured into a CUDA
+ *    graph).  hpf_destroy() and the *_host calls synchronise by design.
+ *  - One kernel sequence in flight per handle: the work queue, the w_N scratch and
+ *    the LU workspaces live in the handle, so a call arriving on a different stream
+ *    than the previous one is ordered after it on the device (event wait; the host
+ *    does not block).  A stream under CUDA-graph capture is left alone.
  *  - All arithmetic is IEEE FP64.  Complex values are interleaved (re, im)
  *    doubles (numpy/torch complex128).
  *  - Batch arrays are BATCH-INNERMOST: element (i, b) of an [n, B] array is at
@@ -55,7 +67,7 @@ typedef struct hpf_handle hpf_t;
 #define HPF_ST_NONFINITE    3   /* NaN/Inf in the mismatch or the state            */
 
 /* ABI version of this header: bumped on any signature change. */
-#define HPF_ABI_VERSION 10
+#define HPF_ABI_VERSION 11
 int hpf_abi_version(void);
 
 /* Lifetime.  `device` is the CUDA ordinal the handle is bound to. */
@@ -118,6 +130,14 @@ int hpf_build_Y(hpf_t* h, double* Y_out, void* stream);
  * (host).  This is what pf(Y, buses) of the reference takes (HG:244,255).
  */
 int hpf_set_Y(hpf_t* h, const double* Y);
+
+/*
+ * Optional: run every lazy set-up NOW for batches of up to B_max scenarios - the structured-step
+ * operators of the network, the handle's scratch (w_N, LU workspaces, scenario state slabs) - by
+ * solving B_max all-zero scenarios with zero iterations.  Synchronises `stream`.  Afterwards
+ * hpf_solve / hpf_mismatch / ... with B <= B_max neither allocate nor synchronise.
+ */
+int hpf_prepare(hpf_t* h, int B_max, void* stream);
 
 /* hpf_solve flags */
 #define HPF_SOLVE_RAW   1 /* skip the post-processing of HG:547-549: return the raw iterate */

@@ -1191,3 +1191,47 @@ def test_woodbury_setup_matches_gauss_jordan_setup(kind, n, coupled, gj, tmp_pat
     # (an iterate accepted at mismatch norm e is ~e away from the solution)
     tol = np.maximum(a["res"]["err_h"], b["res"]["err_h"])[same]
     assert (np.abs(Va - Vb)[..., same].reshape(-1, same.sum()).max(0) <= np.maximum(1e-9, tol)).all()
+
+
+def test_prepare_then_async_solves_two_streams_and_graph_capture(solvers):
+    """hpf_prepare: after it a solve of <= B_max scenarios neither allocates nor
+    synchronises, so (a) two solves issued back to back on two different streams are ordered on the
+    device by the handle (one kernel sequence in flight per handle) and both come out bit-identical
+    to a solve alone, and (b) the solve can be captured into a CUDA graph and replayed."""
+    from harmonic_power_flow_b200 import BatchSolver, scenarios
+    _, net, _ = solvers("net3_c_h25")
+    sol = BatchSolver(net)
+    B = 700
+    sol.prepare_batch(B)
+    Pa, Qa, Ia = sol.prepare(*scenarios.make_batch(net, B, "tight"))
+    Pb, Qb, Ib = sol.prepare(*scenarios.make_batch(net, B, "wide"))
+    torch.cuda.synchronize()
+    want_a = sol.solve(Pa, Qa, Ia).to_host()
+    want_b = sol.solve(Pb, Qb, Ib).to_host()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            ra = sol.solve(Pa, Qa, Ia)
+        with torch.cuda.stream(s2):
+            rb = sol.solve(Pb, Qb, Ib)
+        torch.cuda.synchronize()
+        ga, gb = ra.to_host(), rb.to_host()
+        for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status"):
+            assert np.array_equal(ga[k], want_a[k], equal_nan=True), k
+            assert np.array_equal(gb[k], want_b[k], equal_nan=True), k
+    # CUDA-graph capture of one solve, replayed on new inputs written into the captured buffers
+    res, _slab = sol.alloc_result_slab(B)
+    g = torch.cuda.CUDAGraph()
+    sc = torch.cuda.Stream()
+    sc.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.graph(g, stream=sc):
+        rg = sol.solve(Pa, Qa, Ia, out=res)
+    for want, (P, Q, I) in ((want_a, None), (want_b, (Pb, Qb, Ib)), (want_a, (Pa.clone(), Qa.clone(), Ia.clone()))):
+        if P is not None:
+            Pa.copy_(P); Qa.copy_(Q); Ia.copy_(I)
+        g.replay()
+        torch.cuda.synchronize()
+        got = rg.to_host()
+        for k in ("V_m", "V_a", "n_iter_h", "err_h", "status"):
+            assert np.array_equal(got[k], want[k], equal_nan=True), k
+    sol.close()
