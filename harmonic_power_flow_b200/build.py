@@ -41,7 +41,9 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    # $HPF_BUILD_FAST=1: ptxas compiles the kernels in parallel (development builds, 3x faster)
+    fast = ["--split-compile", "0"] if os.environ.get("HPF_BUILD_FAST") else []
+    cmd = [_nvcc()] + NVCC_FLAGS + fast + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

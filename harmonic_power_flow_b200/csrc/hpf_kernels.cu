@@ -1069,6 +1069,8 @@ struct hpf_handle {
     size_t gstate_doubles = 0;
     size_t wN_elems = 0;
     int harm_warps = 8;           // warps per 32-scenario tile of the harmonic kernel (8 or 16)
+    int gmem_threads = 0;         // $HPF_GMEM_THREADS: threads per CTA of the global-memory-state kernels (0 = by system size)
+    size_t gmem_cap = 0;          // $HPF_GMEM_SMEM_KB: shared-memory budget per CTA of those kernels (0 = all of it)
     int harm_minb = 1;
     int no_specialise = 0;        // $HPF_NO_SPECIALISE=1: always use the runtime-dimension kernels
     int mismatch_tile = 0;        // $HPF_MISMATCH_TILE=1: standalone mismatch through the tile kernel
@@ -1222,6 +1224,11 @@ static int ensure_workspace(hpf_t* h, size_t doubles) {
     return HPF_OK;
 }
 
+// shared-memory budget per CTA of the global-memory-state kernels ($HPF_GMEM_SMEM_KB; default: all of it)
+static size_t gmem_smem_cap(const hpf_t* h) {
+    return (h->gmem_cap && h->gmem_cap < (size_t)h->smem_optin) ? h->gmem_cap : (size_t)h->smem_optin;
+}
+
 template <class K>
 static int prep_kernel(hpf_t* h, K kernel, size_t smem, const char* who, int* ctas_per_sm,
                        int threads = HPF_THREADS) {
@@ -1266,15 +1273,20 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     const size_t lubs = gm ? 0 : smem_blocked_lub_doubles(h, net);     // > 0: blocked LU, matrix in smem
     const bool ws_smem = lubs > 0;
     if (ws_smem) gm = true;
-    const size_t lubd = ws_smem ? lubs : (gm ? gmem_kernel_lub_doubles(net.n, net.H, net.q, net.N, (size_t)h->smem_optin) : 0);
+    // the reduced budget / thread count of $HPF_GMEM_* applies when the scenario state leaves room for the LU work area
+    const bool reduced = gm && !ws_smem &&
+                         gmem_kernel_smem_bytes(net.n, net.H, net.q, net.N) + 32 * 1024 <= gmem_smem_cap(h);
+    const size_t lubd = ws_smem ? lubs : (gm ? gmem_kernel_lub_doubles(net.n, net.H, net.q, net.N,
+                                                                      reduced ? gmem_smem_cap(h) : (size_t)h->smem_optin) : 0);
     const size_t smem = gm ? (scn_smem_doubles_aligned(net.n, net.H, net.q, net.N) + lubd +
                               (ws_smem ? (size_t)lub_ld(net.N) * (net.N + 1) : 0)) * sizeof(double) + 16
                            : scn_smem_bytes(net.n, net.H, net.q, net.N, true);
     int occ = 0;
     const bool big = gm && lub_needs_big(net.N, lubd);
+    const int gthreads = (reduced && h->gmem_threads) ? h->gmem_threads : HPF_THREADS_GMEM;
     rc = !gm ? prep_kernel(h, solve_kernel<0>, smem, who, &occ)
-             : big ? prep_kernel(h, solve_kernel<2>, smem, who, &occ, HPF_THREADS_GMEM)
-                   : prep_kernel(h, solve_kernel<1>, smem, who, &occ, HPF_THREADS_GMEM);
+             : big ? prep_kernel(h, solve_kernel<2>, smem, who, &occ, gthreads)
+                   : prep_kernel(h, solve_kernel<1>, smem, who, &occ, gthreads);
     if (rc) return rc;
     SolveArgs a;
     a.B = B; a.mode = mode; a.flags = flags; a.P = P; a.Q = Q; a.I_N = (const double2*)I_N;
@@ -1297,8 +1309,8 @@ static int solve_common(hpf_t* h, int mode, int B, const double* P, const double
     }
     if (h->profiling) { CK(cudaEventRecord(h->ev[1], st)); }
     if (!gm) solve_kernel<0><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, a);
-    else if (big) solve_kernel<2><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, a);
-    else solve_kernel<1><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, a);
+    else if (big) solve_kernel<2><<<(unsigned)grid, gthreads, smem, st>>>(net, a);
+    else solve_kernel<1><<<(unsigned)grid, gthreads, smem, st>>>(net, a);
     if (net.H != H_full) {
         const size_t cnt = (size_t)(H_full - 1) * net.n * B;
         flat_start_fill_kernel<<<(unsigned)((cnt + 255) / 256 < 65535 * 8 ? (cnt + 255) / 256 : 65535 * 8), 256, 0, st>>>(
@@ -1815,15 +1827,20 @@ static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const H
                        bool persistent, cudaStream_t st) {
     if (h->struct_state >= 2) {
         const bool gst = h->struct_state == 3;
-        const size_t lubd = gst ? harm_cta_gmem_lub_doubles(sn.nx, (size_t)h->smem_optin) : 0;
+        const size_t lubd = gst ? harm_cta_gmem_lub_doubles(sn.nx, gmem_smem_cap(h)) : 0;
+        // threads per CTA: every phase of this kernel is barrier- / latency-bound, and a border system whose
+        // panels fit one row per thread of 8 warps runs faster with 8 warps than with 16 (measured, 200-bus
+        // feeder, nx = 238: 217 -> 183 ms per 2,048 scenarios; 1000-bus network, nx = 1198: 2.40 -> 2.78 s
+        // the other way round) - profiles/r2_gmem_ctas_ab.txt
+        const int gthreads = h->gmem_threads ? h->gmem_threads : (sn.nx <= 256 ? 256 : HPF_THREADS_GMEM);
         const size_t smem = gst ? (lubd + 80) * sizeof(double)
                                 : harm_cta_smem_bytes(net.n, net.H, net.m, net.c, net.q, net.N);
         int occ = 0;
         // global-state variant: every phase waits on L2 / HBM, so it runs with twice the warps
         const bool big = gst && lub_needs_big(sn.nx, lubd);
         int rc = !gst ? prep_kernel(h, harm_cta_kernel<HPF_THREADS, false>, smem, "hpf_solve", &occ)
-                      : big ? prep_kernel(h, harm_cta_kernel<HPF_THREADS_GMEM, true>, smem, "hpf_solve", &occ, HPF_THREADS_GMEM)
-                            : prep_kernel(h, harm_cta_kernel<HPF_THREADS_GMEM, false>, smem, "hpf_solve", &occ, HPF_THREADS_GMEM);
+                      : big ? prep_kernel(h, harm_cta_kernel<HPF_THREADS_GMEM, true>, smem, "hpf_solve", &occ, gthreads)
+                            : prep_kernel(h, harm_cta_kernel<HPF_THREADS_GMEM, false>, smem, "hpf_solve", &occ, gthreads);
         if (rc) return rc;
         long long grid = ha.B;
         if ((persistent || gst) && grid > (long long)occ * h->sm_count) grid = (long long)occ * h->sm_count;
@@ -1841,8 +1858,8 @@ static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const H
             ha2.gstate = h->d_gstate; ha2.gstate_stride = stride;
         }
         if (!gst) harm_cta_kernel<HPF_THREADS, false><<<(unsigned)grid, HPF_THREADS, smem, st>>>(net, sn, ha2);
-        else if (big) harm_cta_kernel<HPF_THREADS_GMEM, true><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, sn, ha2);
-        else harm_cta_kernel<HPF_THREADS_GMEM, false><<<(unsigned)grid, HPF_THREADS_GMEM, smem, st>>>(net, sn, ha2);
+        else if (big) harm_cta_kernel<HPF_THREADS_GMEM, true><<<(unsigned)grid, gthreads, smem, st>>>(net, sn, ha2);
+        else harm_cta_kernel<HPF_THREADS_GMEM, false><<<(unsigned)grid, gthreads, smem, st>>>(net, sn, ha2);
         h->launches++;
         CK(cudaGetLastError());
         return HPF_OK;
@@ -2005,6 +2022,8 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_HW_EPOCH")) h->hw_epoch = atoi(ev) >= 1 ? atoi(ev) : 1;
     if (const char* ev = getenv("HPF_HW_MINB")) h->hw_minb = (atoi(ev) == 1) ? 1 : 2;
     if (const char* ev = getenv("HPF_MAX_CTAS")) h->max_ctas = atoi(ev) > 0 ? atoi(ev) : 0;
+    if (const char* ev = getenv("HPF_GMEM_THREADS")) { const int t = atoi(ev); if (t == 128 || t == 256 || t == 512) h->gmem_threads = t; }
+    if (const char* ev = getenv("HPF_GMEM_SMEM_KB")) h->gmem_cap = (size_t)(atoi(ev) > 0 ? atoi(ev) : 0) * 1024;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     e = cudaMalloc((void**)&h->d_counter, 8 * sizeof(int));

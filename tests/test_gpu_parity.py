@@ -1226,9 +1226,9 @@ def test_prepare_then_async_solves_two_streams_and_graph_capture(solvers):
     sc.wait_stream(torch.cuda.current_stream())
     with torch.cuda.graph(g, stream=sc):
         rg = sol.solve(Pa, Qa, Ia, out=res)
-    for want, (P, Q, I) in ((want_a, None), (want_b, (Pb, Qb, Ib)), (want_a, (Pa.clone(), Qa.clone(), Ia.clone()))):
-        if P is not None:
-            Pa.copy_(P); Qa.copy_(Q); Ia.copy_(I)
+    for want, src in ((want_a, None), (want_b, (Pb, Qb, Ib)), (want_a, (Pa.clone(), Qa.clone(), Ia.clone()))):
+        if src is not None:
+            Pa.copy_(src[0]); Qa.copy_(src[1]); Ia.copy_(src[2])
         g.replay()
         torch.cuda.synchronize()
         got = rg.to_host()
