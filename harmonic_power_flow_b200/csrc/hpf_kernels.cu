@@ -972,6 +972,8 @@ harm_cta_kernel(const DevNet net, const StructNet sn, const HarmTileArgs a) {
     (void)N;
 }
 
+#include "hpf_lockstep.cuh"
+
 // flat start of the harmonic rows (HG:183): |V| = 0.1, angle 0
 __global__ void flat_start_fill_kernel(double* __restrict__ Vm, double* __restrict__ Va, size_t cnt) {
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (size_t)gridDim.x * blockDim.x) {
@@ -1081,6 +1083,13 @@ struct hpf_handle {
     int lu_classic = 0;           // $HPF_LU_CLASSIC=1: shared-memory LU with rank-1 updates (lu_solve_smem) instead of the panel LU
     int dense_blocked = 0;        // $HPF_DENSE_BLOCKED=1: blocked tensor-core LU also for smem-sized systems
     int force_variant = 0;        // $HPF_STRUCT_VARIANT=2|3: force a per-CTA variant of the harmonic stage
+    // lock-step batched harmonic stage of the large networks (hpf_lockstep.cuh)
+    int lockstep = -1;            // $HPF_LOCKSTEP=0|1: never / always; default (-1): batches of at least lockstep_min scenarios
+    int lockstep_min = 128;
+    size_t ls_budget = 0;         // $HPF_LOCKSTEP_GB: device memory the lock-step work areas may take (0 = 40 % of the free memory, at most 64 GB)
+    void* d_ls = nullptr;         // one allocation: state slabs | border systems | X | GX | U0 | ints
+    size_t ls_bytes = 0;
+    int ls_slots = 0;
     // host mirror of the network constants for kernels that take them as parameters
     // (constant bank): fetched lazily from the device tables, see host_consts()
     std::vector<double2> hY, hYN, hWNL, hG;
@@ -1340,7 +1349,7 @@ static StructNet structnet(const hpf_t* h) {
 
 static int host_consts(hpf_t* h);
 static int launch_zgemm(hpf_t* h, int M, int N, int K, const double2* A, size_t lda, const double2* B, size_t ldb,
-                        double2* C, size_t ldc, cudaStream_t st, bool subtract = false);
+                        double2* C, size_t ldc, cudaStream_t st, bool subtract = false, const int* n_dev = nullptr);
 
 // In-place complex Gauss-Jordan inverse with partial pivoting of one matrix of order nn (row-major):
 // one CTA for nn <= 768, else four small launches per pivot over the whole GPU.  info[0] = 0 or
@@ -1702,13 +1711,13 @@ static int ensure_struct(hpf_t* h, cudaStream_t st) {
 
 // C [M x N] = A [M x K] B [K x N] (complex, row-major) on the FP64 tensor cores (hpf_zgemm.cuh)
 static int launch_zgemm(hpf_t* h, int M, int N, int K, const double2* A, size_t lda, const double2* B, size_t ldb,
-                        double2* C, size_t ldc, cudaStream_t st, bool subtract) {
+                        double2* C, size_t ldc, cudaStream_t st, bool subtract, const int* n_dev) {
     if (M <= 0 || N <= 0) return HPF_OK;
     CK(cudaFuncSetAttribute(zgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZG_SMEM_BYTES));
     CK(cudaFuncSetAttribute(zgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZG_SMEM_BYTES));
     const dim3 grid((unsigned)((N + ZG_BN - 1) / ZG_BN), (unsigned)((M + ZG_BM - 1) / ZG_BM));
-    if (subtract) zgemm_dmma_kernel<true><<<grid, 256, ZG_SMEM_BYTES, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
-    else zgemm_dmma_kernel<false><<<grid, 256, ZG_SMEM_BYTES, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
+    if (subtract) zgemm_dmma_kernel<true><<<grid, 256, ZG_SMEM_BYTES, st>>>(M, N, K, A, lda, B, ldb, C, ldc, n_dev);
+    else zgemm_dmma_kernel<false><<<grid, 256, ZG_SMEM_BYTES, st>>>(M, N, K, A, lda, B, ldb, C, ldc, n_dev);
     h->launches++;
     CK(cudaGetLastError());
     return HPF_OK;
@@ -1880,6 +1889,266 @@ static int launch_harm(hpf_t* h, const DevNet& net, const StructNet& sn, const H
     return launch_harm_t<8, 1, DynDims>(h, net, sn, ha, persistent, st);
 }
 
+// $HPF_LS_TIMING=1: per-phase device times of the lock-step rounds on stderr (diagnostics: records an
+// event after every launch group and synchronises at the end of the call)
+struct LsTimer {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;
+    void mark(int t) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        tag.push_back(t);
+    }
+    void report(const char* what) {
+        if (!on) return;
+        static const char* names[] = {"start", "mismatch+compact", "pack+zgemm U0", "border assembly", "LU panel",
+                                      "LU swap+trsm", "LU update", "LU backsub", "uf+zgemm G X", "load/store"};
+        cudaStreamSynchronize(st);
+        double acc[10] = {0};
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            acc[tag[i]] += ms;
+        }
+        double tot = 0;
+        for (int t = 1; t < 10; ++t) tot += acc[t];
+        fprintf(stderr, "[hpf lock-step timing] %s: total %.1f ms", what, tot);
+        for (int t = 1; t < 10; ++t) if (acc[t] > 0) fprintf(stderr, " | %s %.1f", names[t], acc[t]);
+        fprintf(stderr, "\n");
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear(); tag.clear();
+    }
+};
+static LsTimer g_ls_timer;
+
+// ---- lock-step batched harmonic stage (hpf_lockstep.cuh) ---------------------------------
+static bool use_lockstep(const hpf_t* h, const StructNet& sn, int B) {
+    if (h->struct_state != 3 || h->lockstep == 0) return false;
+    if (sn.nx < 1 || sn.nx > 2048) return false;             // panel kernel: at most 4 rows per thread of 512
+    return h->lockstep == 1 || B >= h->lockstep_min;
+}
+
+template <class K>
+static int ls_grid(hpf_t* h, K kernel, int threads, size_t smem, long long items, int* grid) {
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    if (occ < 1) return fail(h, HPF_E_UNSUPPORTED, "hpf_solve: lock-step kernel does not fit on an SM");
+    long long g = (long long)occ * h->sm_count;
+    if (g > items) g = items;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    return HPF_OK;
+}
+
+// Batched LU with partial pivoting + solve of the systems [ld x (N+1)] of all active slots
+// (ls_panel -> ls_swap_trsm -> ls_update per 32-column panel, ls_backsub).
+static int launch_ls_lu(hpf_t* h, const LsArgs& la, int cur, int N, int nwave, cudaStream_t st) {
+    const size_t cap = (size_t)h->smem_optin;
+    for (int k0 = 0; k0 < N; k0 += LS_NB) {
+        const int rows = N - k0, nb = rows < LS_NB ? rows : LS_NB, cr = k0 + nb;
+        // panel: all-register when every row has a thread, else sub-panels of 8 columns
+        const size_t want = LS_PANEL_FIXED_BYTES + (size_t)rows * nb * sizeof(double);
+        const int staged = want <= cap ? 1 : 0;
+        const size_t psm = staged ? want : (size_t)LS_PANEL_FIXED_BYTES;
+        int grid = 0, rc;
+        if (rows <= 512) {
+            const int T = rows <= 256 ? 256 : 512;
+            rc = ls_grid(h, ls_panel_kernel<1, 32>, T, psm, nwave, &grid);
+            if (rc) return rc;
+            ls_panel_kernel<1, 32><<<grid, T, psm, st>>>(la, cur, N, k0, staged);
+        } else if (rows <= 1024) {
+            rc = ls_grid(h, ls_panel_kernel<2, 8>, 512, psm, nwave, &grid);
+            if (rc) return rc;
+            ls_panel_kernel<2, 8><<<grid, 512, psm, st>>>(la, cur, N, k0, staged);
+        } else {
+            rc = ls_grid(h, ls_panel_kernel<4, 8>, 512, psm, nwave, &grid);
+            if (rc) return rc;
+            ls_panel_kernel<4, 8><<<grid, 512, psm, st>>>(la, cur, N, k0, staged);
+        }
+        g_ls_timer.mark(4);
+        const int nchunk = (N + 1 - cr + 255) / 256;
+        rc = ls_grid(h, ls_swap_trsm_kernel, 256, 0, (long long)nwave * nchunk, &grid);
+        if (rc) return rc;
+        ls_swap_trsm_kernel<<<grid, 256, 0, st>>>(la, cur, N, k0);
+        g_ls_timer.mark(5);
+        h->launches += 2;
+        if (cr < N) {
+            const size_t usm = ((size_t)LS_NB * LUB_SL + (size_t)LS_UT * (LS_NB + 4)) * sizeof(double);
+            const long long ntr = (N - cr + LS_UT - 1) / LS_UT, ntc = (N + 1 - cr + LS_UT - 1) / LS_UT;
+            rc = ls_grid(h, ls_update_kernel, 256, usm, (long long)nwave * ntr * ntc, &grid);
+            if (rc) return rc;
+            ls_update_kernel<<<grid, 256, usm, st>>>(la, cur, N, k0);
+            g_ls_timer.mark(6);
+            h->launches++;
+        }
+    }
+    int grid = 0;
+    int rc = ls_grid(h, ls_backsub_kernel, 256, 0, nwave, &grid);
+    if (rc) return rc;
+    ls_backsub_kernel<<<grid, 256, 0, st>>>(la, cur, N);
+    g_ls_timer.mark(7);
+    h->launches++;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+// Grow-only work area of the lock-step kernels: room for min(B, budget / per_slot) slots; -> slots
+static int ensure_ls(hpf_t* h, size_t per_slot, int B, int* slots) {
+    size_t have = h->ls_bytes > 4096 ? (h->ls_bytes - 4096) / per_slot : 0;
+    if (have < (size_t)B) {
+        size_t budget = h->ls_budget;
+        if (!budget) {
+            size_t fr = 0, tot = 0;
+            CK(cudaMemGetInfo(&fr, &tot));
+            budget = (size_t)(0.4 * (double)(fr + h->ls_bytes));
+            if (budget > ((size_t)64 << 30)) budget = (size_t)64 << 30;
+        }
+        size_t want = budget / per_slot;
+        if (want > (size_t)B) want = (size_t)B;
+        if (want < 1) want = 1;
+        if (want > have) {
+            if (h->d_ls) { CK(cudaDeviceSynchronize()); cudaFree(h->d_ls); h->d_ls = nullptr; h->ls_bytes = 0; }
+            const size_t bytes = per_slot * want + 4096;
+            cudaError_t e = cudaMalloc(&h->d_ls, bytes);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(h, e == cudaErrorMemoryAllocation ? HPF_E_NOMEM : HPF_E_CUDA,
+                            std::string("lock-step work areas: ") + cudaGetErrorString(e));
+            }
+            h->ls_bytes = bytes;
+            have = want;
+        }
+    }
+    *slots = (int)(have < (size_t)B ? have : (size_t)B);
+    return HPF_OK;
+}
+
+// hpf_lu_solve for systems beyond shared memory through the batched LU (all matrices panel by panel)
+static int lu_solve_batched(hpf_t* h, int N, int B, const double* J, size_t stride, const double* f, double* dx,
+                            int* info, cudaStream_t st) {
+    const int ldb = lub_ld(N);
+    const size_t mat_stride = ((size_t)ldb * (N + 1) + 15) / 16 * 16;
+    const size_t per_slot = mat_stride * sizeof(double) + (size_t)(LS_PERM_INTS + 8) * sizeof(int);
+    int S = 0;
+    int rc = ensure_ls(h, per_slot, B, &S);
+    if (rc) return rc;
+    LsArgs la;
+    memset(&la, 0, sizeof(la));
+    la.B = B; la.S = S; la.ldb = ldb; la.mat_stride = mat_stride;
+    char* p = reinterpret_cast<char*>(h->d_ls);
+    la.M = reinterpret_cast<double*>(p); p += mat_stride * sizeof(double) * (size_t)S;
+    int* ip = reinterpret_cast<int*>(p);
+    la.act = ip;  ip += 2 * (size_t)S;
+    la.flag = ip; ip += S;
+    la.itc = ip;  ip += S;
+    la.stat = ip; ip += S;
+    la.info = ip; ip += S;
+    la.nact = ip; ip += 2;
+    la.perm = ip;
+    const long long nt = (N + 31) / 32;
+    for (int b0 = 0; b0 < B; b0 += S) {
+        la.b0 = b0;
+        la.nwave = (B - b0 < S) ? B - b0 : S;
+        ls_init_kernel<<<(S + 255) / 256, 256, 0, st>>>(la);
+        const long long items = (long long)la.nwave * nt * nt;
+        ls_lu_load_kernel<<<(unsigned)std::min<long long>(items, (long long)h->sm_count * 8), 256, 0, st>>>(la, N, J, stride, f);
+        rc = launch_ls_lu(h, la, 0, N, la.nwave, st);
+        if (rc) return rc;
+        const long long tot = (long long)la.nwave * N;
+        ls_lu_store_kernel<<<(unsigned)std::min<long long>((tot + 255) / 256, (long long)h->sm_count * 8), 256, 0, st>>>(la, N, dx, info);
+        h->launches += 3;
+    }
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+static int launch_lockstep(hpf_t* h, const DevNet& net, const StructNet& sn, const HarmTileArgs& ha, cudaStream_t st) {
+    const int nx = sn.nx, nZ = sn.nZ, m = net.m, q = net.q;
+    const int ldb = lub_ld(nx);
+    const size_t mat_stride = ((size_t)ldb * (nx + 1) + 15) / 16 * 16;
+    const size_t state_stride = (scn_smem_doubles_aligned(net.n, net.H, net.q, net.N) + 15) / 16 * 16;
+    const size_t per_slot = (mat_stride + state_stride) * sizeof(double) + ((size_t)m + nZ + q) * sizeof(double2) +
+                            (size_t)(LS_PERM_INTS + 8) * sizeof(int);
+    // slots: the whole batch when it fits the memory budget, else waves
+    {
+        int rcs = ensure_ls(h, per_slot, ha.B, &h->ls_slots);
+        if (rcs) return rcs;
+    }
+    const int S = h->ls_slots;
+    LsArgs la;
+    la.B = ha.B; la.S = S; la.flags = ha.flags; la.P = ha.P; la.Q = ha.Q; la.I_N = ha.I_N; la.wN = ha.wN;
+    la.thresh_h = ha.thresh_h; la.max_h = ha.max_h; la.V_m = ha.V_m; la.V_a = ha.V_a; la.I_inj = ha.I_inj;
+    la.n_iter_h = ha.n_iter_h; la.status = ha.status; la.err_h = ha.err_h; la.hist_h = ha.hist_h;
+    {
+        char* p = reinterpret_cast<char*>(h->d_ls);
+        la.M = reinterpret_cast<double*>(p);      p += mat_stride * sizeof(double) * (size_t)S;
+        la.state = reinterpret_cast<double*>(p);  p += state_stride * sizeof(double) * (size_t)S;
+        la.X = reinterpret_cast<double2*>(p);     p += (size_t)m * S * sizeof(double2);
+        la.GX = reinterpret_cast<double2*>(p);    p += (size_t)nZ * S * sizeof(double2);
+        la.U0 = reinterpret_cast<double2*>(p);    p += (size_t)q * S * sizeof(double2);
+        int* ip = reinterpret_cast<int*>(p);
+        la.act = ip;  ip += 2 * (size_t)S;
+        la.flag = ip; ip += S;
+        la.itc = ip;  ip += S;
+        la.stat = ip; ip += S;
+        la.info = ip; ip += S;
+        la.nact = ip; ip += 2;
+        la.perm = ip;
+    }
+    la.mat_stride = mat_stride; la.state_stride = state_stride; la.ldb = ldb;
+    int g_mis = 0, g_bor = 0, rc;
+    rc = ls_grid(h, ls_mismatch_kernel, 256, 0, S, &g_mis);
+    if (rc) return rc;
+    const long long btiles = (long long)((m - 1 + 31) / 32) * ((nx + 1 + 31) / 32);
+    rc = ls_grid(h, ls_border_kernel, 256, 0, (long long)S * btiles, &g_bor);
+    if (rc) return rc;
+    const int g_el = (int)std::min<long long>(((long long)S * m + 255) / 256, (long long)h->sm_count * 8);
+    g_ls_timer.on = getenv("HPF_LS_TIMING") != nullptr && !stream_capturing(st);
+    g_ls_timer.st = st;
+    for (int b0 = 0; b0 < ha.B; b0 += S) {
+        la.b0 = b0;
+        la.nwave = (ha.B - b0 < S) ? ha.B - b0 : S;
+        ls_init_kernel<<<(S + 255) / 256, 256, 0, st>>>(la);
+        h->launches++;
+        g_ls_timer.mark(0);
+        for (int r = 0; r <= ha.max_h; ++r) {
+            const int cur = r & 1, nxt = cur ^ 1;
+            ls_mismatch_kernel<<<g_mis, 256, 0, st>>>(net, sn, la, cur, r == 0);
+            ls_compact_kernel<<<1, 1024, 0, st>>>(la, cur);
+            h->launches += 2;
+            g_ls_timer.mark(1);
+            if (r == ha.max_h) break;
+            ls_pack_vf_kernel<<<g_el, 256, 0, st>>>(net, la, nxt);
+            h->launches++;
+            if (q > 0) {
+                rc = launch_zgemm(h, q, la.nwave, m, sn.G, (size_t)m, la.X, (size_t)S, la.U0, (size_t)S, st, false, la.nact + nxt);
+                if (rc) return rc;
+            }
+            g_ls_timer.mark(2);
+            ls_border_kernel<<<g_bor, 256, 0, st>>>(net, sn, la, nxt);
+            h->launches++;
+            g_ls_timer.mark(3);
+            rc = launch_ls_lu(h, la, nxt, nx, la.nwave, st);
+            if (rc) return rc;
+            ls_uf_kernel<<<g_el, 256, 0, st>>>(net, sn, la, nxt);
+            h->launches++;
+            rc = launch_zgemm(h, nZ, la.nwave, m, sn.G, (size_t)m, la.X, (size_t)S, la.GX, (size_t)S, st, false, la.nact + nxt);
+            if (rc) return rc;
+            g_ls_timer.mark(8);
+        }
+    }
+    g_ls_timer.report("harmonic stage");
+    g_ls_timer.on = false;
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
 static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, const double* I_N,
                             double thresh_f, int max_f, double thresh_h, int max_h, int flags,
                             double* V_m, double* V_a, double* I_inj, int* n_iter_f, int* n_iter_h,
@@ -1935,7 +2204,7 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
         ha.thresh_h = thresh_h; ha.max_h = max_h; ha.V_m = V_m; ha.V_a = V_a; ha.I_inj = (double2*)I_inj;
         ha.n_iter_h = n_iter_h; ha.status = status; ha.err_h = err_h; ha.work_counter = h->d_counter + h->cur_slot;
         ha.dx_out = nullptr; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0; ha.hist_h = hist_h; ha.epoch = h->hw_epoch;
-        rc = launch_harm(h, net, sn, ha, true, st);
+        rc = use_lockstep(h, sn, B) ? launch_lockstep(h, net, sn, ha, st) : launch_harm(h, net, sn, ha, true, st);
         if (rc) return rc;
     }
     if (h->profiling) { CK(cudaEventRecord(h->ev[2], st)); h->ev_valid = 1; }
@@ -2012,6 +2281,9 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_NO_SPECIALISE")) h->no_specialise = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_MISMATCH_TILE")) h->mismatch_tile = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_STRUCT_VARIANT")) h->force_variant = atoi(ev);
+    if (const char* ev = getenv("HPF_LOCKSTEP")) h->lockstep = atoi(ev) ? 1 : 0;
+    if (const char* ev = getenv("HPF_LOCKSTEP_MIN")) h->lockstep_min = atoi(ev) > 0 ? atoi(ev) : 1;
+    if (const char* ev = getenv("HPF_LOCKSTEP_GB")) h->ls_budget = (size_t)(atof(ev) > 0 ? atof(ev) * 1073741824.0 : 0);
     if (const char* ev = getenv("HPF_DENSE_BLOCKED")) h->dense_blocked = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_LU_CLASSIC")) h->lu_classic = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_GJ_SINGLE_MAX")) h->gj_single_max = atoi(ev);
@@ -2046,7 +2318,7 @@ int hpf_destroy(hpf_t* h) {
     cudaFree(h->d_R); cudaFree(h->d_X); cudaFree(h->d_G); cudaFree(h->d_B); cudaFree(h->d_Xsh);
     cudaFree(h->d_Y); cudaFree(h->d_YN); cudaFree(h->d_counter); cudaFree(h->d_work); cudaFree(h->d_io); cudaFree(h->d_Ainv); cudaFree(h->d_Gz);
     cudaFree(h->d_WNL); cudaFree(h->d_wN); cudaFree(h->d_GzT); cudaFree(h->d_nbr_ptr); cudaFree(h->d_nbr_idx);
-    cudaFree(h->d_gstate); cudaFree(h->d_ell_col); cudaFree(h->d_tau); cudaFree(h->d_phase);
+    cudaFree(h->d_gstate); cudaFree(h->d_ls); cudaFree(h->d_ell_col); cudaFree(h->d_tau); cudaFree(h->d_phase);
     for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 4; ++i) if (h->st_io[i]) cudaStreamDestroy(h->st_io[i]);
     for (int i = 0; i < 16; ++i) if (h->ev_io[i]) cudaEventDestroy(h->ev_io[i]);
@@ -2667,6 +2939,8 @@ static int lu_solve_impl(hpf_t* h, int B, const double* J, const double* f, doub
              : big ? prep_kernel(h, lu_solve_kernel<2>, smem, "hpf_lu_solve", &occ, HPF_THREADS_GMEM)
                    : prep_kernel(h, lu_solve_kernel<1>, smem, "hpf_lu_solve", &occ, HPF_THREADS_GMEM);
     if (rc) return rc;
+    if (gm && !ws_smem && net.N <= 2048 && (h->lockstep == 1 || (h->lockstep != 0 && B >= h->lockstep_min)))
+        return lu_solve_batched(h, net.N, B, J, a.stride, f, dx, info, (cudaStream_t)stream);
     long long grid = (long long)occ * h->sm_count;
     if (grid > B) grid = B;
     a.workspace = nullptr;

@@ -39,14 +39,21 @@ __device__ __forceinline__ void zg_cp16(double2* sdst, const double2* gsrc, cons
 }
 
 // SUB = false: C = A B;  SUB = true: C -= A B (the deferred rank-64 update of the blocked Gauss-Jordan)
+// n_dev (optional): the number of columns actually in use lives in device memory (the lock-step Newton
+// rounds of hpf_lockstep.cuh launch without knowing how many scenarios are still active): column tiles
+// beyond it exit at once.
 template <bool SUB>
 __global__ void __launch_bounds__(256, 2)
-zgemm_dmma_kernel(const int M, const int N, const int K, const double2* __restrict__ A, const size_t lda,
-                  const double2* __restrict__ B, const size_t ldb, double2* __restrict__ C, const size_t ldc) {
+zgemm_dmma_kernel(const int M, const int N_, const int K, const double2* __restrict__ A, const size_t lda,
+                  const double2* __restrict__ B, const size_t ldb, double2* __restrict__ C, const size_t ldc,
+                  const int* __restrict__ n_dev) {
     extern __shared__ __align__(16) double2 zsm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp & 3, wn = warp >> 2;                   // warp grid 4 (M) x 2 (N)
     const int m0 = blockIdx.y * ZG_BM, n0 = blockIdx.x * ZG_BN;
+    int N = N_;
+    if (n_dev) { const int nd = *n_dev; N = nd < N_ ? nd : N_; }
+    if (n0 >= N) return;
     const int nk = (K + ZG_BK - 1) / ZG_BK;
 
     auto stage_load = [&](const int kt, const int st) {
