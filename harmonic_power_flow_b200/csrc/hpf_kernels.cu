@@ -1090,6 +1090,8 @@ struct hpf_handle {
     void* d_ls = nullptr;         // one allocation: state slabs | border systems | X | GX | U0 | ints
     size_t ls_bytes = 0;
     int ls_slots = 0;
+    int ls_upd = 0;               // $HPF_LS_UPD=big|direct: rank-64 update with 128 x 64 tiles of 8 warps, 2 CTAs per SM (1) / barrier-free, fragments straight from L1 / L2 (2); default: 64 x 64 tiles of 4 warps, 3 CTAs per SM (A/B: profiles/r3_lockstep_ab.txt)
+    int ls_no_pair = 0;           // $HPF_LS_NO_PAIR=1: rank-32 update after every panel (A/B against the paired rank-64 update)
     // host mirror of the network constants for kernels that take them as parameters
     // (constant bank): fetched lazily from the device tables, see host_consts()
     std::vector<double2> hY, hYN, hWNL, hG;
@@ -1950,9 +1952,9 @@ static int ls_grid(hpf_t* h, K kernel, int threads, size_t smem, long long items
 // (ls_panel -> ls_swap_trsm -> ls_update per 32-column panel, ls_backsub).
 static int launch_ls_lu(hpf_t* h, const LsArgs& la, int cur, int N, int nwave, cudaStream_t st) {
     const size_t cap = (size_t)h->smem_optin;
-    for (int k0 = 0; k0 < N; k0 += LS_NB) {
-        const int rows = N - k0, nb = rows < LS_NB ? rows : LS_NB, cr = k0 + nb;
-        // panel: all-register when every row has a thread, else sub-panels of 8 columns
+    auto panel = [&](int k0, int left) -> int {
+        const int rows = N - k0, nb = rows < LS_NB ? rows : LS_NB;
+        // all-register when every row has a thread, else sub-panels of 8 columns; staged in shared memory when it fits
         const size_t want = LS_PANEL_FIXED_BYTES + (size_t)rows * nb * sizeof(double);
         const int staged = want <= cap ? 1 : 0;
         const size_t psm = staged ? want : (size_t)LS_PANEL_FIXED_BYTES;
@@ -1961,35 +1963,78 @@ static int launch_ls_lu(hpf_t* h, const LsArgs& la, int cur, int N, int nwave, c
             const int T = rows <= 256 ? 256 : 512;
             rc = ls_grid(h, ls_panel_kernel<1, 32>, T, psm, nwave, &grid);
             if (rc) return rc;
-            ls_panel_kernel<1, 32><<<grid, T, psm, st>>>(la, cur, N, k0, staged);
+            ls_panel_kernel<1, 32><<<grid, T, psm, st>>>(la, cur, N, k0, staged, left);
         } else if (rows <= 1024) {
             rc = ls_grid(h, ls_panel_kernel<2, 8>, 512, psm, nwave, &grid);
             if (rc) return rc;
-            ls_panel_kernel<2, 8><<<grid, 512, psm, st>>>(la, cur, N, k0, staged);
+            ls_panel_kernel<2, 8><<<grid, 512, psm, st>>>(la, cur, N, k0, staged, left);
         } else {
             rc = ls_grid(h, ls_panel_kernel<4, 8>, 512, psm, nwave, &grid);
             if (rc) return rc;
-            ls_panel_kernel<4, 8><<<grid, 512, psm, st>>>(la, cur, N, k0, staged);
+            ls_panel_kernel<4, 8><<<grid, 512, psm, st>>>(la, cur, N, k0, staged, left);
         }
         g_ls_timer.mark(4);
-        const int nchunk = (N + 1 - cr + 255) / 256;
-        rc = ls_grid(h, ls_swap_trsm_kernel, 256, 0, (long long)nwave * nchunk, &grid);
+        h->launches++;
+        return HPF_OK;
+    };
+    auto swap_trsm = [&](int k0, int pair) -> int {
+        const int nb = (N - k0) < LS_NB ? (N - k0) : LS_NB, cr = k0 + nb;
+        const int nchunk = (N + 1 - cr + LS_ST - 1) / LS_ST;
+        int grid = 0;
+        int rc = ls_grid(h, ls_swap_trsm_kernel, LS_ST, 0, (long long)nwave * nchunk, &grid);
         if (rc) return rc;
-        ls_swap_trsm_kernel<<<grid, 256, 0, st>>>(la, cur, N, k0);
+        ls_swap_trsm_kernel<<<grid, LS_ST, 0, st>>>(la, cur, N, k0, pair);
         g_ls_timer.mark(5);
-        h->launches += 2;
-        if (cr < N) {
-            const size_t usm = ((size_t)LS_NB * LUB_SL + (size_t)LS_UT * (LS_NB + 4)) * sizeof(double);
-            const long long ntr = (N - cr + LS_UT - 1) / LS_UT, ntc = (N + 1 - cr + LS_UT - 1) / LS_UT;
-            rc = ls_grid(h, ls_update_kernel, 256, usm, (long long)nwave * ntr * ntc, &grid);
+        h->launches++;
+        return HPF_OK;
+    };
+    auto update = [&](int K, int kb, int rlo, int clo, int chi) -> int {
+        if (rlo >= N || clo > chi) return HPF_OK;
+        int grid = 0, rc;
+        auto go = [&](auto kernel, int TR, int TC, int NT) -> int {
+            const size_t usm = ((size_t)K * (TR + 4) + (size_t)TC * (K + 4)) * sizeof(double);
+            const long long ntr = (N - rlo + TR - 1) / TR, ntc = (chi + 1 - clo + TC - 1) / TC;
+            rc = ls_grid(h, kernel, NT, usm, (long long)nwave * ntr * ntc, &grid);
             if (rc) return rc;
-            ls_update_kernel<<<grid, 256, usm, st>>>(la, cur, N, k0);
-            g_ls_timer.mark(6);
-            h->launches++;
+            kernel<<<grid, NT, usm, st>>>(la, cur, N, kb, rlo, clo, chi);
+            return HPF_OK;
+        };
+        if (K == 64 && h->ls_upd == 2) {
+            const long long nsr = (N - rlo + 31) / 32, nsc = (chi + 1 - clo + 31) / 32;
+            rc = ls_grid(h, ls_update_direct_kernel<64>, 128, 0, ((long long)nwave * nsr * nsc + 3) / 4, &grid);
+            if (rc) return rc;
+            ls_update_direct_kernel<64><<<grid, 128, 0, st>>>(la, cur, N, kb, rlo, clo, chi);
+        } else if (K == 64) rc = h->ls_upd == 1 ? go(ls_update_kernel<64, 128, 64, 256, 2>, 128, 64, 256)
+                                                : go(ls_update_kernel<64, 64, 64, 128, 3>, 64, 64, 128);
+        else rc = go(ls_update_kernel<32, 128, 128, 256, 2>, 128, 128, 256);
+        if (rc) return rc;
+        g_ls_timer.mark(6);
+        h->launches++;
+        return HPF_OK;
+    };
+    int rc;
+    for (int k0 = 0; k0 < N;) {
+        const int rows = N - k0, nb = rows < LS_NB ? rows : LS_NB, cr = k0 + nb;
+        const bool pair = nb == LS_NB && N - cr >= LS_NB && !h->ls_no_pair;
+        if ((rc = panel(k0, 0))) return rc;
+        if ((rc = swap_trsm(k0, 0))) return rc;
+        if (!pair) {
+            if ((rc = update(32, k0, cr, cr, N))) return rc;
+            k0 = cr;
+            continue;
         }
+        // pair of panels: the first one is applied to the second one's 32 columns only; after the second
+        // one is factored (its interchanges also move the first one's L21) and its pivot rows have taken
+        // the first one's contribution (ls_swap_trsm, pair), the rest takes both in ONE rank-64 pass
+        const int k1 = cr, c2 = k1 + LS_NB;
+        if ((rc = update(32, k0, k1, k1, c2 - 1))) return rc;
+        if ((rc = panel(k1, LS_NB))) return rc;
+        if ((rc = swap_trsm(k1, 1))) return rc;
+        if ((rc = update(64, k0, c2, c2, N))) return rc;
+        k0 = c2;
     }
     int grid = 0;
-    int rc = ls_grid(h, ls_backsub_kernel, 256, 0, nwave, &grid);
+    rc = ls_grid(h, ls_backsub_kernel, 256, 0, nwave, &grid);
     if (rc) return rc;
     ls_backsub_kernel<<<grid, 256, 0, st>>>(la, cur, N);
     g_ls_timer.mark(7);
@@ -2064,6 +2109,87 @@ static int lu_solve_batched(hpf_t* h, int N, int B, const double* J, size_t stri
         ls_lu_store_kernel<<<(unsigned)std::min<long long>((tot + 255) / 256, (long long)h->sm_count * 8), 256, 0, st>>>(la, N, dx, info);
         h->launches += 3;
     }
+    CK(cudaGetLastError());
+    return HPF_OK;
+}
+
+static void ls_carve_ints(LsArgs& la, char* p, int S) {
+    int* ip = reinterpret_cast<int*>(p);
+    la.act = ip;  ip += 2 * (size_t)S;
+    la.flag = ip; ip += S;
+    la.itc = ip;  ip += S;
+    la.stat = ip; ip += S;
+    la.info = ip; ip += S;
+    la.nact = ip; ip += 2;
+    la.perm = ip;
+}
+
+// fundamental stage of the large networks in lock step (dense Jacobians of order Nf through the batched LU)
+static bool use_lockstep_fund(const hpf_t* h, int B) {
+    if (h->struct_state != 3 || h->lockstep == 0) return false;
+    const int Nf = 2 * h->n - 1 - h->c;
+    if (Nf < 1 || Nf > 2048) return false;
+    return h->lockstep == 1 || B >= h->lockstep_min;
+}
+
+static int launch_lockstep_fund(hpf_t* h, int B, const double* P, const double* Q, double thresh_f, int max_f,
+                                double* V_m, double* V_a, int* n_iter_f, int* status, double* hist_f, cudaStream_t st) {
+    DevNet nf = devnet(h);
+    const int H_full = nf.H, Nf = nf.Nf;
+    nf.N = Nf; nf.H = 1; nf.nH = nf.n;
+    const int ldb = lub_ld(Nf);
+    const size_t mat_stride = ((size_t)ldb * (Nf + 1) + 15) / 16 * 16;
+    const size_t state_stride = (scn_smem_doubles_aligned(nf.n, 1, nf.q, Nf) + 15) / 16 * 16;
+    const size_t per_slot = (mat_stride + state_stride) * sizeof(double) + (size_t)(LS_PERM_INTS + 8) * sizeof(int);
+    int S = 0;
+    int rc = ensure_ls(h, per_slot, B, &S);
+    if (rc) return rc;
+    LsArgs la;
+    memset(&la, 0, sizeof(la));
+    la.B = B; la.S = S; la.P = P; la.Q = Q; la.thresh_h = thresh_f; la.max_h = max_f; la.V_m = V_m; la.V_a = V_a;
+    la.n_iter_h = n_iter_f; la.status = status; la.hist_h = hist_f;
+    la.ldb = ldb; la.mat_stride = mat_stride; la.state_stride = state_stride;
+    {
+        char* p = reinterpret_cast<char*>(h->d_ls);
+        la.M = reinterpret_cast<double*>(p);      p += mat_stride * sizeof(double) * (size_t)S;
+        la.state = reinterpret_cast<double*>(p);  p += state_stride * sizeof(double) * (size_t)S;
+        ls_carve_ints(la, p, S);
+    }
+    int g_mis = 0, g_jac = 0;
+    rc = ls_grid(h, ls_fund_mismatch_kernel, 256, 0, S, &g_mis);
+    if (rc) return rc;
+    rc = ls_grid(h, ls_fund_jac_kernel, 256, 0, S, &g_jac);
+    if (rc) return rc;
+    g_ls_timer.on = getenv("HPF_LS_TIMING") != nullptr && !stream_capturing(st);
+    g_ls_timer.st = st;
+    for (int b0 = 0; b0 < B; b0 += S) {
+        la.b0 = b0;
+        la.nwave = (B - b0 < S) ? B - b0 : S;
+        ls_init_kernel<<<(S + 255) / 256, 256, 0, st>>>(la);
+        h->launches++;
+        g_ls_timer.mark(0);
+        for (int r = 0; r <= max_f; ++r) {
+            const int cur = r & 1, nxt = cur ^ 1;
+            ls_fund_mismatch_kernel<<<g_mis, 256, 0, st>>>(nf, la, cur, r == 0);
+            ls_compact_kernel<<<1, 1024, 0, st>>>(la, cur);
+            h->launches += 2;
+            g_ls_timer.mark(1);
+            if (r == max_f) break;
+            ls_fund_jac_kernel<<<g_jac, 256, 0, st>>>(nf, la, nxt);
+            h->launches++;
+            g_ls_timer.mark(3);
+            rc = launch_ls_lu(h, la, nxt, Nf, la.nwave, st);
+            if (rc) return rc;
+        }
+    }
+    if (H_full > 1) {
+        const size_t cnt = (size_t)(H_full - 1) * nf.n * B;
+        flat_start_fill_kernel<<<(unsigned)((cnt + 255) / 256 < 65535 * 8 ? (cnt + 255) / 256 : 65535 * 8), 256, 0, st>>>(
+            V_m + (size_t)nf.n * B, V_a + (size_t)nf.n * B, cnt);
+        h->launches++;
+    }
+    g_ls_timer.report("fundamental stage");
+    g_ls_timer.on = false;
     CK(cudaGetLastError());
     return HPF_OK;
 }
@@ -2162,8 +2288,10 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
     if (h->profiling) { CK(cudaEventRecord(h->ev[0], st)); }
     // fundamental stage: one lane per scenario (variant 1) or the per-CTA kernel (variant 2)
     if (h->struct_state >= 2) {
-        int rc = solve_common(h, 1, B, P, Q, nullptr, thresh_f, max_f, 0.0, 0, 0, V_m, V_a, nullptr, n_iter_f,
-                              nullptr, nullptr, nullptr, status, hist_f, nullptr, st);
+        int rc = use_lockstep_fund(h, B)
+                     ? launch_lockstep_fund(h, B, P, Q, thresh_f, max_f, V_m, V_a, n_iter_f, status, hist_f, st)
+                     : solve_common(h, 1, B, P, Q, nullptr, thresh_f, max_f, 0.0, 0, 0, V_m, V_a, nullptr, n_iter_f,
+                                    nullptr, nullptr, nullptr, status, hist_f, nullptr, st);
         if (rc) return rc;
         CK(cudaMemsetAsync(h->d_counter + h->cur_slot, 0, sizeof(int), st));     // solve_common used the counter
     } else {
@@ -2282,6 +2410,8 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_MISMATCH_TILE")) h->mismatch_tile = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_STRUCT_VARIANT")) h->force_variant = atoi(ev);
     if (const char* ev = getenv("HPF_LOCKSTEP")) h->lockstep = atoi(ev) ? 1 : 0;
+    if (const char* ev = getenv("HPF_LS_UPD")) h->ls_upd = (strcmp(ev, "big") == 0) ? 1 : (strcmp(ev, "direct") == 0) ? 2 : 0;
+    if (const char* ev = getenv("HPF_LS_NO_PAIR")) h->ls_no_pair = atoi(ev) ? 1 : 0;
     if (const char* ev = getenv("HPF_LOCKSTEP_MIN")) h->lockstep_min = atoi(ev) > 0 ? atoi(ev) : 1;
     if (const char* ev = getenv("HPF_LOCKSTEP_GB")) h->ls_budget = (size_t)(atof(ev) > 0 ? atof(ev) * 1073741824.0 : 0);
     if (const char* ev = getenv("HPF_DENSE_BLOCKED")) h->dense_blocked = atoi(ev) ? 1 : 0;

