@@ -175,7 +175,15 @@ def run_other_configs(torch, dist, BatchSolver, scenarios, local, rank, world, f
         nnzY = int((sol.Y != 0).sum().item())
         fl, fl_iter = structured_flops(net.n, net.H, net.m, net.c, net.q, nnzY, vals[3].item(), vals[2].item(), B)
         ach = fl / (ms / 1e3) / 1e12                               # this rank's flops over this rank's time
+        path = sol.last_solve_path
+        sol.set_profiling(True)
+        sol.solve(dP, dQ, dI, out=r)
+        torch.cuda.synchronize()
+        kms = sol.last_kernel_ms()
+        sol.set_profiling(False)
         out.append({"config": label, "batch_per_gpu": B, "N": int(sol.N), "strategy_variant": int(info["available"]),
+                    "harmonic_stage_path": BatchSolver.PATHS.get(path, str(path)),
+                    "kernel_ms_per_step": {"fundamental_stage": kms[0], "harmonic_stage": kms[1]},
                     "value": sm[1].item() / (mx[0].item() / 1e3), "unit": UNIT, "ms_per_step": mx[0].item(),
                     "converged_fraction": sm[1].item() / (B * world),
                     "mean_harmonic_iterations": sm[2].item() / (B * world),

@@ -55,6 +55,7 @@ SIGNATURES = {
     "hpf_dim_N": (_i, [_vp]),
     "hpf_dim_Nf": (_i, [_vp]),
     "hpf_launch_count": (_ll, [_vp]),
+    "hpf_last_solve_path": (_i, [_vp]),
 }
 
 _lib = None

@@ -1090,6 +1090,7 @@ struct hpf_handle {
     void* d_ls = nullptr;         // one allocation: state slabs | border systems | X | GX | U0 | ints
     size_t ls_bytes = 0;
     int ls_slots = 0;
+    int last_path = 0;            // hpf_last_solve_path
     int ls_upd = 0;               // $HPF_LS_UPD=big|direct: rank-64 update with 128 x 64 tiles of 8 warps, 2 CTAs per SM (1) / barrier-free, fragments straight from L1 / L2 (2); default: 64 x 64 tiles of 4 warps, 3 CTAs per SM (A/B: profiles/r3_lockstep_ab.txt)
     int ls_no_pair = 0;           // $HPF_LS_NO_PAIR=1: rank-32 update after every panel (A/B against the paired rank-64 update)
     // host mirror of the network constants for kernels that take them as parameters
@@ -2332,8 +2333,10 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
         ha.thresh_h = thresh_h; ha.max_h = max_h; ha.V_m = V_m; ha.V_a = V_a; ha.I_inj = (double2*)I_inj;
         ha.n_iter_h = n_iter_h; ha.status = status; ha.err_h = err_h; ha.work_counter = h->d_counter + h->cur_slot;
         ha.dx_out = nullptr; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0; ha.hist_h = hist_h; ha.epoch = h->hw_epoch;
-        rc = use_lockstep(h, sn, B) ? launch_lockstep(h, net, sn, ha, st) : launch_harm(h, net, sn, ha, true, st);
+        const bool ls = use_lockstep(h, sn, B);
+        rc = ls ? launch_lockstep(h, net, sn, ha, st) : launch_harm(h, net, sn, ha, true, st);
         if (rc) return rc;
+        h->last_path = ls ? 4 : (h->struct_state >= 2 ? h->struct_state : 1);
     }
     if (h->profiling) { CK(cudaEventRecord(h->ev[2], st)); h->ev_valid = 1; }
     return HPF_OK;
@@ -2630,6 +2633,7 @@ int hpf_last_kernel_ms(hpf_t* h, double* ms) {
 int hpf_dim_N(const hpf_t* h) { return (h && h->have_net) ? 2 * h->n * h->H - 1 - h->c : 0; }
 int hpf_dim_Nf(const hpf_t* h) { return (h && h->have_net) ? 2 * h->n - 1 - h->c : 0; }
 long long hpf_launch_count(const hpf_t* h) { return h ? h->launches : 0; }
+int hpf_last_solve_path(const hpf_t* h) { return h ? h->last_path : 0; }
 
 long long hpf_jacobian_stride(const hpf_t* h) {
     if (!h || !h->have_net) return 0;
@@ -2659,8 +2663,10 @@ static int solve_dispatch(hpf_t* h, int B, const double* P, const double* Q, con
                                     V_m, V_a, I_inj, n_iter_f, n_iter_h, err_h, status, err_hist_f, err_hist_h,
                                     (cudaStream_t)stream);
     }
-    return solve_common(h, 0, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a,
-                        I_inj, n_iter_f, n_iter_h, err_h, nullptr, status, err_hist_f, err_hist_h, stream);
+    const int rcd = solve_common(h, 0, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a,
+                                 I_inj, n_iter_f, n_iter_h, err_h, nullptr, status, err_hist_f, err_hist_h, stream);
+    if (h && rcd == HPF_OK && B > 0) h->last_path = 5;
+    return rcd;
 }
 
 extern "C" {

@@ -162,6 +162,14 @@ class BatchSolver:
     def launch_count(self):
         return int(self.lib.hpf_launch_count(self._h))
 
+    PATHS = {0: "none", 1: "lane-per-scenario / one-warp-per-harmonic kernels", 2: "one CTA per scenario (shared memory)",
+             3: "one CTA per scenario (global-memory state)", 4: "lock-step batched rounds", 5: "dense Jacobian + LU"}
+
+    @property
+    def last_solve_path(self):
+        """Which kernels the last solve ran for the harmonic stage (hpf_last_solve_path)."""
+        return int(self.lib.hpf_last_solve_path(self._h))
+
     # -- kernel 1 ----------------------------------------------------------------------
     def build_Y(self):
         """Y(h) [H, n, n] complex128 on the device (HG:132-171)."""

@@ -307,6 +307,17 @@ int hpf_dim_Nf(const hpf_t* h);
  */
 long long hpf_launch_count(const hpf_t* h);
 
+/*
+ * Which kernels the last hpf_solve / hpf_solve_host of this handle ran for the harmonic
+ * stage (HG:531-542; diagnostics for tests and bench.py): 0 none yet, 1 lane-per-scenario
+ * tile / one-warp-per-harmonic kernels (small networks), 2 one CTA per scenario, state in
+ * shared memory, 3 one CTA per scenario, state in global memory (large networks, small
+ * batches), 4 lock-step batched rounds (large networks: batched tensor-core LU of the
+ * border systems, G products as complex GEMMs), 5 dense Jacobian + LU (HPF_SOLVE_DENSE
+ * or structured set-up not available).
+ */
+int hpf_last_solve_path(const hpf_t* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1296,9 +1296,10 @@ def test_lockstep_path_against_oracle_and_cta_path(kind, n, B, tmp_path, monkeyp
     P, Q, I_N = scenarios.make_batch(net, B, "tight")
     n0 = sol.launch_count
     r = sol.solve(P, Q, I_N, history=True)
-    assert sol.launch_count - n0 > 50, "the lock-step path did not run"
+    assert sol.launch_count - n0 > 50 and sol.last_solve_path == 4, "the lock-step path did not run"
     res = r.to_host()
     ref = cta.solve(P, Q, I_N, history=True).to_host()
+    assert cta.last_solve_path == 3
     assert (res["status"] == 0).all()
     # The iteration count of these networks is decided by round-off in ~10 % of the scenarios (the oracle
     # with a LAPACK step against the oracle with the reference's SuperLU step: 19 of 150 on the 70-bus
