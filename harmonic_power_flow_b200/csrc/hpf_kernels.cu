@@ -1091,7 +1091,7 @@ struct hpf_handle {
     size_t ls_bytes = 0;
     int ls_slots = 0;
     int last_path = 0;            // hpf_last_solve_path
-    int ls_upd = 0;               // $HPF_LS_UPD=big|direct: rank-64 update with 128 x 64 tiles of 8 warps, 2 CTAs per SM (1) / barrier-free, fragments straight from L1 / L2 (2); default: 64 x 64 tiles of 4 warps, 3 CTAs per SM (A/B: profiles/r3_lockstep_ab.txt)
+    int ls_upd = 0;               // $HPF_LS_UPD=big|direct: rank-64 update with 128 x 64 tiles of 8 warps, 2 CTAs per SM (1) / barrier-free, fragments straight from L1 / L2 (2); default: 64 x 64 tiles of 4 warps, 3 CTAs per SM (A/B: profiles/r2_lockstep_ab.txt)
     int ls_no_pair = 0;           // $HPF_LS_NO_PAIR=1: rank-32 update after every panel (A/B against the paired rank-64 update)
     // host mirror of the network constants for kernels that take them as parameters
     // (constant bank): fetched lazily from the device tables, see host_consts()
@@ -1995,7 +1995,8 @@ static int launch_ls_lu(hpf_t* h, const LsArgs& la, int cur, int N, int nwave, c
         auto go = [&](auto kernel, int TR, int TC, int NT) -> int {
             const size_t usm = ((size_t)K * (TR + 4) + (size_t)TC * (K + 4)) * sizeof(double);
             const long long ntr = (N - rlo + TR - 1) / TR, ntc = (chi + 1 - clo + TC - 1) / TC;
-            rc = ls_grid(h, kernel, NT, usm, (long long)nwave * ntr * ntc, &grid);
+            (void)ntc;
+            rc = ls_grid(h, kernel, NT, usm, (long long)nwave * ntr, &grid);   // (strips: row tiles of the matrices)
             if (rc) return rc;
             kernel<<<grid, NT, usm, st>>>(la, cur, N, kb, rlo, clo, chi);
             return HPF_OK;

@@ -29,7 +29,7 @@
 
 #define LS_NB 32                   // panel width
 #define LS_PERM_INTS 100           // per slot: srcTop[32] | cnt | mvSrc[32] | mvDst[32]
-#define LS_PANEL_FIXED_BYTES (2048 * 4 + 16 * 32 * 8 + 32 * 32 * 8 + 1024)   // orig | tmp | Ubuf | scratch
+#define LS_PANEL_FIXED_BYTES 29696   // orig 8192 | tmp 4096 | Ubuf 8192 | cand 8192 | keys, lists 1024
 #define LS_UT 128                  // update tile (rows and columns)
 
 struct LsArgs {
@@ -342,7 +342,7 @@ ls_border_kernel(const DevNet net, const StructNet sn, const LsArgs a, const int
 // in sub-panels of W columns held in REGISTERS: thread t owns the rows t, t + T, .. (R of them) of
 // the sub-panel for its W elimination steps - rows do not move, every register row carries the
 // position it would have after the classic interchanges and is scattered there afterwards; argmax
-// with warp REDUX on the bit patterns (ties -> lowest position = idamax).  After a sub-panel the
+// with warp REDUX on the bit patterns (ties -> lowest position = idamax), one block barrier per step.  After a sub-panel the
 // moved rows of the panel's other columns are exchanged, the columns to its right take the
 // W x W unit-lower solve and the rank-W update.  W = 32, R = 1 when every row has a thread (no
 // in-panel update at all); W = 8, R <= 4 for up to 4 T rows.  The net permutation of the panel is
@@ -356,10 +356,10 @@ ls_panel_kernel(const LsArgs a, const int cur, const int N, const int k0, const 
     int* orig = reinterpret_cast<int*>(ls_sm);                          // [rows <= 2048] original row now at a position
     double* tmp = reinterpret_cast<double*>(ls_sm + 2048 * 4);          // [16][32]
     double* Ubuf = tmp + 16 * 32;                                       // [W <= 32][32]
-    unsigned* rkey = reinterpret_cast<unsigned*>(Ubuf + 32 * 32);       // [16][2]
-    int* redi = reinterpret_cast<int*>(rkey + 32);                      // [16]
-    double* prow = reinterpret_cast<double*>(redi + 16);                // [32]
-    int* mvs = reinterpret_cast<int*>(prow + 32);                       // [16] moved rows: source
+    double* cand = Ubuf + 32 * 32;                                      // [2][16][W <= 32] candidate pivot row of every warp
+    unsigned* rkey = reinterpret_cast<unsigned*>(cand + 2 * 16 * 32);   // [2][16][2]
+    int* redi = reinterpret_cast<int*>(rkey + 64);                      // [2][16]
+    int* mvs = redi + 32;                                               // [16] moved rows: source
     int* mvd = mvs + 16;                                                // [16] destination
     int* mcnt = mvd + 16;                                               // [2]
     double* stage = reinterpret_cast<double*>(ls_sm + LS_PANEL_FIXED_BYTES);
@@ -416,6 +416,58 @@ ls_panel_kernel(const LsArgs a, const int cur, const int N, const int k0, const 
                     unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
                     unsigned mlo = __reduce_max_sync(0xffffffffu, (hi == mhi) ? lo : 0u);
                     unsigned p = __reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? pp : 0x7fffffffu);
+                    if constexpr (W <= 8) {
+                    // ONE barrier per elimination step: every warp publishes its candidate (key, position
+                    // and the row itself); after the barrier every warp picks the winner redundantly and
+                    // reads the pivot row from the winning warp's slot (slots alternate with the parity
+                    // of the step: a warp is at most one step ahead of the slowest one)
+                    const int sb = (j & 1) * 16;
+                    if (lane == 0) { rkey[2 * (sb + warp)] = mhi; rkey[2 * (sb + warp) + 1] = mlo; redi[sb + warp] = (int)p; }
+                    {
+                        double* cw = cand + (sb + warp) * W;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            if (pos[r] >= 0 && (unsigned)pos[r] == p) {
+#pragma unroll
+                                for (int jj = j; jj < W; ++jj) cw[jj] = v[r][jj];
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    unsigned ww;
+                    {
+                        const unsigned h2 = (lane < nw) ? rkey[2 * (sb + lane)] : 0u;
+                        const unsigned l2 = (lane < nw) ? rkey[2 * (sb + lane) + 1] : 0u;
+                        const unsigned p2 = (lane < nw) ? (unsigned)redi[sb + lane] : 0x7fffffffu;
+                        mhi = __reduce_max_sync(0xffffffffu, h2);
+                        mlo = __reduce_max_sync(0xffffffffu, (h2 == mhi) ? l2 : 0u);
+                        p = __reduce_min_sync(0xffffffffu, (h2 == mhi && l2 == mlo && p2 != 0x7fffffffu) ? p2 : 0x7fffffffu);
+                        ww = __reduce_min_sync(0xffffffffu, (h2 == mhi && l2 == mlo && p2 == p && p2 != 0x7fffffffu) ? (unsigned)lane : 0x7fffffffu);
+                    }
+                    const double best = __hiloint2double((int)mhi, (int)mlo);
+                    if ((!(best > 0.0) || !(best < CUDART_INF)) && bad == 0) bad = k0 + o + j + 1;
+                    const int pi = (p == 0x7fffffffu) ? j : (int)p;
+                    const double* prow = cand + (sb + (ww == 0x7fffffffu ? 0u : ww)) * W;
+                    if (tid == 0 && pi != j) { const int x = orig[o + j]; orig[o + j] = orig[o + pi]; orig[o + pi] = x; }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (pos[r] == pi) pos[r] = j;
+                        else if (pos[r] == j) pos[r] = pi;
+                    }
+                    const double rp = 1.0 / prow[j];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (pos[r] > j) {
+                            const double l = v[r][j] * rp;
+                            v[r][j] = l;
+#pragma unroll
+                            for (int jj = j + 1; jj < W; ++jj) v[r][jj] = fma(-l, prow[jj], v[r][jj]);
+                        }
+                    }
+                    } else {
+                        // (32-column register panel: publishing every warp's candidate row would cost the owner
+                        // lanes up to 32 stores per step - two barriers, the winner alone publishes its row)
+                        double* prow_s = cand;
                     if (lane == 0) { rkey[2 * warp] = mhi; rkey[2 * warp + 1] = mlo; redi[warp] = (int)p; }
                     __syncthreads();
                     {
@@ -436,19 +488,20 @@ ls_panel_kernel(const LsArgs a, const int cur, const int N, const int k0, const 
                         else if (pos[r] == j) pos[r] = pi;
                         if (pos[r] == j) {
 #pragma unroll
-                            for (int jj = j; jj < W; ++jj) prow[jj] = v[r][jj];
+                            for (int jj = j; jj < W; ++jj) prow_s[jj] = v[r][jj];
                         }
                     }
                     __syncthreads();
-                    const double rp = 1.0 / prow[j];
+                    const double rp = 1.0 / prow_s[j];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         if (pos[r] > j) {
                             const double l = v[r][j] * rp;
                             v[r][j] = l;
 #pragma unroll
-                            for (int jj = j + 1; jj < W; ++jj) v[r][jj] = fma(-l, prow[jj], v[r][jj]);
+                            for (int jj = j + 1; jj < W; ++jj) v[r][jj] = fma(-l, prow_s[jj], v[r][jj]);
                         }
+                    }
                     }
                 }
             }
@@ -663,25 +716,25 @@ ls_update_kernel(const LsArgs a, const int cur, const int N, const int kb, const
     const int nact = a.nact[cur];
     const int* act = a.act + (size_t)cur * a.S;
     const int ntr = (N - rlo + TR - 1) / TR, ntc = (chi + 1 - clo + TC - 1) / TC;
-    const long long items = (long long)nact * ntr * ntc;
-    const long long per = (items + gridDim.x - 1) / gridDim.x;
-    const long long w0 = (long long)blockIdx.x * per, w1 = (w0 + per < items) ? w0 + per : items;
+    // A strip = one row tile of one matrix, swept over its column tiles (the L slice is staged once per
+    // strip); CTA b takes the strips b, b + grid, ..: neighbouring CTAs sweep neighbouring row tiles of
+    // the SAME matrix at the same time, so the U slice of a column tile is fetched from HBM once and
+    // served to the other row tiles by L2 (contiguous item ranges per CTA re-read it from HBM for every
+    // row tile: ncu 8.2 GB read against 3.9 GB written by the first update of 512 systems of order 1038)
+    const long long strips = (long long)nact * ntr;
     const int fr = lane >> 2, fk = lane & 3;
-    long long lkey = -1;
-    for (long long w = w0; w < w1; ++w) {
-        const long long key = w / ntc;                            // (matrix, row tile)
-        const int tc = (int)(w - key * ntc);
-        const int ai = (int)(key / ntr), tr = (int)(key - (long long)ai * ntr);
+    for (long long sidx = blockIdx.x; sidx < strips; sidx += gridDim.x)
+    for (int tc = 0; tc < ntc; ++tc) {
+        const int ai = (int)(sidx / ntr), tr = (int)(sidx - (long long)ai * ntr);
         double* A = a.M + (size_t)act[ai] * a.mat_stride;
         const int r0 = rlo + tr * TR, c0 = clo + tc * TC;
         __syncthreads();                                          // previous item's slices consumed
-        if (key != lkey) {                                        // (asynchronous like the U slice; r0 is even)
+        if (tc == 0) {                                            // (asynchronous like the U slice; r0 is even)
             for (int t = tid; t < K * (TR >> 1); t += NT) {
                 const int k = t / (TR >> 1), r = (t - k * (TR >> 1)) << 1;
                 const int nbytes = (r0 + r + 1 < N) ? 16 : ((r0 + r < N) ? 8 : 0);
                 lub_cp_async16(Ls + k * SL + r, nbytes ? A + (size_t)(kb + k) * ld + r0 + r : A, nbytes);
             }
-            lkey = key;
         }
         for (int t = tid; t < TC * (K >> 1); t += NT) {
             const int cc = t / (K >> 1), k = (t - cc * (K >> 1)) << 1;

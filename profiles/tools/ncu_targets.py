@@ -38,6 +38,7 @@ torch.cuda.synchronize()
 sol.close()
 
 os.environ["HPF_GJ_UNBLOCKED"] = "1"          # (keeps the set-up's panel GEMMs out of the capture)
+os.environ["HPF_LOCKSTEP"] = "0"              # (per-CTA kernels; the lock-step kernels: run_lu_batched.py / run_other.py)
 net4 = bench.load_other("radial200")
 sol4 = BatchSolver(net4)
 P4, Q4, I4 = scenarios.make_batch(net4, 296, "tight")

@@ -1303,7 +1303,7 @@ def test_lockstep_path_against_oracle_and_cta_path(kind, n, B, tmp_path, monkeyp
     assert (res["status"] == 0).all()
     # The iteration count of these networks is decided by round-off in ~10 % of the scenarios (the oracle
     # with a LAPACK step against the oracle with the reference's SuperLU step: 19 of 150 on the 70-bus
-    # network, lock-step 17, per-CTA kernel 21 - profiles/r3_lockstep_iteration_rates.txt), so the bar is
+    # network, lock-step 17, per-CTA kernel 21 - profiles/r2_lockstep_iteration_rates.txt), so the bar is
     # the oracle's own disagreement on the same sample; scenarios with equal counts must agree in V.
     import oracle_pool
     sample = np.arange(0, B, max(1, B // 24))
