@@ -1961,7 +1961,7 @@ static int launch_ls_lu(hpf_t* h, const LsArgs& la, int cur, int N, int nwave, c
         const size_t psm = staged ? want : (size_t)LS_PANEL_FIXED_BYTES;
         int grid = 0, rc;
         if (rows <= 512) {
-            const int T = rows <= 256 ? 256 : 512;
+            const int T = rows <= 128 ? 128 : rows <= 256 ? 256 : 512;
             rc = ls_grid(h, ls_panel_kernel<1, 32>, T, psm, nwave, &grid);
             if (rc) return rc;
             ls_panel_kernel<1, 32><<<grid, T, psm, st>>>(la, cur, N, k0, staged, left);

@@ -959,13 +959,16 @@ def test_ybus_corrected_options_match_textbook_admittance_matrix():
     sol.close()
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3])
+@pytest.mark.parametrize("variant", [0, 2, 3, 34])
 def test_degenerate_shapes_linear_only_and_fundamental_only(tmp_path, monkeypatch, variant):
     """Edge shapes of the data contract: a network WITHOUT nonlinear buses (q = 0: the harmonic
     stage has nothing to inject, harmonic voltages go to zero) and a fundamental-only run
-    (H = 1: the harmonic Newton loop works on the fundamental alone), through the tile kernel
-    and both per-CTA variants, against the oracle."""
+    (H = 1: the harmonic Newton loop works on the fundamental alone), through the tile kernel,
+    both per-CTA variants and the lock-step batched path, against the oracle."""
     from harmonic_power_flow_b200 import BatchSolver, netio
+    if variant == 34:                                        # variant 3 through the lock-step batched path
+        monkeypatch.setenv("HPF_LOCKSTEP", "1")
+        variant = 3
     if variant:
         monkeypatch.setenv("HPF_STRUCT_VARIANT", str(variant))
     # (a) q = 0: net2 with its SMPS bus turned into a linear PQ load
