@@ -630,6 +630,15 @@ def run_ours(a):
         for _ in range(3):
             sol.solve_host(pgP, pgQ, pgI)
         t_pageable = (time.perf_counter() - t0) / 3
+    # the reference's own return set (HG:560: V, err_h, n_iter_h - no Norton injection currents): same call with I_inj = NULL
+    t_noinj = d2h_noinj = None
+    if world == 1:
+        rn = sol.solve_host(npP, npQ, npI, want_I_inj=False)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            rn = sol.solve_host(npP, npQ, npI, want_I_inj=False)
+        t_noinj = (time.perf_counter() - t0) / a.steps
+        d2h_noinj = sum(rn[k].nbytes for k in RESULT_KEYS if rn[k] is not None)
     # strong-scaling share end to end
     if strong is not None:
         e2s = E2E(torch, dist, sol, net, strong["Bs"], world, rank)
@@ -808,6 +817,12 @@ def run_ours(a):
                              "hbm_bytes_per_scenario": by_solve,
                              "hbm_gbs_of_whole_solve": by_solve * B / step_ms / 1e6},
                 "roofline_kernels": kernels, "hbm_peak_source": hbm_src}
+        if t_noinj is not None:
+            line["e2e"]["without_I_inj"] = {"value": conv_e2e / t_noinj, "unit": UNIT, "ms_per_step": t_noinj * 1e3,
+                                            "d2h_bytes_per_step": d2h_noinj,
+                                            "what": "the same hpf_solve_host call returning what the reference's hpf() returns "
+                                                    "(V_m, V_a, err_h, iteration counts, status); the headline e2e above also "
+                                                    "copies back the Norton injection currents I_inj"}
         if t_pageable is not None:
             line["e2e"]["pageable"] = {"value": conv_e2e / t_pageable, "unit": UNIT, "ms_per_step": t_pageable * 1e3,
                                        "what": "the same hpf_solve_host call with ordinary (pageable) numpy arrays"}

@@ -274,11 +274,13 @@ class BatchSolver:
         slab = torch.empty(total, dtype=torch.uint8, device=self.device)
         return result_from_slab(slab, n.H, n.n, n.q, B), slab
 
-    def solve_host(self, P, Q, I_N, thresh_f=1e-6, max_iter_f=30, thresh_h=1e-4, max_iter_h=50, keep=None):
+    def solve_host(self, P, Q, I_N, thresh_f=1e-6, max_iter_f=30, thresh_h=1e-4, max_iter_h=50, keep=None,
+                   want_I_inj=True):
         """hpf_solve_host: numpy in, numpy out, all copies inside the C call.  ``keep``: a
         BatchResult of device tensors that additionally receives the results (hpf_solve_host_keep),
         e.g. for the NCCL gather of a multi-GPU run; ``keep=True`` allocates one (returned under
-        the key "device")."""
+        the key "device").  ``want_I_inj=False``: the Norton injection currents (which the reference's
+        hpf() does not return either, HG:560) are not copied back (I_inj = NULL in the C call)."""
         n = self.net
         P = np.ascontiguousarray(P, dtype=np.float64)
         Q = np.ascontiguousarray(Q, dtype=np.float64)
@@ -296,8 +298,8 @@ class BatchSolver:
         if keep is None:
             _lib.check(self._h, self.lib.hpf_solve_host(
                 self._h, B, vp(P), vp(Q), vp(I_N), thresh_f, max_iter_f, thresh_h, max_iter_h,
-                vp(V_m), vp(V_a), vp(I_inj), vp(nf), vp(nh), vp(err), vp(st)))
-            return dict(V_m=V_m, V_a=V_a, I_inj=I_inj, n_iter_f=nf, n_iter_h=nh, err_h=err, status=st)
+                vp(V_m), vp(V_a), vp(I_inj) if want_I_inj else None, vp(nf), vp(nh), vp(err), vp(st)))
+            return dict(V_m=V_m, V_a=V_a, I_inj=I_inj if want_I_inj else None, n_iter_f=nf, n_iter_h=nh, err_h=err, status=st)
         if keep is True:
             keep = BatchResult(self._f64(n.H, n.n, B), self._f64(n.H, n.n, B), self._c128(n.q, n.H, B),
                                self._i32(B), self._i32(B), self._f64(B), self._i32(B))

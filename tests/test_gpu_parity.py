@@ -328,6 +328,11 @@ def test_host_buffer_entry_point_is_bit_identical(solvers):
     b = sol.solve_host(P, Q, I_N)
     for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status"):
         assert np.array_equal(a[k], b[k]), k
+    # the reference's return set (no Norton injection currents): I_inj = NULL in the C call
+    c = sol.solve_host(P, Q, I_N, want_I_inj=False)
+    assert c["I_inj"] is None
+    for k in ("V_m", "V_a", "n_iter_f", "n_iter_h", "err_h", "status"):
+        assert np.array_equal(a[k], c[k]), k
 
 
 def test_host_entry_point_keeps_device_copy(solvers):
