@@ -41,7 +41,9 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    # $HPF_BUILD_FAST=1: ptxas compiles the kernels in parallel (development builds, 3x faster)
+    # $HPF_BUILD_FAST=1: ptxas compiles the kernels in parallel (development builds, 3x faster).  NOT for
+    # measurements: the split compile allocates registers differently (ls_border_kernel 64 instead of 78,
+    # ls_backsub_kernel 40 instead of 32 registers) and those kernels run 15-20 % slower - measured same-box.
     fast = ["--split-compile", "0"] if os.environ.get("HPF_BUILD_FAST") else []
     cmd = [_nvcc()] + NVCC_FLAGS + fast + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
