@@ -1039,6 +1039,10 @@ __global__ void bus_currents_kernel(const DevNet net, int B, const double* __res
 
 // =======================================================================================
 // Host side: handle + C ABI
+#define HPF_HOST_MAX_CHUNKS 16          // chunks of one hpf_solve_host call (work-counter slots, event pairs)
+#define HPF_HOST_RAMP 4096, 8192, 12288, 16384   // default chunk plan (sizes in scenarios; the last one repeats)
+#define HPF_HOST_RAMP_MIN_B 8192        // smaller batches go in one chunk
+#define HPF_HOST_STREAMS_DEFAULT 2
 struct hpf_handle {
     int device = 0;
     int sm_count = 0;
@@ -1055,12 +1059,12 @@ struct hpf_handle {
     size_t work_doubles = 0;
     double* d_io = nullptr;       // staging buffers of hpf_solve_host (grow-only)
     size_t io_doubles = 0;
-    cudaStream_t st_io[4] = {nullptr, nullptr, nullptr, nullptr};   // copy-in, compute, copy-out, compute 2
+    cudaStream_t st_io[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // copy-in, compute, copy-out, compute 2..4
     // hpf_solve_host runs consecutive chunks on two compute streams (the tail of chunk k overlaps
     // the start of chunk k+1); each in-flight chunk has its own work counter and w_N scratch
-    int cur_slot = 0;
-    size_t wN_slot_stride = 0;
-    cudaEvent_t ev_io[16] = {};
+    int cur_slot = 0;             // work-counter slot of the chunk being issued (0 outside hpf_solve_host)
+    size_t wN_off = 0;            // offset of that chunk's w_N scratch inside d_wN
+    cudaEvent_t ev_io[2 * HPF_HOST_MAX_CHUNKS] = {};
     // structured strategy: 0 = not set up yet, 1 = ready, -1 = not available for this network
     int struct_state = 0;
     double2 *d_Ainv = nullptr, *d_Gz = nullptr, *d_GzT = nullptr, *d_WNL = nullptr, *d_wN = nullptr;
@@ -1739,7 +1743,7 @@ static bool wn_use_dmma(const hpf_t* h, int nZ, int qH, int B) {
 
 static int launch_wn(hpf_t* h, const DevNet& net, const StructNet& sn, int B, const double* I_N,
                      cudaStream_t st) {
-    const size_t off = (size_t)h->cur_slot * h->wN_slot_stride;
+    const size_t off = h->wN_off;
     const size_t need = off + (size_t)sn.nZ * B;
     if (need > h->wN_elems) {
         if (h->d_wN) { CK(cudaDeviceSynchronize()); cudaFree(h->d_wN); h->d_wN = nullptr; h->wN_elems = 0; }
@@ -2330,7 +2334,7 @@ static int solve_structured(hpf_t* h, int B, const double* P, const double* Q, c
         if (rc) return rc;
         HarmTileArgs ha;
         ha.B = B; ha.flags = flags; ha.step_only = 0; ha.P = P; ha.Q = Q; ha.I_N = (const double2*)I_N;
-        ha.wN = h->d_wN + (size_t)h->cur_slot * h->wN_slot_stride;
+        ha.wN = h->d_wN + h->wN_off;
         ha.thresh_h = thresh_h; ha.max_h = max_h; ha.V_m = V_m; ha.V_a = V_a; ha.I_inj = (double2*)I_inj;
         ha.n_iter_h = n_iter_h; ha.status = status; ha.err_h = err_h; ha.work_counter = h->d_counter + h->cur_slot;
         ha.dx_out = nullptr; ha.gstate = nullptr; ha.gstate_stride = 0; ha.lub_doubles = 0; ha.hist_h = hist_h; ha.epoch = h->hw_epoch;
@@ -2432,7 +2436,7 @@ int hpf_create(hpf_t** out, int device) {
     if (const char* ev = getenv("HPF_GMEM_SMEM_KB")) h->gmem_cap = (size_t)(atoi(ev) > 0 ? atoi(ev) : 0) * 1024;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    e = cudaMalloc((void**)&h->d_counter, 8 * sizeof(int));
+    e = cudaMalloc((void**)&h->d_counter, HPF_HOST_MAX_CHUNKS * sizeof(int));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaFree(h->d_counter);
@@ -2454,8 +2458,8 @@ int hpf_destroy(hpf_t* h) {
     cudaFree(h->d_WNL); cudaFree(h->d_wN); cudaFree(h->d_GzT); cudaFree(h->d_nbr_ptr); cudaFree(h->d_nbr_idx);
     cudaFree(h->d_gstate); cudaFree(h->d_ls); cudaFree(h->d_ell_col); cudaFree(h->d_tau); cudaFree(h->d_phase);
     for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    for (int i = 0; i < 4; ++i) if (h->st_io[i]) cudaStreamDestroy(h->st_io[i]);
-    for (int i = 0; i < 16; ++i) if (h->ev_io[i]) cudaEventDestroy(h->ev_io[i]);
+    for (int i = 0; i < 6; ++i) if (h->st_io[i]) cudaStreamDestroy(h->st_io[i]);
+    for (int i = 0; i < 2 * HPF_HOST_MAX_CHUNKS; ++i) if (h->ev_io[i]) cudaEventDestroy(h->ev_io[i]);
     delete h;
     return HPF_OK;
 }
@@ -2676,7 +2680,7 @@ int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I
               int max_iter_f, double thresh_h, int max_iter_h, int flags, double* V_m, double* V_a,
               double* I_inj, int* n_iter_f, int* n_iter_h, double* err_h, int* status,
               double* err_hist_f, double* err_hist_h, void* stream) {
-    if (h) { h->cur_slot = 0; h->wN_slot_stride = 0; }      // (a failed hpf_solve_host may have left them set)
+    if (h) { h->cur_slot = 0; h->wN_off = 0; }      // (a failed hpf_solve_host may have left them set)
     return ordered(h, stream, [&] {
         return solve_dispatch(h, B, P, Q, I_N, thresh_f, max_iter_f, thresh_h, max_iter_h, flags, V_m, V_a, I_inj,
                               n_iter_f, n_iter_h, err_h, status, err_hist_f, err_hist_h, stream);
@@ -2768,7 +2772,7 @@ int hpf_norton_wn(hpf_t* h, int B, const double* I_N, double* wN, void* stream) 
             return fail(h, HPF_E_UNSUPPORTED, "hpf_norton_wn: structured strategy not available for this network");
         const DevNet net = devnet(h);
         const StructNet sn = structnet(h);
-        h->cur_slot = 0; h->wN_slot_stride = 0;
+        h->cur_slot = 0; h->wN_off = 0;
         rc = launch_wn(h, net, sn, B, I_N, (cudaStream_t)stream);
         if (rc) return rc;
         CK(cudaMemcpyAsync(wN, h->d_wN, (size_t)sn.nZ * B * sizeof(double2), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -2813,6 +2817,50 @@ int hpf_fund_solve(hpf_t* h, int B, const double* P, const double* Q, double thr
 
 } // extern "C"
 
+// Chunk plan of hpf_solve_host: boundaries cb[0..nchunk] (multiples of 32 scenarios except the end) and
+// the number of compute streams the chunks rotate over.  $HPF_HOST_PLAN = comma-separated chunk sizes
+// (the last size repeats until the batch is covered; at most HPF_HOST_MAX_CHUNKS chunks, the last one
+// takes the rest), $HPF_HOST_CHUNKS = number of equal chunks, $HPF_HOST_STREAMS = 1..4 compute streams.
+static int host_chunk_plan(size_t Bs, size_t* cb, int* streams) {
+    static const size_t ramp_default[] = {HPF_HOST_RAMP};
+    size_t sizes[HPF_HOST_MAX_CHUNKS];
+    int ns = 0;
+    if (const char* ev = getenv("HPF_HOST_PLAN")) {
+        for (const char* p = ev; *p && ns < HPF_HOST_MAX_CHUNKS;) {
+            char* end = nullptr;
+            const long v = strtol(p, &end, 10);
+            if (end == p) break;
+            if (v > 0) sizes[ns++] = (size_t)v;
+            p = (*end == ',') ? end + 1 : end;
+            if (*end != ',') break;
+        }
+    }
+    int equal = 0;
+    if (const char* ev = getenv("HPF_HOST_CHUNKS")) { const int v = atoi(ev); if (v >= 1 && v <= HPF_HOST_MAX_CHUNKS) equal = v; }
+    if (ns == 0 && equal == 0) {
+        if (Bs >= HPF_HOST_RAMP_MIN_B) {
+            for (size_t i = 0; i < sizeof(ramp_default) / sizeof(ramp_default[0]); ++i) sizes[ns++] = ramp_default[i];
+        } else {
+            equal = 1;
+        }
+    }
+    if (ns == 0) { sizes[0] = (Bs + equal - 1) / equal; ns = 1; }
+    int k = 0;
+    size_t b = 0;
+    cb[0] = 0;
+    while (b < Bs) {
+        size_t sz = (sizes[k < ns ? k : ns - 1] + 31) / 32 * 32;
+        if (k == HPF_HOST_MAX_CHUNKS - 1 || b + sz > Bs) sz = Bs - b;
+        b += sz;
+        cb[++k] = b;
+    }
+    int st = HPF_HOST_STREAMS_DEFAULT;
+    if (const char* ev = getenv("HPF_HOST_STREAMS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) st = v; }
+    if (getenv("HPF_HOST_SINGLE_STREAM")) st = 1;
+    *streams = st;
+    return k;
+}
+
 // Device copies of the results that hpf_solve_host_keep leaves behind ([rows, B] layout).
 struct HostKeep {
     double *V_m = nullptr, *V_a = nullptr, *I_inj = nullptr, *err_h = nullptr;
@@ -2830,47 +2878,53 @@ static int solve_host_impl(hpf_t* h, int B, const double* P, const double* Q, co
         return fail(h, HPF_E_INVALID, "hpf_solve_host: NULL buffer");
     ENTER_DEVICE(h);
     // Pipelined in chunks of scenarios: while chunk k is being solved, chunk k+1 is copied in and
-    // the results of chunk k-1 are copied out (PCIe is full duplex); consecutive chunks alternate
-    // between two compute streams so that the long-iteration tail of one chunk overlaps the start
-    // of the next (measured on 65,536 net3 scenarios: 1 chunk 2.83 ms, 4 chunks on one compute
-    // stream 2.22 ms, 8 chunks on two 1.89 ms; the D2H copy alone is 1.3 ms).
+    // the results of chunk k-1 are copied out (PCIe is full duplex); consecutive chunks rotate over
+    // the compute streams so that the long-iteration tail of one chunk overlaps the start of the
+    // next.  The copy-out of the results is the floor of the call (1.24 ms for 65,536 net3 scenarios;
+    // 1 chunk 2.30 ms, 8 equal chunks on two compute streams 1.65 ms, the growing plan 1.61 ms:
+    // profiles/r2_e2e_chunk_plans.txt), so the plan starts with a SMALL chunk - the copy-out stream
+    // gets its first results after one short solve - and grows the chunks while the copy engine is
+    // busy: fewer, larger copies and solves later on (host_chunk_plan).
     // The host arrays are batch-innermost [rows, B]; a chunk is a column block, moved with 2-D
     // copies into compact [rows, Bc] device arrays (pinned host memory makes them asynchronous).
     const size_t n = h->n, H = h->H, q = h->q, Bs = (size_t)B;
-    int nchunk = (B >= 65536) ? 8 : (B >= 32768) ? 4 : (B >= 8192 ? 2 : 1);
-    if (const char* ev = getenv("HPF_HOST_CHUNKS")) { const int v = atoi(ev); if (v >= 1 && v <= 8) nchunk = v; }
-    const size_t Bc_max = ((Bs + nchunk - 1) / nchunk + 31) / 32 * 32;
-    nchunk = (int)((Bs + Bc_max - 1) / Bc_max);
-    // per chunk (compact): P, Q [n] | I_N [2qH] | V_m, V_a [nH] | I_inj [2qH] | err [1] | 3 ints
-    const size_t per_scn = 2 * n + 2 * q * H + 2 * n * H + 2 * q * H + 1 + 2;
-    const size_t nd = per_scn * Bc_max * nchunk + 16;
+    size_t cb[HPF_HOST_MAX_CHUNKS + 1];
+    int ncs = 2;
+    const int nchunk = host_chunk_plan(Bs, cb, &ncs);
+    // per scenario and chunk (compact): P, Q [n] | I_N [2qH] | V_m, V_a [nH] | I_inj [2qH]; chunk k lives
+    // at per_scn * cb[k] (chunk starts are multiples of 32 scenarios).  err_h and the three flag arrays
+    // are one row per scenario: they sit behind the chunks as whole-batch arrays [Bp] and go back with
+    // ONE copy each after the last chunk (a copy costs ~3 us of the copy-out stream whatever its size).
+    const size_t per_scn = 2 * n + 2 * q * H + 2 * n * H + 2 * q * H;
+    const size_t Bp = (Bs + 3) / 4 * 4;
+    const size_t nd = per_scn * Bs + Bp + 3 * (Bp / 2);
     if (nd > h->io_doubles) {
         if (h->d_io) { CK(cudaDeviceSynchronize()); cudaFree(h->d_io); h->d_io = nullptr; h->io_doubles = 0; }
         CK(cudaMalloc((void**)&h->d_io, nd * sizeof(double)));
         h->io_doubles = nd;
     }
     if (!h->st_io[0]) {
-        for (int i = 0; i < 4; ++i) CK(cudaStreamCreateWithFlags(&h->st_io[i], cudaStreamNonBlocking));
-        for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&h->ev_io[i], cudaEventDisableTiming));
+        for (int i = 0; i < 6; ++i) CK(cudaStreamCreateWithFlags(&h->st_io[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * HPF_HOST_MAX_CHUNKS; ++i) CK(cudaEventCreateWithFlags(&h->ev_io[i], cudaEventDisableTiming));
     }
     cudaStream_t s_in = h->st_io[0], s_out = h->st_io[2];
+    const int cmp_stream[4] = {1, 3, 4, 5};
     // ordered after the handle's previous kernel sequence like every other entry point (the copy-in
     // overwrites the staging buffers, the solves share the handle's scratch)
     if (h->last_valid)
-        for (int i = 0; i < 4; ++i) CK(cudaStreamWaitEvent(h->st_io[i], h->ev_last, 0));
-    // two compute streams only where concurrent solves share no scratch (tile variant)
+        for (int i = 0; i < 6; ++i) CK(cudaStreamWaitEvent(h->st_io[i], h->ev_last, 0));
+    // several compute streams only where concurrent solves share no scratch (tile variant)
     rc = ensure_struct(h, h->st_io[1]);
     if (rc) return rc;
-    const bool dual = (h->struct_state == 1) && nchunk > 1 && !getenv("HPF_HOST_SINGLE_STREAM");
+    const bool dual = (h->struct_state == 1) && nchunk > 1 && ncs > 1;
+    const size_t wN_rows = (size_t)(h->n * h->H - h->m);
     if (dual) {
-        // reserve the per-chunk w_N scratch up front (no reallocation while chunks are in flight)
-        const size_t stride = (size_t)(h->n * h->H - h->m) * Bc_max;
-        if (stride * nchunk > h->wN_elems) {
+        // reserve the w_N scratch of all chunks up front (no reallocation while chunks are in flight)
+        if (wN_rows * Bs > h->wN_elems) {
             if (h->d_wN) { CK(cudaDeviceSynchronize()); cudaFree(h->d_wN); h->d_wN = nullptr; h->wN_elems = 0; }
-            CK(cudaMalloc((void**)&h->d_wN, stride * nchunk * sizeof(double2)));
-            h->wN_elems = stride * nchunk;
+            CK(cudaMalloc((void**)&h->d_wN, wN_rows * Bs * sizeof(double2)));
+            h->wN_elems = wN_rows * Bs;
         }
-        h->wN_slot_stride = stride;
     }
     auto cp2d = [&](void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows,
                     cudaMemcpyKind kind, cudaStream_t st) {
@@ -2878,36 +2932,51 @@ static int solve_host_impl(hpf_t* h, int B, const double* P, const double* Q, co
     };
     rc = HPF_OK;
     cudaError_t e = cudaSuccess;
+    double* const dErr_all = h->d_io + per_scn * Bs;
+    int* const di_all = reinterpret_cast<int*>(dErr_all + Bp);
+    // $HPF_HOST_TIMELINE: per-chunk completion times of copy-in, solve and copy-out on stderr
+    const bool tl = getenv("HPF_HOST_TIMELINE") != nullptr;
+    cudaEvent_t tle[3 * HPF_HOST_MAX_CHUNKS + 1] = {};
+    if (tl) {
+        for (auto& ev : tle) cudaEventCreate(&ev);
+        cudaEventRecord(tle[3 * HPF_HOST_MAX_CHUNKS], s_in);
+    }
     for (int k = 0; k < nchunk && !rc; ++k) {
-        const size_t b0 = (size_t)k * Bc_max, Bc = (b0 + Bc_max <= Bs) ? Bc_max : Bs - b0;
-        double* d = h->d_io + (size_t)k * per_scn * Bc_max;
+        const size_t b0 = cb[k], Bc = cb[k + 1] - cb[k];
+        double* d = h->d_io + per_scn * b0;
         double *dP = d, *dQ = dP + n * Bc, *dI = dQ + n * Bc, *dVm = dI + 2 * q * H * Bc, *dVa = dVm + n * H * Bc,
-               *dInj = dVa + n * H * Bc, *dErr = dInj + 2 * q * H * Bc;
-        int* di = reinterpret_cast<int*>(dErr + Bc + (Bc & 1));
+               *dInj = dVa + n * H * Bc, *dErr = dErr_all + b0;
+        int *di_f = di_all + b0, *di_h = di_all + Bp + b0, *di_s = di_all + 2 * Bp + b0;
         const size_t w8 = Bc * sizeof(double), w16 = Bc * 2 * sizeof(double);
         const size_t p8 = Bs * sizeof(double), p16 = Bs * 2 * sizeof(double);
         e = cp2d(dP, w8, P + b0, p8, w8, n, cudaMemcpyHostToDevice, s_in);
         if (e == cudaSuccess) e = cp2d(dQ, w8, Q + b0, p8, w8, n, cudaMemcpyHostToDevice, s_in);
         if (e == cudaSuccess && q)
             e = cp2d(dI, w16, I_N + 2 * b0, p16, w16, q * H, cudaMemcpyHostToDevice, s_in);
-        cudaStream_t s_cmp = h->st_io[(dual && (k & 1)) ? 3 : 1];
+        cudaStream_t s_cmp = h->st_io[dual ? cmp_stream[k % ncs] : 1];
         h->cur_slot = dual ? k : 0;
+        h->wN_off = dual ? wN_rows * b0 : 0;
         if (e == cudaSuccess) e = cudaEventRecord(h->ev_io[k], s_in);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(s_cmp, h->ev_io[k], 0);
         if (e != cudaSuccess) break;
+        if (tl) cudaEventRecord(tle[3 * k], s_in);
         rc = solve_dispatch(h, (int)Bc, dP, dQ, dI, thresh_f, max_iter_f, thresh_h, max_iter_h, 0, dVm, dVa,
-                       I_inj ? dInj : nullptr, di, di + Bc, dErr, di + 2 * Bc, nullptr, nullptr, s_cmp);
+                       I_inj ? dInj : nullptr, di_f, di_h, dErr, di_s, nullptr, nullptr, s_cmp);
         if (rc) break;
-        e = cudaEventRecord(h->ev_io[8 + k], s_cmp);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, h->ev_io[8 + k], 0);
+        e = cudaEventRecord(h->ev_io[HPF_HOST_MAX_CHUNKS + k], s_cmp);
+        if (tl) cudaEventRecord(tle[3 * k + 1], s_cmp);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, h->ev_io[HPF_HOST_MAX_CHUNKS + k], 0);
         if (e == cudaSuccess) e = cp2d(V_m + b0, p8, dVm, w8, w8, n * H, cudaMemcpyDeviceToHost, s_out);
         if (e == cudaSuccess) e = cp2d(V_a + b0, p8, dVa, w8, w8, n * H, cudaMemcpyDeviceToHost, s_out);
         if (e == cudaSuccess && I_inj && q)
             e = cp2d(I_inj + 2 * b0, p16, dInj, w16, w16, q * H, cudaMemcpyDeviceToHost, s_out);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(err_h + b0, dErr, Bc * sizeof(double), cudaMemcpyDeviceToHost, s_out);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(n_iter_f + b0, di, Bc * sizeof(int), cudaMemcpyDeviceToHost, s_out);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(n_iter_h + b0, di + Bc, Bc * sizeof(int), cudaMemcpyDeviceToHost, s_out);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(status + b0, di + 2 * Bc, Bc * sizeof(int), cudaMemcpyDeviceToHost, s_out);
+        if (e == cudaSuccess && k == nchunk - 1) {       // s_out has waited for every chunk by now
+            e = cudaMemcpyAsync(err_h, dErr_all, Bs * sizeof(double), cudaMemcpyDeviceToHost, s_out);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(n_iter_f, di_all, Bs * sizeof(int), cudaMemcpyDeviceToHost, s_out);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(n_iter_h, di_all + Bp, Bs * sizeof(int), cudaMemcpyDeviceToHost, s_out);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(status, di_all + 2 * Bp, Bs * sizeof(int), cudaMemcpyDeviceToHost, s_out);
+        }
+        if (tl) cudaEventRecord(tle[3 * k + 2], s_out);
         if (e == cudaSuccess && keep) {
             // also leave the results on the device in the full [rows, B] layout (device-to-device
             // 2-D copies on the compute stream, ~20 us for the whole batch)
@@ -2916,18 +2985,27 @@ static int solve_host_impl(hpf_t* h, int B, const double* P, const double* Q, co
             if (e == cudaSuccess && keep->I_inj && I_inj && q)
                 e = cp2d(keep->I_inj + 2 * b0, p16, dInj, w16, w16, q * H, cudaMemcpyDeviceToDevice, s_cmp);
             if (e == cudaSuccess) e = cudaMemcpyAsync(keep->err_h + b0, dErr, Bc * sizeof(double), cudaMemcpyDeviceToDevice, s_cmp);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(keep->n_iter_f + b0, di, Bc * sizeof(int), cudaMemcpyDeviceToDevice, s_cmp);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(keep->n_iter_h + b0, di + Bc, Bc * sizeof(int), cudaMemcpyDeviceToDevice, s_cmp);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(keep->status + b0, di + 2 * Bc, Bc * sizeof(int), cudaMemcpyDeviceToDevice, s_cmp);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(keep->n_iter_f + b0, di_f, Bc * sizeof(int), cudaMemcpyDeviceToDevice, s_cmp);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(keep->n_iter_h + b0, di_h, Bc * sizeof(int), cudaMemcpyDeviceToDevice, s_cmp);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(keep->status + b0, di_s, Bc * sizeof(int), cudaMemcpyDeviceToDevice, s_cmp);
         }
         if (e != cudaSuccess) break;
     }
     h->cur_slot = 0;
-    h->wN_slot_stride = 0;
+    h->wN_off = 0;
     if (!rc && e != cudaSuccess) rc = fail(h, HPF_E_CUDA, std::string("hpf_solve_host: ") + cudaGetErrorString(e));
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 6; ++i) {
         const cudaError_t e2 = cudaStreamSynchronize(h->st_io[i]);
         if (!rc && e2 != cudaSuccess) rc = fail(h, HPF_E_CUDA, std::string("hpf_solve_host: ") + cudaGetErrorString(e2));
+    }
+    if (tl) {
+        for (int k = 0; k < nchunk && !rc; ++k) {
+            float t[3] = {0.f, 0.f, 0.f};
+            for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&t[i], tle[3 * HPF_HOST_MAX_CHUNKS], tle[3 * k + i]);
+            fprintf(stderr, "hpf_solve_host chunk %2d [%6zu..%6zu): copy-in done %.3f ms, solve done %.3f ms, copy-out done %.3f ms\n",
+                    k, cb[k], cb[k + 1], t[0], t[1], t[2]);
+        }
+        for (auto& ev : tle) cudaEventDestroy(ev);
     }
     if (!rc) h->last_valid = false;        // everything this handle issued has completed
     return rc;

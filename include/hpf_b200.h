@@ -166,7 +166,10 @@ int hpf_solve(hpf_t* h, int B, const double* P, const double* Q, const double* I
 
 /*
  * Same with HOST buffers (pageable or pinned): copies in, solves, copies out,
- * synchronises.  This is the call a reference-side binding would make.
+ * synchronises.  This is the call a reference-side binding would make.  Batches of
+ * 8,192 scenarios and more are pipelined in growing chunks (4,096 / 8,192 / 12,288 /
+ * 16,384 ... scenarios) over a copy-in, two compute and a copy-out stream; results do
+ * not depend on the chunking (bit-identical to hpf_solve).
  */
 int hpf_solve_host(hpf_t* h, int B, const double* P, const double* Q, const double* I_N,
                    double thresh_f, int max_iter_f, double thresh_h, int max_iter_h,

@@ -363,6 +363,26 @@ def test_host_entry_point_chunked_pipeline(solvers, tmp_path):
     assert (b["status"] == 0).all()
 
 
+@pytest.mark.parametrize("plan,streams,B", [("96,160,1000,64", 3, 4099), ("32", 4, 2001), ("4096,8192,12288,16384", 2, 70001),
+                                             ("100000", 2, 777)])
+def test_host_entry_point_chunk_plans(solvers, monkeypatch, plan, streams, B):
+    """$HPF_HOST_PLAN / $HPF_HOST_STREAMS (growing chunks of hpf_solve_host over 1..4 compute streams,
+    more sizes than chunk slots, a last chunk of odd length, a plan larger than the batch): host results
+    and the device copy of hpf_solve_host_keep carry the bits of the device-resident call."""
+    from harmonic_power_flow_b200 import scenarios
+    sol, net, _ = solvers("net3_c_h25")
+    P, Q, I_N = scenarios.make_batch(net, B, "tight")
+    a = sol.solve(P, Q, I_N).to_host()
+    monkeypatch.setenv("HPF_HOST_PLAN", plan)
+    monkeypatch.setenv("HPF_HOST_STREAMS", str(streams))
+    b = sol.solve_host(P, Q, I_N, keep=True)
+    dev = b["device"].to_host()
+    for k in ("V_m", "V_a", "I_inj", "n_iter_f", "n_iter_h", "err_h", "status"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], dev[k]), k
+    assert (b["status"] == 0).all()
+
+
 def test_fused_solve_equals_stepwise_kernels(solvers, tmp_path, monkeypatch):
     """The fused kernel and a host loop over kernels 2-4 share their arithmetic: identical
     iteration counts and (bitwise) identical iterates.  (The standalone mismatch is forced onto
