@@ -800,7 +800,15 @@ def run_ours(a):
                             "note": "each phase timed alone with all ranks running it concurrently; the step is "
                                     "bounded below by the D2H copy of the results over PCIe"},
                         "limiter": max([("solve_host_call (H2D + solve + D2H pipeline; PCIe D2H is its floor)", mx[9]),
-                                        ("nccl_gather_to_rank0", mx[12] if world > 1 else 0.0)], key=lambda t: t[1])[0]},
+                                        ("nccl_gather_to_rank0", mx[12] if world > 1 else 0.0)], key=lambda t: t[1])[0],
+                        "host_path": {
+                            "d2h_gbs_slowest_rank_all_ranks_copying": d2h / mx[11] / 1e6 if mx[11] else None,
+                            "d2h_gbs_one_rank_alone": 56.0,
+                            "what": "rate of the slowest rank's D2H copy of its result slab while all ranks copy at "
+                                    "once (measured in this run) against one GPU copying alone on this pool "
+                                    "(profiles/r2_host_path_8gpu.txt: with 8 ranks 12.0 / 18.8 GB/s per GPU, 123.5 GB/s "
+                                    "in total, whichever GPUs are paired): the multi-GPU end-to-end step is bounded "
+                                    "by the host side of the box that all GPUs share, not by the solver"}},
                 "roofline": {"kernel": kname, "bound": "fp64", "achieved": ach, "peak": fp64_peak,
                              "unit": "TFLOP/s", "frac": (ach / fp64_peak) if fp64_peak else None,
                              "achieved_incl_sincos": ach_sc,
