@@ -1,6 +1,7 @@
 """CPU-only tests: C-ABI surface, data-contract layer, scenario generator, sharding math."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -187,3 +188,39 @@ def test_bus_auto_sorting(tmp_path):
     Y_sorted = O.build_admittance_matrices(mk(b2, l2))
     Y_orig = O.build_admittance_matrices(mk(buses, lines))
     assert np.abs(Y_sorted - Y_orig[:, order][:, :, order]).max() <= 1e-12 * np.abs(Y_orig).max()
+
+
+def test_committed_bench_lines_keep_the_driver_contract():
+    """The bench lines kept under profiles/ (GPU arm and reference arm of the final binary) carry every key
+    of the driver contract; the GPU arm's traffic figure was captured from the sources it was run with."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ours = json.loads(open(os.path.join(root, "profiles", "r2_bench_e_1gpu.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in ours, k
+    assert ours["warmup"] >= 3 and ours["dtype"] == "f64" and ours["gpu_launches"] > 0
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(ours["e2e"])
+    assert ours["e2e"]["h2d_bytes_per_step"] > 0 and ours["e2e"]["d2h_bytes_per_step"] > 0
+    assert ours["e2e"]["value"] < ours["value"]
+    rf = ours["roofline"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(rf)
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert rf["traffic_provenance"]["stale"] is False
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(ours["cpu_baseline"])
+    assert all(ours["parity"]["gpu_within_floor"].values())
+    ref = json.loads(open(os.path.join(root, "profiles", "r2_bench_reference_arm.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == ours["metric"] and ref["unit"] == ours["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] in ("port", "reference")
+
+
+def test_committed_ncu_summary_was_taken_from_the_current_sources():
+    """profiles/r2_ncu_kernels.csv (the source of roofline.traffic) records the hash of the CUDA sources it was
+    captured from: it must be the hash of the sources in this tree (bench.py marks the figure stale otherwise)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    first = open(bench.NCU_CSV).readline()
+    assert first.startswith("#") and ("src_hash=" + bench.source_hash()) in first, first
+    traffic, prov = bench.ncu_traffic("harm_hw_kernel")
+    assert prov["stale"] is False and traffic and 5e7 < traffic < 5e8
