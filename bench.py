@@ -807,7 +807,7 @@ def run_ours(a):
                             "what": "rate of the slowest rank's D2H copy of its result slab while all ranks copy at "
                                     "once (measured in this run) against one GPU copying alone on this pool "
                                     "(profiles/r2_host_path_8gpu.txt: with 8 ranks 12.0 / 18.8 GB/s per GPU, 123.5 GB/s "
-                                    "in total, whichever GPUs are paired): the multi-GPU end-to-end step is bounded "
+                                    "in total): the multi-GPU end-to-end step is bounded "
                                     "by the host side of the box that all GPUs share, not by the solver"}},
                 "roofline": {"kernel": kname, "bound": "fp64", "achieved": ach, "peak": fp64_peak,
                              "unit": "TFLOP/s", "frac": (ach / fp64_peak) if fp64_peak else None,
